@@ -1,0 +1,167 @@
+"""ctypes binding of libevk.so (the C ABI declared in include/evk.h).
+
+There is NO CPU fallback: if the shared library is missing or the device is not a B200-class
+(sm_100) GPU, every compute entry point raises.  Build with ``python -c "import
+__graft_entry__ as g; g.build()"`` or ``make -C event_utils_b200/csrc``.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libevk.so")
+
+# flags (mirror include/evk.h)
+ACCUMULATE = 0x1
+BILINEAR = 0x2
+CLIP = 0x4
+VARIANT_AUTO = 0 << 8
+VARIANT_GLOBAL_RED = 1 << 8
+VARIANT_VECTOR_RED = 2 << 8
+VARIANT_SMEM_TILE = 3 << 8
+VARIANT_WARP_AGG = 4 << 8
+CMAX_WANT_GRAD = 0x10
+CMAX_ABS_POLARITY = 0x20
+CMAX_NO_CHANNEL_MIX = 0x40
+
+_lib = None
+_lock = threading.Lock()
+
+
+class EvkError(RuntimeError):
+    pass
+
+
+def _declare(L):
+    c = ctypes
+    vp, i64, f32, f64, ci, cu, sz = c.c_void_p, c.c_int64, c.c_float, c.c_double, c.c_int, c.c_uint, c.c_size_t
+    L.evk_version.restype = ci
+    L.evk_last_error.restype = c.c_char_p
+    L.evk_device_check.restype = ci
+    L.evk_voxel_workspace_bytes.restype = sz
+    L.evk_voxel_workspace_bytes.argtypes = [ci, ci, ci, cu]
+    L.evk_voxel_f32.restype = ci
+    L.evk_voxel_f32.argtypes = [vp, vp, vp, vp, i64, f32, f32, ci, ci, ci, cu, vp, vp, sz, vp, vp]
+    L.evk_voxel_aos_f32.restype = ci
+    L.evk_voxel_aos_f32.argtypes = [vp, i64, f32, f32, ci, ci, ci, cu, vp, vp, sz, vp, vp]
+    L.evk_voxel_windows_f32.restype = ci
+    L.evk_voxel_windows_f32.argtypes = [vp, vp, vp, vp, vp, ci, i64, ci, ci, ci, cu, vp, vp, vp]
+    L.evk_image_workspace_bytes.restype = sz
+    L.evk_image_workspace_bytes.argtypes = [ci, ci, cu]
+    L.evk_image_f32.restype = ci
+    L.evk_image_f32.argtypes = [vp, vp, vp, i64, ci, ci, f32, f32, cu, f32, vp, vp, sz, vp, vp]
+    L.evk_count_u32.restype = ci
+    L.evk_count_u32.argtypes = [vp, vp, i64, ci, ci, f32, f32, cu, vp, vp, vp]
+    L.evk_splat_idx_f32.restype = ci
+    L.evk_splat_idx_f32.argtypes = [vp, vp, vp, vp, vp, i64, ci, ci, vp, vp, vp]
+    L.evk_splat_drv_idx_f32.restype = ci
+    L.evk_splat_drv_idx_f32.argtypes = [vp, vp, vp, vp, vp, vp, ci, i64, ci, ci, vp, vp, vp]
+    L.evk_image_drv_f32.restype = ci
+    L.evk_image_drv_f32.argtypes = [vp, vp, vp, vp, vp, ci, i64, ci, ci, f32, f32, cu, vp, vp, vp, vp]
+    L.evk_gather_bilinear_f64.restype = ci
+    L.evk_gather_bilinear_f64.argtypes = [vp, vp, i64, vp, ci, ci, vp, vp, vp]
+    L.evk_warp_flow_f32.restype = ci
+    L.evk_warp_flow_f32.argtypes = [vp, vp, vp, i64, vp, ci, ci, f32, vp, vp, vp]
+    L.evk_cmax_workspace_bytes.restype = sz
+    L.evk_cmax_workspace_bytes.argtypes = [ci, ci]
+    L.evk_cmax_linvel_variance_f64.restype = ci
+    L.evk_cmax_linvel_variance_f64.argtypes = [vp, vp, vp, vp, i64, f64, f64, f64, f64, ci, ci, ci, ci, f64, cu,
+                                               vp, vp, vp, vp, sz, vp]
+    L.evk_cmax_linvel_variance_f32.restype = ci
+    L.evk_cmax_linvel_variance_f32.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, ci, ci, ci, ci, f64, cu,
+                                               vp, vp, vp, vp, sz, vp]
+    L.evk_variance_objective_f32.restype = ci
+    L.evk_variance_objective_f32.argtypes = [vp, vp, ci, ci, f64, cu, vp, vp, sz, vp]
+    L.evk_cmax_flow_variance_f32.restype = ci
+    L.evk_cmax_flow_variance_f32.argtypes = [vp, vp, vp, vp, i64, vp, f32, ci, ci, f64, cu, vp, vp, vp, sz, vp]
+    L.evk_pipeline_create.restype = ci
+    L.evk_pipeline_create.argtypes = [c.POINTER(vp), i64]
+    L.evk_pipeline_destroy.restype = None
+    L.evk_pipeline_destroy.argtypes = [vp]
+    L.evk_voxel_host_f32.restype = ci
+    L.evk_voxel_host_f32.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, ci, ci, ci, cu, vp, c.POINTER(c.c_ulonglong)]
+
+
+def load():
+    """Load libevk.so (no GPU needed for this step) and declare the prototypes."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(SO_PATH):
+                raise EvkError("libevk.so not found at %s -- build it (make -C event_utils_b200/csrc); "
+                               "there is no CPU fallback" % SO_PATH)
+            L = ctypes.CDLL(SO_PATH)
+            _declare(L)
+            _lib = L
+    return _lib
+
+
+_device_ok = {}
+
+
+def lib():
+    """Library handle for compute calls: requires a CUDA device of compute capability 10.x."""
+    L = load()
+    if not torch.cuda.is_available():
+        raise EvkError("event_utils_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.cuda.current_device()
+    if dev not in _device_ok:
+        torch.cuda.init()
+        torch.empty(1, device="cuda")  # make sure the primary context exists
+        check(L.evk_device_check())
+        _device_ok[dev] = True
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().evk_last_error()
+        raise EvkError("libevk error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+_scratch = {}
+
+
+def scratch(key, nbytes, device):
+    """A cached 256-byte aligned device scratch buffer (uint8) of at least nbytes."""
+    k = (key, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _scratch.get(k)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _scratch[k] = buf
+    return buf
+
+
+def oob_counter(device):
+    k = ("oob", device.index if device.index is not None else torch.cuda.current_device())
+    buf = _scratch.get(k)
+    if buf is None:
+        buf = torch.zeros(1, dtype=torch.int64, device=device)
+        _scratch[k] = buf
+    else:
+        buf.zero_()
+    return buf
+
+
+_pipelines = {}
+
+
+def pipeline(chunk_events=4 << 20):
+    dev = torch.cuda.current_device()
+    p = _pipelines.get(dev)
+    if p is None:
+        h = ctypes.c_void_p()
+        check(lib().evk_pipeline_create(ctypes.byref(h), chunk_events))
+        p = h
+        _pipelines[dev] = p
+    return p

@@ -1,0 +1,295 @@
+"""Contrast-maximisation objectives -- drop-in for the hot-path part of the reference's
+lib/contrast_max/objectives.py: `objective_function` (base class, :10-140), `get_iwe`
+(:165-199) and `variance_objective` (:202-264).
+
+The reference rebuilds everything from the raw host arrays for every f and every f' call
+(~25 O(N) numpy/torch passes + 4 or 12 scatters).  Here:
+  * the event arrays are uploaded to the GPU once and cached (the optimiser hands over the same
+    numpy arrays at every iteration, events_cmax.py:341);
+  * warp + bounds mask + IWE + derivative images + blur + variance + gradient is ONE fused
+    evaluation (csrc/evk_cmax.cu) that returns f and g together;
+  * (params -> f, g) is memoised, so scipy's separate f / f' calls at the same point cost one
+    launch.
+Objects keep the reference's attributes and calling conventions (positional `args=` form,
+keyword form, and the precomputed `iwe=` / `d_iwe=` form).
+"""
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..representations import _events as E
+from ..representations.image import events_to_image_drv, image_to_event_weights
+from ..util.event_util import events_bounds_mask
+
+SENSOR_SIZE = (180, 240)  # the reference never forwards sensor_size to events_to_image_drv
+                          # (objectives.py:191-192 -> image.py:163): the IWE is always 181x241
+
+
+# ---------------------------------------------------------------------------------------------
+# device-side event cache
+# ---------------------------------------------------------------------------------------------
+class _DeviceEvents:
+    __slots__ = ("key", "x", "y", "t", "p", "n", "t_last", "mode")
+
+
+_event_cache = []          # most recent first, at most _CACHE_SLOTS entries
+_CACHE_SLOTS = 2
+precision = "f64"          # "f64": parity mode (events kept as f64, 32 B/event)
+                           # "f32": fast mode (x, y, t - t_last, p as f32, 16 B/event)
+
+
+def _fingerprint(a):
+    """Cheap content check so that in-place edits of a cached array are noticed: pointer,
+    length and a strided sample of 64 values."""
+    n = a.shape[0]
+    step = max(1, n // 64)
+    return (a.__array_interface__["data"][0], n, a.dtype.str, a[::step][:64].tobytes())
+
+
+def _device_events(xs, ys, ts, ps):
+    xs, ys, ts, ps = (np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1)) for a in (xs, ys, ts, ps))
+    key = (precision,) + tuple(_fingerprint(a) for a in (xs, ys, ts, ps))
+    for i, ev in enumerate(_event_cache):
+        if ev.key == key:
+            if i:
+                _event_cache.insert(0, _event_cache.pop(i))
+            return ev
+    dev = E.compute_device()
+    ev = _DeviceEvents()
+    ev.key, ev.n, ev.mode = key, xs.shape[0], precision
+    ev.t_last = float(ts[-1]) if ts.shape[0] else 0.0
+    with torch.cuda.device(dev):
+        if precision == "f64":
+            ev.x, ev.y, ev.t, ev.p = (torch.from_numpy(a).to(dev) for a in (xs, ys, ts, ps))
+        else:
+            ev.x, ev.y, ev.p = (torch.from_numpy(a).to(dev).float() for a in (xs, ys, ps))
+            ev.t = torch.from_numpy(ts - ev.t_last).to(dev).float()  # relative in f64, then f32
+    _event_cache.insert(0, ev)
+    del _event_cache[_CACHE_SLOTS:]
+    return ev
+
+
+def clear_cache():
+    del _event_cache[:]
+
+
+def _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, want_grad, use_polarity,
+                  first=0, last=None, p_scale=1.0, want_images=False, channel_mix=True):
+    """One fused evaluation on events [first:last) of the cached device copy.
+    Returns (result[8] as numpy f64, iwe or None, d_iwe or None)."""
+    L = _lib.lib()
+    ev = _device_events(xs, ys, ts, ps)
+    n_all = ev.n
+    last = n_all if last is None else (last if last >= 0 else n_all + last)
+    first = first if first >= 0 else n_all + first
+    first, last = max(0, min(first, n_all)), max(0, min(last, n_all))
+    n = max(0, last - first)
+    if n == 0:
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")
+    Hs, Ws = SENSOR_SIZE
+    dev = ev.x.device
+    with torch.cuda.device(dev):
+        ws_bytes = L.evk_cmax_workspace_bytes(Hs, Ws)
+        ws = _lib.scratch("cmax_ws", ws_bytes, dev)
+        result = torch.empty(8, dtype=torch.float64, device=dev)
+        iwe = torch.empty((Hs + 1, Ws + 1), dtype=torch.float32, device=dev) if want_images else None
+        d_iwe = torch.empty((2, Hs + 1, Ws + 1), dtype=torch.float32, device=dev) if (want_images and want_grad) else None
+        flags = (_lib.CMAX_WANT_GRAD if want_grad else 0) | (0 if use_polarity else _lib.CMAX_ABS_POLARITY) \
+            | (0 if channel_mix else _lib.CMAX_NO_CHANNEL_MIX)
+        sigma = float(blur_sigma) if blur_sigma is not None else 0.0
+        # the reference warps to the LAST timestamp of the (possibly sliced) event set (objectives.py:186)
+        if ev.mode == "f64":
+            t_ref = float(ev.t[last - 1].item()) if last != n_all else ev.t_last
+            off = first * 8
+            _lib.check(L.evk_cmax_linvel_variance_f64(
+                ev.x.data_ptr() + off, ev.y.data_ptr() + off, ev.t.data_ptr() + off, ev.p.data_ptr() + off, n,
+                float(p_scale), float(params[0]), float(params[1]), t_ref, int(img_size[0]), int(img_size[1]),
+                Hs, Ws, sigma, flags, _lib.ptr(result), _lib.ptr(iwe), _lib.ptr(d_iwe), _lib.ptr(ws), ws.numel(),
+                _lib.stream()))
+        else:
+            if last != n_all:
+                raise NotImplementedError("f32 fast mode stores t relative to the last event; "
+                                          "slicing the tail (adaptive_lifespan) needs precision='f64'")
+            off = first * 4
+            _lib.check(L.evk_cmax_linvel_variance_f32(
+                ev.x.data_ptr() + off, ev.y.data_ptr() + off, ev.t.data_ptr() + off, ev.p.data_ptr() + off, n,
+                float(p_scale), float(params[0]), float(params[1]), int(img_size[0]), int(img_size[1]),
+                Hs, Ws, sigma, flags, _lib.ptr(result), _lib.ptr(iwe), _lib.ptr(d_iwe), _lib.ptr(ws), ws.numel(),
+                _lib.stream()))
+        res = result.cpu().numpy()
+        if res[4] != 0:
+            raise IndexError("%d warped events index outside the IWE canvas %s" % (int(res[4]), (Hs + 1, Ws + 1)))
+        return res, (iwe.cpu().numpy() if iwe is not None else None), (d_iwe.cpu().numpy() if d_iwe is not None else None)
+
+
+def _objective_of_images(iwe, d_iwe, blur_sigma, want_grad):
+    """variance objective (+ gradient) of precomputed images, on the GPU (evk_variance_objective_f32)."""
+    L = _lib.lib()
+    dev = E.compute_device()
+    iwe = np.ascontiguousarray(iwe, dtype=np.float32)
+    with torch.cuda.device(dev):
+        a = torch.from_numpy(iwe).to(dev)
+        d = torch.from_numpy(np.ascontiguousarray(d_iwe, dtype=np.float32)).to(dev) if d_iwe is not None else None
+        ws = _lib.scratch("cmax_ws", L.evk_cmax_workspace_bytes(iwe.shape[0] - 1, iwe.shape[1] - 1), dev)
+        result = torch.empty(8, dtype=torch.float64, device=dev)
+        flags = _lib.CMAX_WANT_GRAD if (want_grad and d is not None) else 0
+        _lib.check(L.evk_variance_objective_f32(_lib.ptr(a), _lib.ptr(d), iwe.shape[0], iwe.shape[1],
+                                                float(blur_sigma), flags, _lib.ptr(result), _lib.ptr(ws),
+                                                ws.numel(), _lib.stream()))
+        return result.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# reference API
+# ---------------------------------------------------------------------------------------------
+class objective_function(ABC):
+    """
+    Parent class of the contrast-maximisation objectives (reference objectives.py:10-140):
+    same constructor arguments, attributes and housekeeping methods.
+    """
+    def __init__(self, name="template", use_polarity=True,
+            has_derivative=True, default_blur=1.0, adaptive_lifespan=False,
+            pixel_crossings=5, minimum_events=10000):
+        self.name = name
+        self.use_polarity = use_polarity
+        self.has_derivative = has_derivative
+        self.default_blur = default_blur
+        self.adaptive_lifespan = adaptive_lifespan
+        self.pixel_crossings = pixel_crossings
+        self.minimum_events = minimum_events
+
+        self.recompute_lifespan = True
+        self.lifespan = 0.5
+        self.s_idx = 0
+        self.num_events = None
+        self._memo = None   # (key, f, g) of the last fused evaluation
+        super().__init__()
+
+    @abstractmethod
+    def evaluate_function(self, params=None, xs=None, ys=None, ts=None, ps=None,
+            warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None):
+        pass
+
+    @abstractmethod
+    def evaluate_gradient(self, params=None, xs=None, ys=None, ts=None, ps=None,
+            warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None, d_iwe=None):
+        pass
+
+    def iter_update(self, params, pixel_crossings=None):
+        """Optimiser callback (objectives.py:113-127): new lifespan from the current speed."""
+        pixel_crossings = self.pixel_crossings if pixel_crossings is None else pixel_crossings
+        magnitude = np.linalg.norm(params)
+        if magnitude == 0:
+            dt = 5
+        else:
+            dt = pixel_crossings / magnitude
+        self.lifespan = dt
+        self.recompute_lifespan = True
+
+    def update_lifespan(self, ts):
+        """New start index of the events used when adaptive_lifespan is on (objectives.py:129-140)."""
+        if self.adaptive_lifespan:
+            self.s_idx = np.searchsorted(ts, ts[-1] - self.lifespan)
+            self.s_idx = len(ts) - self.minimum_events if len(ts) - self.s_idx < self.minimum_events else self.s_idx
+        if self.num_events is None:
+            self.num_events = len(ts) - self.s_idx
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            setattr(new, k, None if k == "_memo" else copy.deepcopy(v, memo))
+        return new
+
+
+def get_iwe(params, xs, ys, ts, ps, warpfunc, img_size, compute_gradient=False,
+        use_polarity=True, return_events=False, return_per_event_contrast=False):
+    """
+    Image of warped events (and dIWE/dparams) for a parameter vector; drop-in for
+    objectives.py:165-199.  numpy in, numpy float32 (181,241) / (dims,181,241) out.
+    @returns tuple: iwe, d_iwe (or None) [, (xs_warped, ys_warped)] [, per-event contrast]
+    """
+    fused = getattr(warpfunc, "fused_kind", None) == "linvel"
+    if fused and not return_events and not return_per_event_contrast:
+        _, iwe, d_iwe = _fused_linvel(params, xs, ys, ts, ps, img_size, 0.0, compute_gradient, use_polarity,
+                                      want_images=True)
+        return (iwe, d_iwe)
+    # generic warp objects (and the two debugging outputs): host warp + mask as in the
+    # reference, image formation on the GPU
+    xs, ys, ts, ps = (np.asarray(a) for a in (xs, ys, ts, ps))
+    if not use_polarity:
+        ps = np.abs(ps)
+    xw, yw, jx, jy = warpfunc.warp(xs, ys, ts, ps, ts[-1], params, compute_grad=compute_gradient)
+    mask = events_bounds_mask(xw, yw, 0, img_size[1], 0, img_size[0])
+    xw, yw, ps = xw * mask, yw * mask, ps * mask
+    if compute_gradient:
+        jx, jy = jx * mask, jy * mask
+    iwe, iwe_drv = events_to_image_drv(xw, yw, ps, jx, jy, interpolation='bilinear', compute_gradient=compute_gradient)
+    returnval = [iwe, iwe_drv]
+    if return_events:
+        returnval.append((xw, yw))
+    if return_per_event_contrast:
+        returnval.append(image_to_event_weights(xw, yw, iwe))
+    return tuple(returnval)
+
+
+class variance_objective(objective_function):
+    """
+    Variance objective (Gallego & Scaramuzza, RAL'17); drop-in for objectives.py:202-264.
+        f(params)   = -var( G_sigma * IWE )
+        f'(params)_k = -mean( 2 (IWE - mean IWE) * (G_sigma *3d dIWE)_k )
+    Bug-compatible with the reference: the gradient uses the UN-blurred IWE and scipy's 3-D blur
+    of the (2,H,W) derivative stack mixes its two channels (objectives.py:253).
+    """
+    def __init__(self, adaptive_lifespan=False, minimum_events=10000):
+        super().__init__(name="variance", use_polarity=True, has_derivative=True,
+                default_blur=1.0, adaptive_lifespan=adaptive_lifespan, pixel_crossings=5,
+                minimum_events=minimum_events)
+
+    # one fused evaluation returns f and g; remember it for the sibling call at the same point
+    def _evaluate(self, params, xs, ys, ts, ps, warpfunc, img_size, blur_sigma):
+        first, last, scale = 0, None, 1.0
+        if self.adaptive_lifespan:
+            if self.recompute_lifespan:
+                self.update_lifespan(ts)
+                self.recompute_lifespan = False
+            first, last, scale = int(self.s_idx), -1, 100.0   # xs[s_idx:-1], ps*100 (objectives.py:224-225)
+        blur_sigma = self.default_blur if blur_sigma is None else blur_sigma
+        key = (tuple(float(v) for v in params), id(xs), id(ys), id(ts), id(ps), len(xs), tuple(img_size),
+               float(blur_sigma), first, last, scale, self.use_polarity, precision)
+        if self._memo is not None and self._memo[0] == key:
+            return self._memo[1], self._memo[2]
+        if getattr(warpfunc, "fused_kind", None) == "linvel":
+            res, _, _ = _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, True, self.use_polarity,
+                                      first=first, last=last, p_scale=scale)
+        else:
+            sl = slice(first, last)
+            iwe, d_iwe = get_iwe(params, xs[sl], ys[sl], ts[sl], ps[sl] * scale, warpfunc, img_size,
+                                 use_polarity=self.use_polarity, compute_gradient=True)
+            res = _objective_of_images(iwe, d_iwe, blur_sigma, True)
+        f, g = float(res[0]), np.array([res[1], res[2]])
+        self._memo = (key, f, g)
+        return f, g
+
+    def evaluate_function(self, params=None, xs=None, ys=None, ts=None, ps=None,
+            warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None):
+        """-var(blurred IWE) at `params` (or of a precomputed `iwe`)."""
+        if iwe is not None:
+            blur_sigma = self.default_blur if blur_sigma is None else blur_sigma
+            return float(_objective_of_images(iwe, None, blur_sigma, False)[0])
+        f, _ = self._evaluate(params, xs, ys, ts, ps, warpfunc, img_size, blur_sigma)
+        return f
+
+    def evaluate_gradient(self, params=None, xs=None, ys=None, ts=None, ps=None,
+            warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None, d_iwe=None):
+        """Analytic gradient of the objective wrt the warp parameters (np.ndarray[dims])."""
+        if iwe is not None and d_iwe is not None:
+            blur_sigma = self.default_blur if blur_sigma is None else blur_sigma
+            res = _objective_of_images(iwe, d_iwe, blur_sigma, True)
+            return np.array([res[1], res[2]])
+        _, g = self._evaluate(params, xs, ys, ts, ps, warpfunc, img_size, blur_sigma)
+        return g.copy()

@@ -1,0 +1,474 @@
+// evk_cmax.cu -- fused contrast-maximisation evaluation on B200:
+//   warp -> bounds mask -> bilinear IWE (+ Jacobian-weighted derivative images) -> Gaussian
+//   blur -> variance objective and its analytic gradient, one pass over the events.
+//
+// Semantics (reference):
+//   linvel_warp.warp              lib/contrast_max/warps.py:51-61        (f64)
+//   events_bounds_mask            lib/util/event_util.py:26-27           (f64)
+//   get_iwe                       lib/contrast_max/objectives.py:184-192
+//   events_to_image_drv           lib/representations/image.py:179-217   (f64 -> f32 cast, splat)
+//   interpolate_to_derivative_img lib/representations/image.py:131-135
+//   variance_objective            lib/contrast_max/objectives.py:231-236, 251-264
+//   warp_events_flow_torch + IWE  lib/transforms/optic_flow.py:37-44, lib/visualization/draw_flow.py:18-21
+//
+// B200 design:
+//   * ONE pass over the events.  The IWE and both derivative images are interleaved per pixel
+//     as float4 {I, D0, D1, 0}; each of the 4 bilinear taps of an event is ONE
+//     red.global.add.v4.f32 (REDG.E.ADD.F32x4) that updates all three images at once, so the
+//     gradient costs no extra reduction traffic.  The accumulator (181*241*16 B = 698 KB per
+//     replica, R replicas to spread same-address serialisation) never leaves L2.
+//   * The reference blurs both derivative images and multiplies by the un-blurred IWE.  The
+//     reflect-boundary Gaussian is self-adjoint, so  sum(2(I-mu) * G(D_k)) == sum(G(2(I-mu)) * D_k)
+//     and G(2(I-mu)) = 2(G(I)-mu): ONE blur of ONE image (which f needs anyway) serves f and g.
+//   * scipy blurs the (2,H,W) derivative stack along its length-2 axis as well
+//     (objectives.py:253), mixing the two gradient components by [[a,b],[b,a]]; applied to the
+//     two scalars at the end (host supplies a,b).
+#include <math.h>
+
+#include "evk_common.cuh"
+
+namespace evk {
+
+constexpr int kMaxRadius = 64;
+constexpr int kMaxReplicas = 8;
+
+struct BlurTaps {
+    int r;
+    double w[kMaxRadius + 1];  // w[k] = weight at distance k (symmetric)
+};
+
+struct CmaxArgs {
+    const void *x, *y, *t, *p;
+    int64_t n;
+    double vx, vy, t_ref;  // linvel
+    double p_scale;        // polarity multiplier (objectives.py:225 uses 100)
+    const float *flow;     // dense flow [2][Hs][Ws]
+    float flow_t0;
+    int Hm, Wm;  // bounds-mask size (img_size)
+    int Hc, Wc;  // canvas = sensor + 1
+    int abs_polarity;
+    int replicas;
+    float *acc;  // [R][Hc*Wc][4]
+    unsigned long long *oob;
+};
+
+enum { WARP_LINVEL_F64 = 0, WARP_LINVEL_F32 = 1, WARP_FLOW_F32 = 2 };
+
+// bilinear splat of weight w (and derivative weight a) at (xf, yf) on the canvas:
+// image.py:199-207 (IWE) and :131-135 (derivative images) with w1 = [a;0], w2 = [0;a].
+template <bool GRAD>
+__device__ __forceinline__ void splat(const CmaxArgs &A, float *acc, float xf, float yf, float w, float a,
+                                      bool clip, unsigned &oob)
+{
+    const float clipx = (float)(A.Wc - 1), clipy = (float)(A.Hc - 1);
+    float m2 = 1.0f;
+    if (clip) m2 = (xf >= clipx ? 0.0f : 1.0f) * (yf >= clipy ? 0.0f : 1.0f);
+    const float pxf = floorf(xf), pyf = floorf(yf);
+    const float dx = __fsub_rn(xf, pxf), dy = __fsub_rn(yf, pyf);
+    int upx, upy, x0, x1, y0, y1;
+    if (!trunc_checked(__fmul_rn(pxf, m2), upx) || !trunc_checked(__fmul_rn(pyf, m2), upy) ||
+        !wrap_int_index(upx, A.Wc, x0) || !wrap_int_index(upx + 1, A.Wc, x1) ||
+        !wrap_int_index(upy, A.Hc, y0) || !wrap_int_index(upy + 1, A.Hc, y1)) { ++oob; return; }
+    const float wm = __fmul_rn(w, m2);
+    const float am = GRAD ? __fmul_rn(a, wm) : 0.0f;  // jacobian * masked_ps (image.py:211-212)
+    if (wm == 0.0f && am == 0.0f) return;
+    const float ox = __fsub_rn(1.0f, dx), oy = __fsub_rn(1.0f, dy);
+    const float wl = __fmul_rn(wm, ox), wr = __fmul_rn(wm, dx);
+    float4 v00, v01, v10, v11;
+    v00.x = __fmul_rn(wl, oy); v01.x = __fmul_rn(wr, oy); v10.x = __fmul_rn(wl, dy); v11.x = __fmul_rn(wr, dy);
+    if (GRAD) {
+        v00.y = __fmul_rn(am, -oy); v01.y = __fmul_rn(am, oy); v10.y = __fmul_rn(am, -dy); v11.y = __fmul_rn(am, dy);
+        v00.z = __fmul_rn(am, -ox); v01.z = __fmul_rn(am, -dx); v10.z = __fmul_rn(am, ox); v11.z = __fmul_rn(am, dx);
+    } else {
+        v00.y = v01.y = v10.y = v11.y = 0.0f;
+        v00.z = v01.z = v10.z = v11.z = 0.0f;
+    }
+    v00.w = v01.w = v10.w = v11.w = 0.0f;
+    red_add4(acc + ((int64_t)y0 * A.Wc + x0) * 4, v00);
+    red_add4(acc + ((int64_t)y0 * A.Wc + x1) * 4, v01);
+    red_add4(acc + ((int64_t)y1 * A.Wc + x0) * 4, v10);
+    red_add4(acc + ((int64_t)y1 * A.Wc + x1) * 4, v11);
+}
+
+__device__ __forceinline__ float flow_tap(const float *f, int H, int W, int yy, int xx)
+{
+    return ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? __ldg(f + (int64_t)yy * W + xx) : 0.0f;
+}
+
+template <int WARP, bool GRAD>
+__device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, int64_t i, unsigned &oob)
+{
+    if (WARP == WARP_LINVEL_F64) {
+        const double x = ld_stream((const double *)A.x + i), y = ld_stream((const double *)A.y + i);
+        const double t = ld_stream((const double *)A.t + i);
+        double p = ld_stream((const double *)A.p + i);
+        if (A.p_scale != 1.0) p = __dmul_rn(p, A.p_scale);
+        if (A.abs_polarity) p = fabs(p);
+        const double d = __dsub_rn(t, A.t_ref);
+        const double xw = __dsub_rn(x, __dmul_rn(d, A.vx));  // warps.py:52-54
+        const double yw = __dsub_rn(y, __dmul_rn(d, A.vy));
+        // event_util.py:26-27: keep iff 0 < x' <= Wm and 0 < y' <= Hm (NaN compares false -> kept)
+        const bool keep = !(xw <= 0.0 || xw > (double)A.Wm) && !(yw <= 0.0 || yw > (double)A.Hm);
+        if (!keep) return;  // x,y,p,j all multiplied by 0: only exact zeros are added at (0,0)..(1,1)
+        splat<GRAD>(A, acc, (float)xw, (float)yw, (float)p, (float)(-d), true, oob);  // image.py:180-183 casts
+    } else if (WARP == WARP_LINVEL_F32) {
+        const float x = ld_stream((const float *)A.x + i), y = ld_stream((const float *)A.y + i);
+        const float d = ld_stream((const float *)A.t + i);  // already t - t_ref
+        float p = ld_stream((const float *)A.p + i);
+        if (A.p_scale != 1.0) p = __fmul_rn(p, (float)A.p_scale);
+        if (A.abs_polarity) p = fabsf(p);
+        const float vx = (float)A.vx, vy = (float)A.vy;
+        const float xw = __fsub_rn(x, __fmul_rn(d, vx)), yw = __fsub_rn(y, __fmul_rn(d, vy));
+        const bool keep = !(xw <= 0.0f || xw > (float)A.Wm) && !(yw <= 0.0f || yw > (float)A.Hm);
+        if (!keep) return;
+        splat<GRAD>(A, acc, xw, yw, p, -d, true, oob);
+    } else {
+        // optic_flow.py:37-44 then events_to_image_torch(..., interpolation='bilinear') defaults
+        const float xe = ld_stream((const float *)A.x + i), ye = ld_stream((const float *)A.y + i);
+        const float te = ld_stream((const float *)A.t + i);
+        float p = ld_stream((const float *)A.p + i);
+        if (A.abs_polarity) p = fabsf(p);
+        const int H = A.Hc - 1, W = A.Wc - 1;
+        const float *fu = A.flow, *fv = A.flow + (int64_t)H * W;
+        const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+        const float gx = __fsub_rn(__fmul_rn(__fdiv_rn(xe, wm1), 2.0f), 1.0f);
+        const float gy = __fsub_rn(__fmul_rn(__fdiv_rn(ye, hm1), 2.0f), 1.0f);
+        const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), wm1);
+        const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), hm1);
+        float u = 0.0f, v = 0.0f;
+        if (fabsf(ix) < 1.0e9f && fabsf(iy) < 1.0e9f) {
+            const float fx = floorf(ix), fy = floorf(iy);
+            const int x0 = (int)fx, y0 = (int)fy;
+            const float xs = fx + 1.0f, ys = fy + 1.0f;
+            const float nw = __fmul_rn(__fsub_rn(xs, ix), __fsub_rn(ys, iy));
+            const float ne = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(ys, iy));
+            const float sw = __fmul_rn(__fsub_rn(xs, ix), __fsub_rn(iy, fy));
+            const float se = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(iy, fy));
+            u = __fadd_rn(u, __fmul_rn(flow_tap(fu, H, W, y0, x0), nw));         v = __fadd_rn(v, __fmul_rn(flow_tap(fv, H, W, y0, x0), nw));
+            u = __fadd_rn(u, __fmul_rn(flow_tap(fu, H, W, y0, x0 + 1), ne));     v = __fadd_rn(v, __fmul_rn(flow_tap(fv, H, W, y0, x0 + 1), ne));
+            u = __fadd_rn(u, __fmul_rn(flow_tap(fu, H, W, y0 + 1, x0), sw));     v = __fadd_rn(v, __fmul_rn(flow_tap(fv, H, W, y0 + 1, x0), sw));
+            u = __fadd_rn(u, __fmul_rn(flow_tap(fu, H, W, y0 + 1, x0 + 1), se)); v = __fadd_rn(v, __fmul_rn(flow_tap(fv, H, W, y0 + 1, x0 + 1), se));
+        }
+        const float d = __fsub_rn(te, A.flow_t0);
+        splat<false>(A, acc, __fadd_rn(xe, __fmul_rn(u, d)), __fadd_rn(ye, __fmul_rn(v, d)), p, 0.0f, true, oob);
+    }
+}
+
+template <int WARP, bool GRAD>
+__global__ void __launch_bounds__(256) cmax_scatter_kernel(const CmaxArgs A)
+{
+    unsigned oob = 0;
+    float *acc = A.acc + (int64_t)(blockIdx.x % A.replicas) * A.Hc * A.Wc * 4;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + stride < A.n; i += 2 * stride) {
+        cmax_event<WARP, GRAD>(A, acc, i, oob);
+        cmax_event<WARP, GRAD>(A, acc, i + stride, oob);
+    }
+    if (i < A.n) cmax_event<WARP, GRAD>(A, acc, i, oob);
+    flush_oob(A.oob, oob);
+}
+
+// ---- image-space tail (43.6 K pixels; negligible next to the event pass) ------------------
+// sums[]: 0 sum(I)  1 sum(G)  2 sum(G^2)  3 sum(G*D0)  4 sum(G*D1)  5 sum(D0)  6 sum(D1)
+// block-wide sum of v (all 256 threads participate), one atomicAdd(double) per block
+__device__ __forceinline__ void block_add(double v, double *dst)
+{
+    __shared__ double part[8];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();  // protect `part` against the previous call's readers
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += part[w];
+        atomicAdd(dst, s);
+    }
+}
+
+__global__ void __launch_bounds__(256) cmax_gather_kernel(const float *__restrict__ acc, int replicas, int npix,
+                                                          float *__restrict__ I, float *__restrict__ D0,
+                                                          float *__restrict__ D1, float *__restrict__ iwe_out,
+                                                          float *__restrict__ diwe_out, double *sums)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    float a = 0.f, b = 0.f, c = 0.f;
+    if (i < npix) {
+        for (int r = 0; r < replicas; ++r) {
+            const float4 v = reinterpret_cast<const float4 *>(acc)[(int64_t)r * npix + i];
+            a += v.x; b += v.y; c += v.z;
+        }
+        I[i] = a; D0[i] = b; D1[i] = c;
+        if (iwe_out) iwe_out[i] = a;
+        if (diwe_out) { diwe_out[i] = b; diwe_out[npix + i] = c; }
+    }
+    block_add((double)a, sums + 0);
+    block_add((double)b, sums + 5);
+    block_add((double)c, sums + 6);
+}
+
+__device__ __forceinline__ int reflect_idx(int i, int n)
+{
+    if (n == 1) return 0;
+    const int period = 2 * n;
+    i %= period;
+    if (i < 0) i += period;
+    return i < n ? i : period - 1 - i;
+}
+
+// scipy applies axis 0 first and rounds the intermediate to f32
+__global__ void __launch_bounds__(256) cmax_blur_axis0_kernel(const float *__restrict__ I, float *__restrict__ tmp,
+                                                              int Hc, int Wc, const BlurTaps taps)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= Hc * Wc) return;
+    const int y = i / Wc, x = i - y * Wc;
+    double acc = (double)I[i] * taps.w[0];
+    for (int k = 1; k <= taps.r; ++k)
+        acc += ((double)I[reflect_idx(y - k, Hc) * Wc + x] + (double)I[reflect_idx(y + k, Hc) * Wc + x]) * taps.w[k];
+    tmp[i] = (float)acc;
+}
+
+__global__ void __launch_bounds__(256) cmax_blur_axis1_sums_kernel(const float *__restrict__ tmp, const float *__restrict__ I,
+                                                                   const float *__restrict__ D0, const float *__restrict__ D1,
+                                                                   int Hc, int Wc, const BlurTaps taps, int do_blur,
+                                                                   double *sums)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    double g = 0.0, d0 = 0.0, d1 = 0.0;
+    if (i < Hc * Wc) {
+        if (do_blur) {
+            const int y = i / Wc, x = i - y * Wc;
+            const float *row = tmp + y * Wc;
+            double acc = (double)row[x] * taps.w[0];
+            for (int k = 1; k <= taps.r; ++k)
+                acc += ((double)row[reflect_idx(x - k, Wc)] + (double)row[reflect_idx(x + k, Wc)]) * taps.w[k];
+            g = (double)(float)acc;
+        } else {
+            g = (double)I[i];
+        }
+        d0 = (double)D0[i]; d1 = (double)D1[i];
+    }
+    block_add(g, sums + 1);
+    block_add(g * g, sums + 2);
+    block_add(g * d0, sums + 3);
+    block_add(g * d1, sums + 4);
+}
+
+// result[0]=f  [1]=g0  [2]=g1  [3]=sum(IWE)  [4]=oob events  [5]=var  [6],[7] un-mixed 2-D gradient
+__global__ void cmax_final_kernel(const double *sums, const unsigned long long *oob, int npix, double mix_a,
+                                  double mix_b, int want_grad, double *result)
+{
+    const double P = (double)npix;
+    const double mean_g = sums[1] / P;
+    const double var = sums[2] / P - mean_g * mean_g;
+    const double mu = sums[0] / P;
+    // g2d_k = -mean( 2 (G(I) - mu) D_k )   (adjoint form of objectives.py:256-262)
+    const double g0 = -2.0 * (sums[3] - mu * sums[5]) / P;
+    const double g1 = -2.0 * (sums[4] - mu * sums[6]) / P;
+    result[0] = -var;
+    result[1] = want_grad ? (mix_a * g0 + mix_b * g1) : 0.0;
+    result[2] = want_grad ? (mix_b * g0 + mix_a * g1) : 0.0;
+    result[3] = sums[0];
+    result[4] = (double)(*oob);
+    result[5] = var;
+    result[6] = g0;
+    result[7] = g1;
+}
+
+struct CmaxWorkspace {
+    float *acc, *I, *D0, *D1, *tmp;
+    double *sums;               // 8 doubles
+    unsigned long long *oob;    // 1
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t carve(void *base, int Hs, int Ws, CmaxWorkspace *ws)
+{
+    const size_t npix = (size_t)(Hs + 1) * (Ws + 1);
+    size_t off = 0;
+    char *b = static_cast<char *>(base);
+    auto take = [&](size_t bytes) { char *p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
+    float *acc = (float *)take(npix * 4 * sizeof(float) * kMaxReplicas);
+    float *I = (float *)take(npix * sizeof(float));
+    float *D0 = (float *)take(npix * sizeof(float));
+    float *D1 = (float *)take(npix * sizeof(float));
+    float *tmp = (float *)take(npix * sizeof(float));
+    double *sums = (double *)take(8 * sizeof(double));
+    unsigned long long *oob = (unsigned long long *)take(sizeof(unsigned long long));
+    if (ws) { ws->acc = acc; ws->I = I; ws->D0 = D0; ws->D1 = D1; ws->tmp = tmp; ws->sums = sums; ws->oob = oob; }
+    return off;
+}
+
+// channel-mix coefficients of scipy's blur along the length-2 stack axis (reflect):
+// blurring the unit vector [1,0]: index i of the reflected signal equals 0 for i mod 4 in {0,3}.
+static void mix_coeffs(const BlurTaps &t, double *a, double *b)
+{
+    double sa = 0.0, sb = 0.0;
+    for (int k = -t.r; k <= t.r; ++k) {
+        int i = k % 4;
+        if (i < 0) i += 4;
+        const double w = t.w[k < 0 ? -k : k];
+        if (i == 0 || i == 3) sa += w; else sb += w;
+    }
+    *a = sa; *b = sb;
+}
+
+static int make_taps(double sigma, BlurTaps *t)
+{
+    int r = (int)(4.0 * sigma + 0.5);
+    if (r > kMaxRadius) { set_error("evk_cmax: blur sigma %.3f needs radius %d > %d", sigma, r, kMaxRadius); return EVK_E_UNSUPPORTED; }
+    t->r = r;
+    double s = 0.0;
+    for (int k = -r; k <= r; ++k) s += exp(-0.5 / (sigma * sigma) * (double)k * (double)k);
+    for (int k = 0; k <= r; ++k) t->w[k] = exp(-0.5 / (sigma * sigma) * (double)k * (double)k) / s;
+    return EVK_OK;
+}
+
+template <int WARP>
+static int run_cmax(CmaxArgs A, double sigma, unsigned flags, double *result, float *iwe_out, float *diwe_out,
+                    void *workspace, size_t workspace_bytes, cudaStream_t st)
+{
+    const int Hs = A.Hc - 1, Ws = A.Wc - 1;
+    if (A.n < 0 || Hs < 1 || Ws < 1 || !result || !workspace) { set_error("evk_cmax: bad arguments"); return EVK_E_ARG; }
+    if (((uintptr_t)workspace & 255) != 0) { set_error("evk_cmax: workspace must be 256-byte aligned"); return EVK_E_ARG; }
+    CmaxWorkspace ws;
+    const size_t need = carve(workspace, Hs, Ws, &ws);
+    if (workspace_bytes < need) { set_error("evk_cmax: workspace of %zu bytes required, %zu given", need, workspace_bytes); return EVK_E_WORKSPACE; }
+    const int npix = A.Hc * A.Wc;
+    const bool grad = (flags & EVK_CMAX_WANT_GRAD) != 0 && WARP != WARP_FLOW_F32;
+    A.abs_polarity = (flags & EVK_CMAX_ABS_POLARITY) ? 1 : 0;
+    // replicas spread same-address serialisation in L2; small problems do not need them
+    int R = (int)(A.n / (1 << 20));
+    R = R < 1 ? 1 : (R > kMaxReplicas ? kMaxReplicas : R);
+    A.replicas = R;
+    A.acc = ws.acc;
+    A.oob = ws.oob;
+    BlurTaps taps{};
+    double mix_a = 1.0, mix_b = 0.0;
+    const int do_blur = sigma > 0.0;
+    if (do_blur) {
+        int rc = make_taps(sigma, &taps);
+        if (rc) return rc;
+        if (!(flags & EVK_CMAX_NO_CHANNEL_MIX)) mix_coeffs(taps, &mix_a, &mix_b);
+    }
+    EVK_CUDA(cudaMemsetAsync(ws.acc, 0, (size_t)R * npix * 4 * sizeof(float), st));
+    EVK_CUDA(cudaMemsetAsync(ws.sums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.sums), st));  // sums + oob are adjacent
+    if (A.n > 0) {
+        const int grid = grid_for(A.n, 256 * 8, 8);
+        if (grad) cmax_scatter_kernel<WARP, true><<<grid, 256, 0, st>>>(A);
+        else cmax_scatter_kernel<WARP, false><<<grid, 256, 0, st>>>(A);
+    }
+    const int g = (npix + 255) / 256;
+    cmax_gather_kernel<<<g, 256, 0, st>>>(ws.acc, R, npix, ws.I, ws.D0, ws.D1, iwe_out, diwe_out, ws.sums);
+    if (do_blur) cmax_blur_axis0_kernel<<<g, 256, 0, st>>>(ws.I, ws.tmp, A.Hc, A.Wc, taps);
+    cmax_blur_axis1_sums_kernel<<<g, 256, 0, st>>>(ws.tmp, ws.I, ws.D0, ws.D1, A.Hc, A.Wc, taps, do_blur, ws.sums);
+    cmax_final_kernel<<<1, 1, 0, st>>>(ws.sums, ws.oob, npix, mix_a, mix_b, grad ? 1 : 0, result);
+    EVK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+// planar iwe / diwe -> the interleaved single-replica accumulator, so that the precomputed-image
+// entry point shares the whole image-space tail
+__global__ void __launch_bounds__(256) cmax_pack_kernel(const float *__restrict__ iwe, const float *__restrict__ diwe,
+                                                        int npix, float *__restrict__ acc)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= npix) return;
+    float4 v;
+    v.x = iwe[i];
+    v.y = diwe ? diwe[i] : 0.0f;
+    v.z = diwe ? diwe[npix + i] : 0.0f;
+    v.w = 0.0f;
+    reinterpret_cast<float4 *>(acc)[i] = v;
+}
+
+}  // namespace evk
+
+extern "C" {
+
+size_t evk_cmax_workspace_bytes(int Hs, int Ws)
+{
+    if (Hs < 1 || Ws < 1) return 0;
+    return evk::carve(nullptr, Hs, Ws, nullptr);
+}
+
+int evk_cmax_linvel_variance_f64(const double *x, const double *y, const double *t, const double *p, int64_t n,
+                                 double p_scale, double vx, double vy, double t_ref, int Hm, int Wm, int Hs, int Ws,
+                                 double sigma,
+                                 unsigned flags, double *result, float *iwe_out, float *diwe_out, void *workspace,
+                                 size_t workspace_bytes, void *stream)
+{
+    using namespace evk;
+    if (n > 0 && (!x || !y || !t || !p)) { set_error("evk_cmax_linvel_variance_f64: null event array"); return EVK_E_ARG; }
+    CmaxArgs A{};
+    A.x = x; A.y = y; A.t = t; A.p = p; A.n = n;
+    A.vx = vx; A.vy = vy; A.t_ref = t_ref; A.p_scale = p_scale;
+    A.Hm = Hm; A.Wm = Wm; A.Hc = Hs + 1; A.Wc = Ws + 1;
+    return run_cmax<WARP_LINVEL_F64>(A, sigma, flags, result, iwe_out, diwe_out, workspace, workspace_bytes,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+int evk_cmax_linvel_variance_f32(const float *x, const float *y, const float *t_rel, const float *p, int64_t n,
+                                 float p_scale, float vx, float vy, int Hm, int Wm, int Hs, int Ws, double sigma,
+                                 unsigned flags,
+                                 double *result, float *iwe_out, float *diwe_out, void *workspace,
+                                 size_t workspace_bytes, void *stream)
+{
+    using namespace evk;
+    if (n > 0 && (!x || !y || !t_rel || !p)) { set_error("evk_cmax_linvel_variance_f32: null event array"); return EVK_E_ARG; }
+    CmaxArgs A{};
+    A.x = x; A.y = y; A.t = t_rel; A.p = p; A.n = n;
+    A.vx = vx; A.vy = vy; A.t_ref = 0.0; A.p_scale = p_scale;
+    A.Hm = Hm; A.Wm = Wm; A.Hc = Hs + 1; A.Wc = Ws + 1;
+    return run_cmax<WARP_LINVEL_F32>(A, sigma, flags, result, iwe_out, diwe_out, workspace, workspace_bytes,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+int evk_cmax_flow_variance_f32(const float *x, const float *y, const float *t, const float *p, int64_t n,
+                               const float *flow, float t0, int Hs, int Ws, double sigma, unsigned flags,
+                               double *result, float *iwe_out, void *workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace evk;
+    if (!flow || (n > 0 && (!x || !y || !t || !p))) { set_error("evk_cmax_flow_variance_f32: null array"); return EVK_E_ARG; }
+    CmaxArgs A{};
+    A.x = x; A.y = y; A.t = t; A.p = p; A.n = n;
+    A.flow = flow; A.flow_t0 = t0; A.p_scale = 1.0;
+    A.Hm = Hs; A.Wm = Ws; A.Hc = Hs + 1; A.Wc = Ws + 1;
+    return run_cmax<WARP_FLOW_F32>(A, sigma, flags, result, iwe_out, nullptr, workspace, workspace_bytes,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int evk_variance_objective_f32(const float *iwe, const float *diwe, int Hc, int Wc, double sigma, unsigned flags,
+                               double *result, void *workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace evk;
+    if (!iwe || !result || !workspace || Hc < 2 || Wc < 2) { set_error("evk_variance_objective_f32: bad arguments"); return EVK_E_ARG; }
+    if (((uintptr_t)workspace & 255) != 0) { set_error("evk_variance_objective_f32: workspace must be 256-byte aligned"); return EVK_E_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CmaxWorkspace ws;
+    const size_t need = carve(workspace, Hc - 1, Wc - 1, &ws);
+    if (workspace_bytes < need) { set_error("evk_variance_objective_f32: workspace of %zu bytes required", need); return EVK_E_WORKSPACE; }
+    const int npix = Hc * Wc;
+    const bool grad = (flags & EVK_CMAX_WANT_GRAD) != 0 && diwe != nullptr;
+    BlurTaps taps{};
+    double mix_a = 1.0, mix_b = 0.0;
+    const int do_blur = sigma > 0.0;
+    if (do_blur) {
+        int rc = make_taps(sigma, &taps);
+        if (rc) return rc;
+        if (!(flags & EVK_CMAX_NO_CHANNEL_MIX)) mix_coeffs(taps, &mix_a, &mix_b);
+    }
+    EVK_CUDA(cudaMemsetAsync(ws.sums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.sums), st));
+    const int g = (npix + 255) / 256;
+    cmax_pack_kernel<<<g, 256, 0, st>>>(iwe, grad ? diwe : nullptr, npix, ws.acc);
+    cmax_gather_kernel<<<g, 256, 0, st>>>(ws.acc, 1, npix, ws.I, ws.D0, ws.D1, nullptr, nullptr, ws.sums);
+    if (do_blur) cmax_blur_axis0_kernel<<<g, 256, 0, st>>>(ws.I, ws.tmp, Hc, Wc, taps);
+    cmax_blur_axis1_sums_kernel<<<g, 256, 0, st>>>(ws.tmp, ws.I, ws.D0, ws.D1, Hc, Wc, taps, do_blur, ws.sums);
+    cmax_final_kernel<<<1, 1, 0, st>>>(ws.sums, ws.oob, npix, mix_a, mix_b, grad ? 1 : 0, result);
+    EVK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+}  // extern "C"

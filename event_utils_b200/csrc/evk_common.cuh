@@ -1,0 +1,96 @@
+// evk_common.cuh -- shared host/device helpers for libevk.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "evk.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libevk is written for sm_100a (B200) only"
+#endif
+
+namespace evk {
+
+// ---- host side ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+int num_sms();  // SM count of the current device (cached)
+
+#define EVK_CUDA(call)                                              \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return ::evk::cuda_fail(e__, #call); \
+    } while (0)
+
+#define EVK_REQUIRE(cond, msg)                      \
+    do {                                            \
+        if (!(cond)) {                              \
+            ::evk::set_error("%s: %s", __func__, msg); \
+            return EVK_E_ARG;                       \
+        }                                           \
+    } while (0)
+
+static inline unsigned variant_of(unsigned flags) { return flags & EVK_VARIANT_MASK; }
+
+// Persistent-style launch geometry: a multiple of the SM count, capped by the work available.
+static inline int grid_for(int64_t work_items, int items_per_cta, int ctas_per_sm)
+{
+    int64_t need = (work_items + items_per_cta - 1) / items_per_cta;
+    int64_t cap = (int64_t)num_sms() * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// ---- device side -------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// torch `Tensor.long()` (truncate toward zero) followed by python index wrapping:
+// [-size,-1] wraps once, everything else outside [0,size) is the reference's IndexError.
+// NaN / inf / |v| >= 2^31 can never be a valid index.
+__device__ __forceinline__ bool wrap_trunc_index(float v, int size, int &out)
+{
+    if (!(fabsf(v) < 2.0e9f)) return false;
+    int i = __float2int_rz(v);
+    if (i < 0) i += size;
+    out = i;
+    return (unsigned)i < (unsigned)size;
+}
+
+// float -> int truncation that refuses NaN / inf / values no index can take
+__device__ __forceinline__ bool trunc_checked(float v, int &i)
+{
+    if (!(fabsf(v) < 2.0e9f)) return false;
+    i = __float2int_rz(v);
+    return true;
+}
+
+__device__ __forceinline__ bool wrap_int_index(int i, int size, int &out)
+{
+    if (i < 0) i += size;
+    out = i;
+    return (unsigned)i < (unsigned)size;
+}
+
+// streaming (evict-first) loads: the event arrays are read exactly once and must not push the
+// L2-resident accumulation grid out.
+__device__ __forceinline__ float4 ld_stream4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ double2 ld_stream2(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
+
+// no-return global reductions (SASS: REDG.E.ADD.F32 / .F32x2 / .F32x4)
+__device__ __forceinline__ void red_add(float *addr, float v) { atomicAdd(addr, v); }
+__device__ __forceinline__ void red_add4(float *addr16, float4 v) { atomicAdd(reinterpret_cast<float4 *>(addr16), v); }
+__device__ __forceinline__ void red_add2(float *addr8, float2 v) { atomicAdd(reinterpret_cast<float2 *>(addr8), v); }
+
+__device__ __forceinline__ void flush_oob(unsigned long long *oob, unsigned local)
+{
+    // one atomic per warp, only when something was out of range
+    unsigned tot = __reduce_add_sync(0xffffffffu, local);
+    if (tot != 0 && (threadIdx.x & 31) == 0 && oob != nullptr) atomicAdd(oob, (unsigned long long)tot);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace evk

@@ -1,0 +1,386 @@
+// evk_image.cu -- events -> 2-D event image (nearest / bilinear), integer count image and the
+// dense-flow warp on B200.
+//
+// Semantics:
+//   events_to_image_torch   reference lib/representations/image.py:46-100
+//   interpolate_to_image    reference lib/representations/image.py:102-115
+//   warp_events_flow_torch  reference lib/transforms/optic_flow.py:5-46
+//
+// Variants:
+//   GLOBAL_RED : one red.global.add.f32 per tap straight into out.
+//   VECTOR_RED : (bilinear) the two taps of an image row are adjacent; rows are kept in a
+//                "quad" workspace where quad q holds columns 3q..3q+3 (overlap of one column, so
+//                every (x, x+1) pair is inside one 16-byte aligned quad) -> 2 vector reds per
+//                event instead of 4 scalar ones, then a fold epilogue.
+//   WARP_AGG   : lanes of a warp that hit the same cell are combined with match.any before the
+//                red (hot-spot / Zipf streams, where same-address serialisation in L2 dominates).
+#include "evk_common.cuh"
+
+namespace evk {
+
+struct ImageArgs {
+    const float *x, *y, *p;
+    int64_t n;
+    int H, W;  // canvas
+    int clip;
+    float clipx, clipy;
+    int nqx;  // quads per row (vector variant)
+    float *out;
+    float *ws;
+    unsigned *out_u32;
+    unsigned long long *oob;
+};
+
+enum { ISINK_SCALAR = 0, ISINK_QUAD = 1, ISINK_WARPAGG = 2 };
+
+static inline int quads_for_cols(int W) { return W <= 1 ? 1 : (W - 1 + 2) / 3; }
+
+// Combine lanes that target the same cell: every lane learns its peers, the lowest peer lane
+// adds the group's sum.  Returns true in the lane that must issue the red, with `v` = group sum.
+__device__ __forceinline__ bool warp_combine(int64_t cell, bool active, float &v)
+{
+    // inactive lanes use a cell id no active lane can have
+    const unsigned long long key = active ? (unsigned long long)cell : ~0ull - (threadIdx.x & 31);
+    unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    // segmented sum: walk the peer mask (groups are small except on the hottest cells)
+    float sum = 0.0f;
+    unsigned any_multi = __ballot_sync(0xffffffffu, peers != (1u << lane));
+    if (any_multi == 0) return active;  // all cells distinct: nothing to combine
+    // every lane publishes its value; leaders accumulate their peers in lane order
+    for (int src = 0; src < 32; ++src) {
+        float o = __shfl_sync(0xffffffffu, v, src);
+        if ((peers >> src) & 1u) sum += o;
+    }
+    v = sum;
+    return active && lane == leader;
+}
+
+template <int SINK, bool BIL>
+__device__ __forceinline__ void image_event(const ImageArgs &A, float x, float y, float p, bool valid,
+                                            unsigned &oob)
+{
+    if (!BIL) {
+        // image.py:88-95: index = trunc(coord) * mask, weight NOT masked
+        int xi = 0, yi = 0;
+        bool ok = valid;
+        if (ok) {
+            const bool keep = !A.clip || (!(x >= A.clipx) && !(y >= A.clipy));
+            int ux, uy;
+            if (!trunc_checked(x, ux) || !trunc_checked(y, uy)) { ok = false; ++oob; }
+            else {
+                if (!keep) { ux = 0; uy = 0; }
+                if (!wrap_int_index(ux, A.W, xi) || !wrap_int_index(uy, A.H, yi)) { ok = false; ++oob; }
+            }
+        }
+        const int64_t cell = (int64_t)yi * A.W + xi;
+        if (SINK == ISINK_WARPAGG) {
+            float v = ok ? p : 0.0f;
+            if (warp_combine(cell, ok, v) && v != 0.0f) red_add(A.out + cell, v);
+        } else {
+            if (ok && p != 0.0f) red_add(A.out + cell, p);
+        }
+    } else {
+        // image.py:79-86 + 111-114
+        if (!valid) return;
+        float m = 1.0f;
+        if (A.clip) m = (x >= A.clipx ? 0.0f : 1.0f) * (y >= A.clipy ? 0.0f : 1.0f);
+        const float pxf = floorf(x), pyf = floorf(y);
+        const float dx = __fsub_rn(x, pxf), dy = __fsub_rn(y, pyf);
+        int upx, upy, x0, x1, y0, y1;
+        if (!trunc_checked(__fmul_rn(pxf, m), upx) || !trunc_checked(__fmul_rn(pyf, m), upy) ||
+            !wrap_int_index(upx, A.W, x0) || !wrap_int_index(upx + 1, A.W, x1) ||
+            !wrap_int_index(upy, A.H, y0) || !wrap_int_index(upy + 1, A.H, y1)) { ++oob; return; }
+        const float w = __fmul_rn(p, m);
+        const float ox = __fsub_rn(1.0f, dx), oy = __fsub_rn(1.0f, dy);
+        const float wl = __fmul_rn(w, ox), wr = __fmul_rn(w, dx);
+        const float v00 = __fmul_rn(wl, oy), v01 = __fmul_rn(wr, oy);
+        const float v10 = __fmul_rn(wl, dy), v11 = __fmul_rn(wr, dy);
+        if (SINK == ISINK_QUAD) {
+            if (x1 == x0 + 1) {
+                int q = x0 / 3;
+                if (q > A.nqx - 1) q = A.nqx - 1;
+                const int s = x0 - 3 * q;  // 0..2 (x0+1 <= W-1 guarantees s+1 <= 3)
+                if (v00 != 0.0f || v01 != 0.0f) {
+                    float4 v;
+                    v.x = (s == 0) ? v00 : 0.0f;
+                    v.y = (s == 1) ? v00 : ((s == 0) ? v01 : 0.0f);
+                    v.z = (s == 2) ? v00 : ((s == 1) ? v01 : 0.0f);
+                    v.w = (s == 2) ? v01 : 0.0f;
+                    red_add4(A.ws + ((int64_t)y0 * A.nqx + q) * 4, v);
+                }
+                if (v10 != 0.0f || v11 != 0.0f) {
+                    float4 v;
+                    v.x = (s == 0) ? v10 : 0.0f;
+                    v.y = (s == 1) ? v10 : ((s == 0) ? v11 : 0.0f);
+                    v.z = (s == 2) ? v10 : ((s == 1) ? v11 : 0.0f);
+                    v.w = (s == 2) ? v11 : 0.0f;
+                    red_add4(A.ws + ((int64_t)y1 * A.nqx + q) * 4, v);
+                }
+            } else {
+                // wrapped pair (negative px): scalar taps into the quad rows
+                auto tap = [&](int yy, int xx, float v) {
+                    if (v == 0.0f) return;
+                    int q = xx / 3;
+                    if (q > A.nqx - 1) q = A.nqx - 1;
+                    red_add(A.ws + ((int64_t)yy * A.nqx + q) * 4 + (xx - 3 * q), v);
+                };
+                tap(y0, x0, v00); tap(y0, x1, v01); tap(y1, x0, v10); tap(y1, x1, v11);
+            }
+        } else {
+            if (v00 != 0.0f) red_add(A.out + (int64_t)y0 * A.W + x0, v00);
+            if (v01 != 0.0f) red_add(A.out + (int64_t)y0 * A.W + x1, v01);
+            if (v10 != 0.0f) red_add(A.out + (int64_t)y1 * A.W + x0, v10);
+            if (v11 != 0.0f) red_add(A.out + (int64_t)y1 * A.W + x1, v11);
+        }
+    }
+}
+
+constexpr int kThreads = 256;
+
+template <int SINK, bool BIL, bool VEC4>
+__global__ void __launch_bounds__(kThreads) image_scatter_kernel(const ImageArgs A)
+{
+    unsigned oob = 0;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    if (VEC4) {
+        const int64_t n4 = A.n >> 2;
+        // warp-uniform trip count so that the warp-aggregated variant can use full-mask collectives
+        const int64_t iters = (n4 + stride - 1) / stride;
+        for (int64_t it = 0; it < iters; ++it) {
+            const int64_t g = tid + it * stride;
+            const bool v = g < n4;
+            float4 X = make_float4(0, 0, 0, 0), Y = X, P = X;
+            if (v) { X = ld_stream4(A.x + 4 * g); Y = ld_stream4(A.y + 4 * g); P = ld_stream4(A.p + 4 * g); }
+            image_event<SINK, BIL>(A, X.x, Y.x, P.x, v, oob);
+            image_event<SINK, BIL>(A, X.y, Y.y, P.y, v, oob);
+            image_event<SINK, BIL>(A, X.z, Y.z, P.z, v, oob);
+            image_event<SINK, BIL>(A, X.w, Y.w, P.w, v, oob);
+        }
+        const int64_t tail0 = n4 << 2;
+        const int64_t j = tail0 + tid;
+        if (tail0 < A.n && tid < 32 * ((A.n - tail0 + 31) / 32)) {
+            const bool v = j < A.n;
+            image_event<SINK, BIL>(A, v ? A.x[j] : 0.f, v ? A.y[j] : 0.f, v ? A.p[j] : 0.f, v, oob);
+        }
+    } else {
+        const int64_t iters = (A.n + stride - 1) / stride;
+        for (int64_t it = 0; it < iters; ++it) {
+            const int64_t i = tid + it * stride;
+            const bool v = i < A.n;
+            image_event<SINK, BIL>(A, v ? ld_stream(A.x + i) : 0.f, v ? ld_stream(A.y + i) : 0.f,
+                                   v ? ld_stream(A.p + i) : 0.f, v, oob);
+        }
+    }
+    flush_oob(A.oob, oob);
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float *out, int64_t n, float v)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
+}
+
+// quad rows -> out[H][W] (+ fill).  Column x lives in quad x/3 slot x%3 and, when x%3==0 and
+// x>0, also in quad x/3-1 slot 3.
+template <bool ACCUM>
+__global__ void __launch_bounds__(256) image_fold_kernel(const float *__restrict__ ws, float *__restrict__ out,
+                                                         int H, int W, int nqx, float fill)
+{
+    const int64_t npix = (int64_t)H * W;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+        const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+        const float *row = ws + (int64_t)y * nqx * 4;
+        int q = x / 3;
+        float v = 0.0f;
+        if (q < nqx) v = row[q * 4 + (x - 3 * q)];
+        if (x > 0 && x % 3 == 0) v += row[(x / 3 - 1) * 4 + 3];
+        out[i] = ACCUM ? (out[i] + v) : (fill + v);
+    }
+}
+
+// ---- integer-exact count image ------------------------------------------------------------
+template <bool AGG>
+__global__ void __launch_bounds__(kThreads) count_kernel(const ImageArgs A)
+{
+    unsigned oob = 0;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    const int64_t iters = (A.n + stride - 1) / stride;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i = tid + it * stride;
+        bool ok = i < A.n;
+        int xi = 0, yi = 0;
+        if (ok) {
+            const float x = ld_stream(A.x + i), y = ld_stream(A.y + i);
+            const bool keep = !A.clip || (!(x >= A.clipx) && !(y >= A.clipy));
+            int ux, uy;
+            if (!trunc_checked(x, ux) || !trunc_checked(y, uy)) { ok = false; ++oob; }
+            else {
+                if (!keep) { ux = 0; uy = 0; }
+                if (!wrap_int_index(ux, A.W, xi) || !wrap_int_index(uy, A.H, yi)) { ok = false; ++oob; }
+            }
+        }
+        const int64_t cell = (int64_t)yi * A.W + xi;
+        if (AGG) {
+            const unsigned long long key = ok ? (unsigned long long)cell : ~0ull - (threadIdx.x & 31);
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(A.out_u32 + cell, (unsigned)__popc(peers));
+        } else {
+            if (ok) atomicAdd(A.out_u32 + cell, 1u);
+        }
+    }
+    flush_oob(A.oob, oob);
+}
+
+// ---- dense-flow warp (optic_flow.py:37-44 + ATen grid_sampler bilinear/zeros/align_corners) ---
+__device__ __forceinline__ float flow_at(const float *f, int H, int W, int yy, int xx)
+{
+    return ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? __ldg(f + (int64_t)yy * W + xx) : 0.0f;
+}
+
+__global__ void __launch_bounds__(256) warp_flow_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                                        const float *__restrict__ t, int64_t n,
+                                                        const float *__restrict__ flow, int H, int W, float t0,
+                                                        float *__restrict__ xw, float *__restrict__ yw)
+{
+    const float *fu = flow, *fv = flow + (int64_t)H * W;
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float xe = ld_stream(x + i), ye = ld_stream(y + i), te = ld_stream(t + i);
+        // the reference normalises to [-1,1] (optic_flow.py:37-38) and grid_sample maps back
+        const float gx = __fsub_rn(__fmul_rn(__fdiv_rn(xe, wm1), 2.0f), 1.0f);
+        const float gy = __fsub_rn(__fmul_rn(__fdiv_rn(ye, hm1), 2.0f), 1.0f);
+        const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), wm1);
+        const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), hm1);
+        float u = 0.0f, v = 0.0f;
+        if (fabsf(ix) < 1.0e9f && fabsf(iy) < 1.0e9f) {
+            const float fx = floorf(ix), fy = floorf(iy);
+            const int x0 = (int)fx, y0 = (int)fy;
+            const float xs = fx + 1.0f, ys = fy + 1.0f;
+            const float nw = __fmul_rn(__fsub_rn(xs, ix), __fsub_rn(ys, iy));
+            const float ne = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(ys, iy));
+            const float sw = __fmul_rn(__fsub_rn(xs, ix), __fsub_rn(iy, fy));
+            const float se = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(iy, fy));
+            u = __fadd_rn(u, __fmul_rn(flow_at(fu, H, W, y0, x0), nw));         v = __fadd_rn(v, __fmul_rn(flow_at(fv, H, W, y0, x0), nw));
+            u = __fadd_rn(u, __fmul_rn(flow_at(fu, H, W, y0, x0 + 1), ne));     v = __fadd_rn(v, __fmul_rn(flow_at(fv, H, W, y0, x0 + 1), ne));
+            u = __fadd_rn(u, __fmul_rn(flow_at(fu, H, W, y0 + 1, x0), sw));     v = __fadd_rn(v, __fmul_rn(flow_at(fv, H, W, y0 + 1, x0), sw));
+            u = __fadd_rn(u, __fmul_rn(flow_at(fu, H, W, y0 + 1, x0 + 1), se)); v = __fadd_rn(v, __fmul_rn(flow_at(fv, H, W, y0 + 1, x0 + 1), se));
+        }
+        const float d = __fsub_rn(te, t0);
+        xw[i] = __fadd_rn(xe, __fmul_rn(u, d));
+        yw[i] = __fadd_rn(ye, __fmul_rn(v, d));
+    }
+}
+
+}  // namespace evk
+
+extern "C" {
+
+size_t evk_image_workspace_bytes(int Himg, int Wimg, unsigned flags)
+{
+    if (Himg < 1 || Wimg < 1 || !(flags & EVK_BILINEAR)) return 0;
+    return (size_t)Himg * evk::quads_for_cols(Wimg) * 4 * sizeof(float);
+}
+
+int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int Himg, int Wimg, float clipx,
+                  float clipy, unsigned flags, float fill, float *out, void *workspace, size_t workspace_bytes,
+                  unsigned long long *oob, void *stream)
+{
+    using namespace evk;
+    if (n < 0 || Himg < 1 || Wimg < 1 || !out || (n > 0 && (!x || !y || !p))) {
+        set_error("evk_image_f32: bad arguments");
+        return EVK_E_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool bil = (flags & EVK_BILINEAR) != 0, accum = (flags & EVK_ACCUMULATE) != 0;
+    if (bil && (Himg < 2 || Wimg < 2)) { set_error("evk_image_f32: bilinear needs a canvas of at least 2x2"); return EVK_E_ARG; }
+    ImageArgs A{};
+    A.x = x; A.y = y; A.p = p; A.n = n; A.H = Himg; A.W = Wimg;
+    A.clip = (flags & EVK_CLIP) ? 1 : 0; A.clipx = clipx; A.clipy = clipy;
+    A.out = out; A.oob = oob;
+    A.nqx = quads_for_cols(Wimg);
+    unsigned variant = variant_of(flags);
+    if (variant == EVK_VARIANT_AUTO)
+        variant = (bil && workspace && n >= ((int64_t)1 << 20)) ? EVK_VARIANT_VECTOR_RED : EVK_VARIANT_GLOBAL_RED;
+    if (variant == EVK_VARIANT_VECTOR_RED && !bil) variant = EVK_VARIANT_GLOBAL_RED;
+    if (variant == EVK_VARIANT_WARP_AGG && bil) variant = EVK_VARIANT_GLOBAL_RED;
+    const int64_t npix = (int64_t)Himg * Wimg;
+    const bool vec4 = ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)p) & 15) == 0);
+    const int grid = grid_for(n, kThreads * 16, 8);
+    if (variant == EVK_VARIANT_VECTOR_RED) {
+        const size_t need = (size_t)Himg * A.nqx * 4 * sizeof(float);
+        if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) {
+            set_error("evk_image_f32: 16-byte aligned workspace of %zu bytes required", need);
+            return EVK_E_WORKSPACE;
+        }
+        A.ws = static_cast<float *>(workspace);
+        EVK_CUDA(cudaMemsetAsync(A.ws, 0, need, st));
+        if (n > 0) {
+            if (vec4) image_scatter_kernel<ISINK_QUAD, true, true><<<grid, kThreads, 0, st>>>(A);
+            else image_scatter_kernel<ISINK_QUAD, true, false><<<grid, kThreads, 0, st>>>(A);
+        }
+        const int g2 = grid_for(npix, 256, 8);
+        if (accum) image_fold_kernel<true><<<g2, 256, 0, st>>>(A.ws, out, Himg, Wimg, A.nqx, fill);
+        else image_fold_kernel<false><<<g2, 256, 0, st>>>(A.ws, out, Himg, Wimg, A.nqx, fill);
+    } else if (variant == EVK_VARIANT_GLOBAL_RED || variant == EVK_VARIANT_WARP_AGG) {
+        if (!accum) {
+            if (fill == 0.0f) EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)npix * sizeof(float), st));
+            else fill_kernel<<<grid_for(npix, 256, 8), 256, 0, st>>>(out, npix, fill);
+        }
+        if (n > 0) {
+            if (bil) {
+                if (vec4) image_scatter_kernel<ISINK_SCALAR, true, true><<<grid, kThreads, 0, st>>>(A);
+                else image_scatter_kernel<ISINK_SCALAR, true, false><<<grid, kThreads, 0, st>>>(A);
+            } else if (variant == EVK_VARIANT_WARP_AGG) {
+                if (vec4) image_scatter_kernel<ISINK_WARPAGG, false, true><<<grid, kThreads, 0, st>>>(A);
+                else image_scatter_kernel<ISINK_WARPAGG, false, false><<<grid, kThreads, 0, st>>>(A);
+            } else {
+                if (vec4) image_scatter_kernel<ISINK_SCALAR, false, true><<<grid, kThreads, 0, st>>>(A);
+                else image_scatter_kernel<ISINK_SCALAR, false, false><<<grid, kThreads, 0, st>>>(A);
+            }
+        }
+    } else {
+        set_error("evk_image_f32: variant 0x%x not available", variant);
+        return EVK_E_UNSUPPORTED;
+    }
+    EVK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+int evk_count_u32(const float *x, const float *y, int64_t n, int Himg, int Wimg, float clipx, float clipy,
+                  unsigned flags, unsigned int *out, unsigned long long *oob, void *stream)
+{
+    using namespace evk;
+    if (n < 0 || Himg < 1 || Wimg < 1 || !out || (n > 0 && (!x || !y))) { set_error("evk_count_u32: bad arguments"); return EVK_E_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ImageArgs A{};
+    A.x = x; A.y = y; A.n = n; A.H = Himg; A.W = Wimg;
+    A.clip = (flags & EVK_CLIP) ? 1 : 0; A.clipx = clipx; A.clipy = clipy;
+    A.out_u32 = out; A.oob = oob;
+    if (!(flags & EVK_ACCUMULATE)) EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)Himg * Wimg * sizeof(unsigned), st));
+    if (n > 0) {
+        const int grid = grid_for(n, kThreads * 8, 8);
+        if (variant_of(flags) == EVK_VARIANT_GLOBAL_RED) count_kernel<false><<<grid, kThreads, 0, st>>>(A);
+        else count_kernel<true><<<grid, kThreads, 0, st>>>(A);
+    }
+    EVK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+int evk_warp_flow_f32(const float *x, const float *y, const float *t, int64_t n, const float *flow, int H, int W,
+                      float t0, float *xw, float *yw, void *stream)
+{
+    using namespace evk;
+    if (n < 0 || H < 1 || W < 1 || !flow || (n > 0 && (!x || !y || !t || !xw || !yw))) { set_error("evk_warp_flow_f32: bad arguments"); return EVK_E_ARG; }
+    if (n == 0) return EVK_OK;
+    warp_flow_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, t, n, flow, H, W, t0, xw, yw);
+    EVK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,418 @@
+// evk_voxel.cu -- events -> (B,H,W) voxel grid on B200.
+//
+// Semantics: events_to_voxel_torch, reference lib/representations/voxel_grid.py:129-153
+// (per-bin weights :136-139, scatter through events_to_image_torch image.py:88-95).
+//
+// B200 design:
+//   * the reference makes B passes over all N events and scatters B*N values (mostly zeros);
+//     an event has at most TWO non-zero temporal taps (bins floor(tau), floor(tau)+1), so one
+//     pass over the events with <= 2 taps is the same sum.
+//   * events are streamed once with 16-byte evict-first loads (16 B/event of HBM traffic);
+//     the accumulation grid (B*H*W*4 B = 6.1 MB at 5x480x640) stays L2 resident.
+//   * GLOBAL_RED variant : one red.global.add.f32 per tap straight into out[B][H][W].
+//   * VECTOR_RED variant : the two temporal taps of an event are adjacent in a pixel-major
+//     "quad" workspace ws[H*W][nq][4]; quad q holds bins 3q..3q+3 (neighbouring quads overlap by
+//     one bin so that EVERY (b, b+1) pair lives inside one 16-byte aligned quad) and the event is
+//     ONE red.global.add.v4.f32 (sm_90+ vector reduction, SASS REDG.E.ADD.F32x4).  A gather
+//     epilogue folds the quads back into out[B][H][W].  Halves the number of L2 reduction
+//     operations, which (not HBM) is what bounds this kernel.
+#include "evk_common.cuh"
+
+namespace evk {
+
+struct VoxelArgs {
+    const float *x, *y, *t, *p;  // SoA arrays (AoS: x is the interleaved base)
+    int64_t n;
+    int64_t head;  // SoA vec4 layout: scalar events before the 16-byte aligned body
+    float t0, dt, bm1;
+    int B, H, W, nq;
+    int clip;  // trilinear only
+    float clipx, clipy;
+    float *out;  // [B][H][W]
+    float *ws;   // [H*W][nq][4]
+    unsigned long long *oob;
+};
+
+enum { SINK_SCALAR = 0, SINK_QUAD = 1 };
+enum { LAYOUT_SOA4 = 0, LAYOUT_SOA1 = 1, LAYOUT_AOS = 2 };
+
+static inline int quads_for_bins(int B) { return B <= 1 ? 1 : (B - 1 + 2) / 3; }
+
+// Add the temporal tap pair (value v0 at bin b0, v1 at bin b0+1) of one pixel.
+template <int SINK>
+__device__ __forceinline__ void add_bin_pair(const VoxelArgs &A, int64_t pix, int b0, float v0, float v1)
+{
+    if (SINK == SINK_SCALAR) {
+        const int64_t plane = (int64_t)A.H * A.W;
+        if ((unsigned)b0 < (unsigned)A.B && v0 != 0.0f) red_add(A.out + (int64_t)b0 * plane + pix, v0);
+        if ((unsigned)(b0 + 1) < (unsigned)A.B && v1 != 0.0f) red_add(A.out + (int64_t)(b0 + 1) * plane + pix, v1);
+    } else {
+        int lo = b0 < 0 ? 0 : b0;
+        int hi = (b0 + 1 > A.B - 1) ? A.B - 1 : b0 + 1;
+        if (lo > hi) return;
+        float a = (lo == b0) ? v0 : v1;                       // value of bin lo
+        float b = (lo + 1 == b0 + 1 && lo + 1 <= hi) ? v1 : 0.0f;  // value of bin lo+1
+        if (a == 0.0f && b == 0.0f) return;
+        int q = lo / 3;
+        if (q > A.nq - 1) q = A.nq - 1;
+        int s = lo - 3 * q;  // 0..3 (3 only in the clamped last quad, where b is 0)
+        float4 v;
+        v.x = (s == 0) ? a : 0.0f;
+        v.y = (s == 1) ? a : ((s == 0) ? b : 0.0f);
+        v.z = (s == 2) ? a : ((s == 1) ? b : 0.0f);
+        v.w = (s == 3) ? a : ((s == 2) ? b : 0.0f);
+        red_add4(A.ws + (pix * A.nq + q) * 4, v);
+    }
+}
+
+// Rare path: non-finite tau or polarity.  Literal restatement of voxel_grid.py:138-139 for
+// every bin so that NaN propagation matches (dt == 0 -> NaN in V[:, y, x]).
+template <int SINK>
+__device__ __noinline__ void add_all_bins_slow(const VoxelArgs &A, int64_t pix, float tn, float p)
+{
+    for (int b = 0; b < A.B; ++b) {
+        float w = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, (float)b)));
+        float wb = (w != w) ? w : (w > 0.0f ? w : 0.0f);  // torch.max(zeros, w) propagates NaN
+        float v = __fmul_rn(p, wb);
+        if (v == 0.0f) continue;
+        if (SINK == SINK_SCALAR) {
+            red_add(A.out + ((int64_t)b * A.H * A.W) + pix, v);
+        } else {
+            int q = b / 3;
+            if (q > A.nq - 1) q = A.nq - 1;
+            red_add(A.ws + (pix * A.nq + q) * 4 + (b - 3 * q), v);
+        }
+    }
+}
+
+template <int SINK, bool SPATIAL_BILINEAR>
+__device__ __forceinline__ void voxel_event(const VoxelArgs &A, float x, float y, float t, float p,
+                                            unsigned &oob)
+{
+    // tau = (t - t0) / dt * (B-1), evaluated in exactly this order, no FMA (voxel_grid.py:134)
+    const float tn = __fmul_rn(__fdiv_rn(__fsub_rn(t, A.t0), A.dt), A.bm1);
+    const bool finite = (fabsf(tn) < 1.0e9f) && (fabsf(p) <= FLT_MAX);
+
+    if (!SPATIAL_BILINEAR) {
+        int xi, yi;
+        if (!wrap_trunc_index(x, A.W, xi) || !wrap_trunc_index(y, A.H, yi)) { ++oob; return; }
+        const int64_t pix = (int64_t)yi * A.W + xi;
+        if (!finite) { add_all_bins_slow<SINK>(A, pix, tn, p); return; }
+        const float fl = floorf(tn);
+        const float w0 = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fl)));         // bin floor(tau)
+        const float w1 = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fl + 1.0f)));  // bin floor(tau)+1
+        add_bin_pair<SINK>(A, pix, (int)fl, __fmul_rn(p, w0), __fmul_rn(p, w1));
+    } else {
+        // trilinear extension: per-bin events_to_image_torch(..., interpolation='bilinear')
+        // (image.py:78-86,102-115) with the bin weight folded into the polarity.
+        float m = 1.0f;
+        if (A.clip) m = (x >= A.clipx ? 0.0f : 1.0f) * (y >= A.clipy ? 0.0f : 1.0f);
+        const float pxf = floorf(x), pyf = floorf(y);
+        const float dx = __fsub_rn(x, pxf), dy = __fsub_rn(y, pyf);
+        int upx, upy, x0, x1, y0, y1;
+        if (!trunc_checked(__fmul_rn(pxf, m), upx) || !trunc_checked(__fmul_rn(pyf, m), upy) ||
+            !wrap_int_index(upx, A.W, x0) || !wrap_int_index(upx + 1, A.W, x1) ||
+            !wrap_int_index(upy, A.H, y0) || !wrap_int_index(upy + 1, A.H, y1)) { ++oob; return; }
+        if (m == 0.0f && finite) return;  // masked events only add zeros at pixel (0,0)..(1,1)
+        float wb0, wb1;
+        int b0;
+        const float ox = __fsub_rn(1.0f, dx), oy = __fsub_rn(1.0f, dy);
+        if (!finite) {
+            // keep NaN semantics: every bin, every tap
+            for (int b = 0; b < A.B; ++b) {
+                float w = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, (float)b)));
+                float wb = (w != w) ? w : (w > 0.0f ? w : 0.0f);
+                float pw = __fmul_rn(__fmul_rn(p, wb), m);
+                float *o = (SINK == SINK_SCALAR) ? A.out + (int64_t)b * A.H * A.W : nullptr;
+                float v00 = __fmul_rn(__fmul_rn(pw, ox), oy), v01 = __fmul_rn(__fmul_rn(pw, dx), oy);
+                float v10 = __fmul_rn(__fmul_rn(pw, ox), dy), v11 = __fmul_rn(__fmul_rn(pw, dx), dy);
+                if (SINK == SINK_SCALAR) {
+                    if (v00 != 0.0f) red_add(o + (int64_t)y0 * A.W + x0, v00);
+                    if (v01 != 0.0f) red_add(o + (int64_t)y0 * A.W + x1, v01);
+                    if (v10 != 0.0f) red_add(o + (int64_t)y1 * A.W + x0, v10);
+                    if (v11 != 0.0f) red_add(o + (int64_t)y1 * A.W + x1, v11);
+                } else {
+                    int q = b / 3;
+                    if (q > A.nq - 1) q = A.nq - 1;
+                    int s = b - 3 * q;
+                    if (v00 != 0.0f) red_add(A.ws + (((int64_t)y0 * A.W + x0) * A.nq + q) * 4 + s, v00);
+                    if (v01 != 0.0f) red_add(A.ws + (((int64_t)y0 * A.W + x1) * A.nq + q) * 4 + s, v01);
+                    if (v10 != 0.0f) red_add(A.ws + (((int64_t)y1 * A.W + x0) * A.nq + q) * 4 + s, v10);
+                    if (v11 != 0.0f) red_add(A.ws + (((int64_t)y1 * A.W + x1) * A.nq + q) * 4 + s, v11);
+                }
+            }
+            return;
+        }
+        const float fl = floorf(tn);
+        b0 = (int)fl;
+        wb0 = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fl)));
+        wb1 = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fl + 1.0f)));
+        const float pw0 = __fmul_rn(__fmul_rn(p, wb0), m), pw1 = __fmul_rn(__fmul_rn(p, wb1), m);
+        add_bin_pair<SINK>(A, (int64_t)y0 * A.W + x0, b0, __fmul_rn(__fmul_rn(pw0, ox), oy), __fmul_rn(__fmul_rn(pw1, ox), oy));
+        add_bin_pair<SINK>(A, (int64_t)y0 * A.W + x1, b0, __fmul_rn(__fmul_rn(pw0, dx), oy), __fmul_rn(__fmul_rn(pw1, dx), oy));
+        add_bin_pair<SINK>(A, (int64_t)y1 * A.W + x0, b0, __fmul_rn(__fmul_rn(pw0, ox), dy), __fmul_rn(__fmul_rn(pw1, ox), dy));
+        add_bin_pair<SINK>(A, (int64_t)y1 * A.W + x1, b0, __fmul_rn(__fmul_rn(pw0, dx), dy), __fmul_rn(__fmul_rn(pw1, dx), dy));
+    }
+}
+
+constexpr int kThreads = 256;
+
+template <int SINK, bool BIL, int LAYOUT>
+__global__ void __launch_bounds__(kThreads) voxel_scatter_kernel(const VoxelArgs A)
+{
+    unsigned oob = 0;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+
+    if (LAYOUT == LAYOUT_SOA4) {
+        // 16-byte aligned body: 4 events per thread per iteration, four LDG.128 in flight
+        const int64_t head = A.head;
+        const int64_t n4 = (A.n - head) >> 2;
+        const float *bx = A.x + head, *by = A.y + head, *bt = A.t + head, *bp = A.p + head;
+        for (int64_t g = tid; g < n4; g += stride) {
+            const float4 X = ld_stream4(bx + 4 * g), Y = ld_stream4(by + 4 * g);
+            const float4 T = ld_stream4(bt + 4 * g), P = ld_stream4(bp + 4 * g);
+            voxel_event<SINK, BIL>(A, X.x, Y.x, T.x, P.x, oob);
+            voxel_event<SINK, BIL>(A, X.y, Y.y, T.y, P.y, oob);
+            voxel_event<SINK, BIL>(A, X.z, Y.z, T.z, P.z, oob);
+            voxel_event<SINK, BIL>(A, X.w, Y.w, T.w, P.w, oob);
+        }
+        // scalar head [0, head) and tail [head + 4*n4, n)
+        const int64_t tail0 = head + 4 * n4;
+        const int64_t nrest = head + (A.n - tail0);
+        for (int64_t i = tid; i < nrest; i += stride) {
+            const int64_t j = (i < head) ? i : tail0 + (i - head);
+            voxel_event<SINK, BIL>(A, ld_stream(A.x + j), ld_stream(A.y + j), ld_stream(A.t + j), ld_stream(A.p + j), oob);
+        }
+    } else if (LAYOUT == LAYOUT_SOA1) {
+        // arbitrary 4-byte alignment: coalesced scalar loads, 4 independent events in flight
+        int64_t i = tid;
+        for (; i + 3 * stride < A.n; i += 4 * stride) {
+            float xs[4], ys[4], ts[4], ps[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                xs[k] = ld_stream(A.x + i + k * stride); ys[k] = ld_stream(A.y + i + k * stride);
+                ts[k] = ld_stream(A.t + i + k * stride); ps[k] = ld_stream(A.p + i + k * stride);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) voxel_event<SINK, BIL>(A, xs[k], ys[k], ts[k], ps[k], oob);
+        }
+        for (; i < A.n; i += stride)
+            voxel_event<SINK, BIL>(A, ld_stream(A.x + i), ld_stream(A.y + i), ld_stream(A.t + i), ld_stream(A.p + i), oob);
+    } else {
+        // AoS: one 16-byte [x,y,t,p] record per event
+        int64_t i = tid;
+        for (; i + 3 * stride < A.n; i += 4 * stride) {
+            float4 e[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[k] = ld_stream4(A.x + 4 * (i + k * stride));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) voxel_event<SINK, BIL>(A, e[k].x, e[k].y, e[k].z, e[k].w, oob);
+        }
+        for (; i < A.n; i += stride) {
+            const float4 e = ld_stream4(A.x + 4 * i);
+            voxel_event<SINK, BIL>(A, e.x, e.y, e.z, e.w, oob);
+        }
+    }
+    flush_oob(A.oob, oob);
+}
+
+// quad workspace -> out[B][H][W]; bin b lives in quad b/3 (slot b%3) and, when b%3==0 and b>0,
+// also in quad b/3-1 (slot 3).
+template <bool ACCUM>
+__global__ void __launch_bounds__(256) voxel_fold_kernel(const float *__restrict__ ws, float *__restrict__ out,
+                                                         int64_t npix, int B, int nq)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += stride) {
+        const float4 *src = reinterpret_cast<const float4 *>(ws) + pix * nq;
+        float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < nq; ++q) {
+            const float4 cur = src[q];
+            const float vals[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int b = 3 * q + s;
+                if (b >= B) break;
+                const bool shared_with_next = (s == 3) && (q + 1 < nq);
+                if (shared_with_next) continue;  // emitted by the next quad (slot 0) together with this slot 3
+                float v = vals[s];
+                if (s == 0 && q > 0) v += prev.w;
+                float *o = out + (int64_t)b * npix + pix;
+                *o = ACCUM ? (*o + v) : v;
+            }
+            prev = cur;
+        }
+    }
+}
+
+// Batched windows: CTA (w, s) scatters slice s of window w into out[w] with that window's own
+// t0 / dt (voxel_grid.py:133-134 applied per window, as voxel_grids_fixed_n_torch :53-56 does).
+__global__ void __launch_bounds__(kThreads) voxel_windows_kernel(const VoxelArgs A, const int64_t *__restrict__ offsets,
+                                                                 int n_windows, int slices)
+{
+    unsigned oob = 0;
+    const int w = blockIdx.x / slices, s = blockIdx.x - w * slices;
+    if (w < n_windows) {
+        const int64_t first = offsets[w], last = offsets[w + 1];
+        if (last > first) {
+            VoxelArgs Aw = A;
+            Aw.t0 = A.t[first];
+            Aw.dt = __fsub_rn(A.t[last - 1], Aw.t0);
+            Aw.out = A.out + (int64_t)w * A.B * A.H * A.W;
+            for (int64_t i = first + (int64_t)s * kThreads + threadIdx.x; i < last; i += (int64_t)slices * kThreads)
+                voxel_event<SINK_SCALAR, false>(Aw, A.x[i], A.y[i], A.t[i], A.p[i], oob);
+        }
+    }
+    flush_oob(A.oob, oob);
+}
+
+static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStream_t st,
+                        void *workspace, size_t workspace_bytes)
+{
+    VoxelArgs A = A0;
+    const bool bil = (flags & EVK_BILINEAR) != 0;
+    const bool accum = (flags & EVK_ACCUMULATE) != 0;
+    const int64_t npix = (int64_t)A.H * A.W;
+    unsigned variant = variant_of(flags);
+    if (variant == EVK_VARIANT_AUTO)
+        variant = (A.n >= (int64_t)1 << 20 && workspace != nullptr) ? EVK_VARIANT_VECTOR_RED : EVK_VARIANT_GLOBAL_RED;
+    if (variant != EVK_VARIANT_VECTOR_RED && variant != EVK_VARIANT_GLOBAL_RED) {
+        set_error("evk_voxel: variant 0x%x not available for this entry point", variant);
+        return EVK_E_UNSUPPORTED;
+    }
+    const int sink = (variant == EVK_VARIANT_VECTOR_RED) ? SINK_QUAD : SINK_SCALAR;
+    A.nq = quads_for_bins(A.B);
+    if (sink == SINK_QUAD) {
+        const size_t need = (size_t)npix * A.nq * 4 * sizeof(float);
+        if (workspace == nullptr || workspace_bytes < need) {
+            set_error("evk_voxel: workspace of %zu bytes required, %zu given", need, workspace_bytes);
+            return EVK_E_WORKSPACE;
+        }
+        if (((uintptr_t)workspace & 15) != 0) { set_error("evk_voxel: workspace must be 16-byte aligned"); return EVK_E_ARG; }
+        A.ws = static_cast<float *>(workspace);
+        EVK_CUDA(cudaMemsetAsync(A.ws, 0, need, st));
+    } else if (!accum) {
+        EVK_CUDA(cudaMemsetAsync(A.out, 0, (size_t)npix * A.B * sizeof(float), st));
+    }
+    if (A.n > 0) {
+        const int per_thread = (layout == LAYOUT_SOA4) ? 4 : 1;
+        const int grid = grid_for(A.n, kThreads * per_thread * 4, 8);
+#define EVK_LAUNCH(S, BL, L) voxel_scatter_kernel<S, BL, L><<<grid, kThreads, 0, st>>>(A)
+#define EVK_DISPATCH_L(S, BL)                                  \
+    do {                                                       \
+        if (layout == LAYOUT_SOA4) EVK_LAUNCH(S, BL, LAYOUT_SOA4); \
+        else if (layout == LAYOUT_SOA1) EVK_LAUNCH(S, BL, LAYOUT_SOA1); \
+        else EVK_LAUNCH(S, BL, LAYOUT_AOS);                    \
+    } while (0)
+        if (sink == SINK_QUAD) { if (bil) EVK_DISPATCH_L(SINK_QUAD, true); else EVK_DISPATCH_L(SINK_QUAD, false); }
+        else { if (bil) EVK_DISPATCH_L(SINK_SCALAR, true); else EVK_DISPATCH_L(SINK_SCALAR, false); }
+#undef EVK_DISPATCH_L
+#undef EVK_LAUNCH
+        EVK_CUDA(cudaGetLastError());
+    }
+    if (sink == SINK_QUAD) {
+        const int grid = grid_for(npix, 256, 8);
+        if (accum) voxel_fold_kernel<true><<<grid, 256, 0, st>>>(A.ws, A.out, npix, A.B, A.nq);
+        else voxel_fold_kernel<false><<<grid, 256, 0, st>>>(A.ws, A.out, npix, A.B, A.nq);
+        EVK_CUDA(cudaGetLastError());
+    }
+    return EVK_OK;
+}
+
+static int check_common(int64_t n, int B, int H, int W, const void *out)
+{
+    if (n < 0 || B < 1 || H < 1 || W < 1 || out == nullptr) {
+        set_error("evk_voxel: bad arguments (n=%lld B=%d H=%d W=%d out=%p)", (long long)n, B, H, W, out);
+        return EVK_E_ARG;
+    }
+    if ((int64_t)B * H * W >= ((int64_t)1 << 40)) { set_error("evk_voxel: grid too large"); return EVK_E_ARG; }
+    return EVK_OK;
+}
+
+}  // namespace evk
+
+extern "C" {
+
+size_t evk_voxel_workspace_bytes(int B, int H, int W, unsigned flags)
+{
+    (void)flags;
+    if (B < 1 || H < 1 || W < 1) return 0;
+    return (size_t)H * W * evk::quads_for_bins(B) * 4 * sizeof(float);
+}
+
+int evk_voxel_f32(const float *x, const float *y, const float *t, const float *p, int64_t n, float t0,
+                  float dt, int B, int H, int W, unsigned flags, float *out, void *workspace,
+                  size_t workspace_bytes, unsigned long long *oob, void *stream)
+{
+    using namespace evk;
+    int rc = check_common(n, B, H, W, out);
+    if (rc) return rc;
+    if (n > 0 && (!x || !y || !t || !p)) { set_error("evk_voxel_f32: null event array"); return EVK_E_ARG; }
+    VoxelArgs A{};
+    A.x = x; A.y = y; A.t = t; A.p = p; A.n = n;
+    A.t0 = t0; A.dt = dt; A.bm1 = (float)(B - 1);
+    A.B = B; A.H = H; A.W = W;
+    A.clip = (flags & EVK_CLIP) ? 1 : 0;
+    A.clipx = (float)(W - 1); A.clipy = (float)(H - 1);
+    A.out = out; A.oob = oob;
+    // choose the load layout: 16-byte body if all four arrays share their misalignment
+    const uintptr_t ax = (uintptr_t)x & 15, ay = (uintptr_t)y & 15, at = (uintptr_t)t & 15, ap = (uintptr_t)p & 15;
+    int layout = LAYOUT_SOA1;
+    if (ax == ay && ay == at && at == ap && (ax & 3) == 0) {
+        layout = LAYOUT_SOA4;
+        A.head = ((16 - ax) & 15) >> 2;
+        if (A.head > n) A.head = n;
+    }
+    return launch_voxel(A, flags, layout, static_cast<cudaStream_t>(stream), workspace, workspace_bytes);
+}
+
+int evk_voxel_aos_f32(const float *ev, int64_t n, float t0, float dt, int B, int H, int W, unsigned flags,
+                      float *out, void *workspace, size_t workspace_bytes, unsigned long long *oob,
+                      void *stream)
+{
+    using namespace evk;
+    int rc = check_common(n, B, H, W, out);
+    if (rc) return rc;
+    if (n > 0 && (!ev || ((uintptr_t)ev & 15))) { set_error("evk_voxel_aos_f32: ev must be a 16-byte aligned device pointer"); return EVK_E_ARG; }
+    VoxelArgs A{};
+    A.x = ev; A.n = n;
+    A.t0 = t0; A.dt = dt; A.bm1 = (float)(B - 1);
+    A.B = B; A.H = H; A.W = W;
+    A.clip = (flags & EVK_CLIP) ? 1 : 0;
+    A.clipx = (float)(W - 1); A.clipy = (float)(H - 1);
+    A.out = out; A.oob = oob;
+    return launch_voxel(A, flags, LAYOUT_AOS, static_cast<cudaStream_t>(stream), workspace, workspace_bytes);
+}
+
+int evk_voxel_windows_f32(const float *x, const float *y, const float *t, const float *p, const int64_t *offsets,
+                          int n_windows, int64_t n_events_hint, int B, int H, int W, unsigned flags, float *out,
+                          unsigned long long *oob, void *stream)
+{
+    using namespace evk;
+    if (n_windows < 0 || B < 1 || H < 1 || W < 1 || !out || (n_windows > 0 && (!x || !y || !t || !p || !offsets))) {
+        set_error("evk_voxel_windows_f32: bad arguments");
+        return EVK_E_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!(flags & EVK_ACCUMULATE))
+        EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)n_windows * B * H * W * sizeof(float), st));
+    if (n_windows == 0) return EVK_OK;
+    VoxelArgs A{};
+    A.x = x; A.y = y; A.t = t; A.p = p;
+    A.bm1 = (float)(B - 1);
+    A.B = B; A.H = H; A.W = W; A.nq = quads_for_bins(B);
+    A.out = out; A.oob = oob;
+    // slices per window: enough CTAs to fill the machine, at most one slice per 2K events
+    int64_t per = n_events_hint > 0 ? n_events_hint / n_windows : 8192;
+    int64_t slices = (per + 2047) / 2048;
+    const int64_t fill = ((int64_t)num_sms() * 8 + n_windows - 1) / n_windows;
+    if (slices > fill) slices = fill;
+    if (slices < 1) slices = 1;
+    if ((int64_t)n_windows * slices > 0x7fffffffLL) { set_error("evk_voxel_windows_f32: too many windows"); return EVK_E_ARG; }
+    voxel_windows_kernel<<<(unsigned)(n_windows * slices), kThreads, 0, st>>>(A, offsets, n_windows, (int)slices);
+    EVK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+}  // extern "C"

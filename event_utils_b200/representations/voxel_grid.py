@@ -1,0 +1,214 @@
+"""Voxel-grid builders -- drop-in for the reference's lib/representations/voxel_grid.py.
+
+Same signatures and return types; the work is one CUDA pass over the events
+(csrc/evk_voxel.cu) instead of B passes of ~15 temporaries each.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib, config
+from . import _events as E
+from .image import events_to_image, events_to_image_torch  # noqa: F401  (re-exported like the reference)
+
+
+def _voxel_device(x, y, t, p, t0, dt, B, H, W, flags=0, aos=None, out=None):
+    """Launch the voxel kernels on device-resident f32 arrays; returns (B,H,W) f32 on that device."""
+    L = _lib.lib()
+    dev = (aos if aos is not None else x).device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        flags |= E.variant_flag()
+        ws_bytes = L.evk_voxel_workspace_bytes(B, H, W, flags)
+        ws = _lib.scratch("voxel_ws", ws_bytes, dev)
+        oob = _lib.oob_counter(dev)
+        if aos is not None:
+            _lib.check(L.evk_voxel_aos_f32(_lib.ptr(aos), aos.shape[0], t0, dt, B, H, W, flags, _lib.ptr(out),
+                                           _lib.ptr(ws), ws.numel(), _lib.ptr(oob), _lib.stream()))
+        else:
+            _lib.check(L.evk_voxel_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), x.shape[0], t0, dt,
+                                       B, H, W, flags, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.ptr(oob),
+                                       _lib.stream()))
+        E.raise_if_oob(oob, "voxel grid", (B, H, W))
+    return out
+
+
+def _times_f32(ts, dev):
+    """Timestamps as f32 + the two scalars voxel_grid.py:133-134 derives from them.
+    Integer timestamps are made relative first (exact), like the reference's int arithmetic."""
+    ts = E.as_tensor(ts).reshape(-1)
+    if ts.dtype == torch.float32:
+        t = ts.to(dev, non_blocking=True).contiguous()
+        first, last = (float(v) for v in torch.stack((ts[0], ts[-1])).tolist())
+        t0 = np.float32(first)
+        dt = np.float32(last) - np.float32(first)
+        return t, float(t0), float(dt)
+    if ts.dtype == torch.float64:
+        # the reference fails here: index_put_ f64 weights into an f32 image (image.py:95)
+        raise RuntimeError("Index put requires the source and destination dtypes match, "
+                           "got Float for the destination and Double for the source.")
+    ts = ts.to(dev, non_blocking=True)
+    if not ts.dtype.is_floating_point:
+        rel = (ts - ts[0])
+        dt = np.float32(float(rel[-1].item()))
+        return rel.to(torch.float32).contiguous(), 0.0, float(dt)
+    t = ts.to(torch.float32).contiguous()
+    return t, float(t[0].item()), float((t[-1] - t[0]).item())
+
+
+def events_to_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240), temporal_bilinear=True):
+    """
+    Turn a set of events into a (B,H,W) float32 voxel grid with temporal bilinear interpolation.
+    Drop-in for lib/representations/voxel_grid.py:114-153.
+    @param xs, ys, ts, ps event components (tensors on any device, or numpy arrays)
+    @param B number of bins
+    @param device device of the returned grid (default: the device of xs)
+    @param sensor_size (H, W)
+    @param temporal_bilinear only True is defined (the reference's False branch raises NameError)
+    @returns voxel grid tensor
+    """
+    assert(len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps))
+    if not temporal_bilinear:
+        raise NotImplementedError("temporal_bilinear=False is undefined in the reference "
+                                  "(voxel_grid.py:144-147 raises NameError)")
+    if len(xs) == 0:
+        raise IndexError("index -1 is out of bounds for dimension 0 with size 0")
+    xs_t = E.as_tensor(xs)
+    if device is None:
+        device = xs_t.device
+    device = torch.device(device)
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    B = int(B)
+    ps_t = E.as_tensor(ps)
+    if ps_t.dtype == torch.float64:
+        raise RuntimeError("Index put requires the source and destination dtypes match, "
+                           "got Float for the destination and Double for the source.")
+    dev = E.compute_device(xs, ys, ts, ps)
+
+    host_f32 = all(isinstance(a, torch.Tensor) and not a.is_cuda and a.dtype == torch.float32
+                   and a.dim() == 1 and a.is_contiguous() for a in (xs, ys, ts, ps))
+    if host_f32:
+        # host arrays: chunked, double-buffered H2D copy overlapped with the scatter (evk_host.cu)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            t0 = np.float32(ts[0].item())
+            dt = np.float32(ts[-1].item()) - t0
+            out = torch.empty((B, H, W), dtype=torch.float32, pin_memory=True)
+            bad = ctypes.c_ulonglong(0)
+            _lib.check(L.evk_voxel_host_f32(_lib.pipeline(), _lib.ptr(xs), _lib.ptr(ys), _lib.ptr(ts), _lib.ptr(ps),
+                                            xs.shape[0], float(t0), float(dt), B, H, W, 0, _lib.ptr(out),
+                                            ctypes.byref(bad)))
+        if bad.value and config.check_index_errors:
+            raise IndexError("%d events index outside the voxel grid of shape %s" % (bad.value, (B, H, W)))
+        return out if device.type == "cpu" else out.to(device)
+
+    aos = E.aos_base(xs, ys, ts, ps) if isinstance(xs, torch.Tensor) and xs.is_cuda else None
+    if aos is not None:
+        first, last = aos[0, 2], aos[-1, 2]
+        fl = torch.stack((first, last)).tolist()
+        t0 = np.float32(fl[0])
+        dt = np.float32(fl[1]) - t0
+        grid = _voxel_device(None, None, None, None, float(t0), float(dt), B, H, W, aos=aos)
+    else:
+        t, t0, dt = _times_f32(ts, dev)
+        grid = _voxel_device(E.coords_f32(xs, dev), E.coords_f32(ys, dev), t, E.weights_f32(ps_t, dev),
+                             t0, dt, B, H, W)
+    return grid if grid.device == device else grid.to(device)
+
+
+def events_to_neg_pos_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240), temporal_bilinear=True):
+    """
+    Positive and negative events in separate voxel grids; drop-in for voxel_grid.py:155-182
+    (weights [p>0] and [p<=0]).
+    @returns (voxel_pos, voxel_neg)
+    """
+    ps_t = E.as_tensor(ps)
+    dev = E.compute_device(xs, ys, ts, ps)
+    psd = ps_t.to(dev)
+    pos = (psd > 0).to(torch.float32)
+    neg = (psd <= 0).to(torch.float32)
+    xs_d, ys_d, ts_d = (E.as_tensor(a).to(dev) for a in (xs, ys, ts))
+    if device is None:
+        device = E.as_tensor(xs).device
+    vp = events_to_voxel_torch(xs_d, ys_d, ts_d, pos, B, device=device, sensor_size=sensor_size,
+                               temporal_bilinear=temporal_bilinear)
+    vn = events_to_voxel_torch(xs_d, ys_d, ts_d, neg, B, device=device, sensor_size=sensor_size,
+                               temporal_bilinear=temporal_bilinear)
+    return vp, vn
+
+
+def events_to_voxel(xs, ys, ts, ps, B, sensor_size=(180, 240), temporal_bilinear=True):
+    """
+    numpy flavour; drop-in for voxel_grid.py:184-217: integer xs/ys, float64 (B,H,W) result.
+    Coordinates equal to H or W fall on the (H+1,W+1) canvas' pad row/column and are dropped
+    (image.py:17,44); anything negative or larger raises ValueError like ravel_multi_index.
+    The accumulation itself runs in f32 on the GPU (<= 1e-6 relative of the f64 reference).
+    """
+    assert(len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps))
+    if not temporal_bilinear:
+        raise NotImplementedError("temporal_bilinear=False is undefined in the reference "
+                                  "(voxel_grid.py:210-214 raises UnboundLocalError)")
+    xs, ys = np.asarray(xs).squeeze(), np.asarray(ys).squeeze()
+    if not (np.issubdtype(xs.dtype, np.integer) and np.issubdtype(ys.dtype, np.integer)):
+        raise TypeError("only int indices permitted")
+    ts, ps = np.asarray(ts, dtype=np.float64).reshape(-1), np.asarray(ps, dtype=np.float64).reshape(-1)
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    dev = E.compute_device()
+    with torch.cuda.device(dev):
+        x = torch.from_numpy(np.ascontiguousarray(xs).reshape(-1)).to(dev)
+        y = torch.from_numpy(np.ascontiguousarray(ys).reshape(-1)).to(dev)
+        lo = min(int(x.min()), int(y.min()))
+        if lo < 0 or int(x.max()) > W or int(y.max()) > H:
+            print("Issue with input arrays! minx={}, maxx={}, miny={}, maxy={}, sensor_size={}".format(
+                int(x.min()), int(x.max()), int(y.min()), int(y.max()), (H + 1, W + 1)))
+            raise ValueError
+        # timestamps relative to the first one in f64, THEN f32: absolute stamps do not fit f32
+        trel = torch.from_numpy(ts - ts[0]).to(dev).to(torch.float32)
+        dt = float(np.float32(ts[-1] - ts[0]))
+        p = torch.from_numpy(ps).to(dev).to(torch.float32)
+        grid = _voxel_device(x.to(torch.float32), y.to(torch.float32), trel, p, 0.0, dt, int(B), H + 1, W + 1)
+        return grid[:, :H, :W].double().cpu().numpy()
+
+
+def events_to_neg_pos_voxel(xs, ys, ts, ps, B, sensor_size=(180, 240), temporal_bilinear=True):
+    """Drop-in for voxel_grid.py:219-243 (weights np.where(ps,1,0) / np.where(ps,0,1))."""
+    ps = np.asarray(ps)
+    pos_weights = np.where(ps, 1, 0)
+    neg_weights = np.where(ps, 0, 1)
+    voxel_pos = events_to_voxel(xs, ys, ts, pos_weights, B, sensor_size=sensor_size, temporal_bilinear=temporal_bilinear)
+    voxel_neg = events_to_voxel(xs, ys, ts, neg_weights, B, sensor_size=sensor_size, temporal_bilinear=temporal_bilinear)
+    return voxel_pos, voxel_neg
+
+
+def events_to_voxel_timesync_torch(xs, ys, ts, ps, B, t0, t1, device=None, np_ts=None,
+        sensor_size=(180, 240), temporal_bilinear=True):
+    """Voxel grid of the events between t0 and t1; drop-in for voxel_grid.py:82-112."""
+    assert(t1 > t0)
+    if np_ts is None:
+        np_ts = ts.cpu().numpy()
+    if device is None:
+        device = xs.device
+    start_idx = np.searchsorted(np_ts, t0)
+    end_idx = np.searchsorted(np_ts, t1)
+    assert(start_idx < end_idx)
+    return events_to_voxel_torch(xs[start_idx:end_idx], ys[start_idx:end_idx], ts[start_idx:end_idx],
+                                 ps[start_idx:end_idx], B, device, sensor_size=sensor_size,
+                                 temporal_bilinear=temporal_bilinear)
+
+
+def voxel_grids_fixed_n_torch(xs, ys, ts, ps, B, n, sensor_size=(180, 240), temporal_bilinear=True):
+    """List of voxel grids of n events each; drop-in for voxel_grid.py:37-57 (windows
+    range(0, len(xs)-n, n))."""
+    return [events_to_voxel_torch(xs[i:i + n], ys[i:i + n], ts[i:i + n], ps[i:i + n], B,
+                                  sensor_size=sensor_size, temporal_bilinear=temporal_bilinear)
+            for i in range(0, len(xs) - n, n)]
+
+
+def voxel_grids_fixed_t_torch(xs, ys, ts, ps, B, t, sensor_size=(180, 240), temporal_bilinear=True):
+    """List of voxel grids of temporal width t; drop-in for voxel_grid.py:59-80."""
+    np_ts = ts.cpu().numpy()
+    return [events_to_voxel_timesync_torch(xs, ys, ts, ps, B, t_start, t_start + t, np_ts=np_ts,
+                                           sensor_size=sensor_size, temporal_bilinear=temporal_bilinear)
+            for t_start in np.arange(ts[0].item(), ts[-1].item() - t, t)]

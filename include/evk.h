@@ -1,0 +1,215 @@
+/*
+ * evk.h -- C ABI of libevk.so: B200 (sm_100a) kernels for the event_utils hot path.
+ *
+ * The reference (TimoStoff/event_utils) is pure Python and has NO FFI of its own; its
+ * "operator API" is a set of module-level Python functions.  Each entry
+ * point below is what a ctypes/cffi binding for one of those functions binds to; the reference
+ * call site it replaces is cited as file:line (paths relative to the reference tree).
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative EVK_E_* code on failure; it never throws
+ *     across the ABI.  evk_last_error() returns a thread-local human-readable message.
+ *   - unless the name says `_host`, all data pointers are caller-owned DEVICE pointers and all
+ *     work is enqueued on the caller's stream (a cudaStream_t passed as void*); nothing
+ *     synchronises.  No torch types anywhere.
+ *   - `oob` (may be NULL) is a device counter the kernels increment once per event whose index
+ *     falls outside the output (the reference raises IndexError for those, image.py:96-99);
+ *     such events are never written.  The caller zeroes and reads it.
+ *   - outputs are fully overwritten unless EVK_ACCUMULATE is set.
+ */
+#ifndef EVK_H_
+#define EVK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define EVK_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define EVK_OK 0
+#define EVK_E_ARG (-1)       /* bad argument (null pointer, negative size, ...) */
+#define EVK_E_CUDA (-2)      /* a CUDA runtime call failed, see evk_last_error() */
+#define EVK_E_WORKSPACE (-3) /* workspace too small */
+#define EVK_E_DEVICE (-4)    /* not an sm_100 device */
+#define EVK_E_UNSUPPORTED (-5)
+
+/* flags shared by the scatter entry points */
+#define EVK_ACCUMULATE 0x1u   /* add into `out` instead of overwriting it */
+#define EVK_BILINEAR 0x2u     /* spatial 4-tap bilinear splat instead of nearest (truncate) */
+#define EVK_CLIP 0x4u         /* events_to_image_torch(clip_out_of_range=True) semantics */
+/* kernel variant selection, bits 8..11 (0 = pick automatically) */
+#define EVK_VARIANT_SHIFT 8
+#define EVK_VARIANT_MASK (0xFu << EVK_VARIANT_SHIFT)
+#define EVK_VARIANT_AUTO (0u << EVK_VARIANT_SHIFT)
+#define EVK_VARIANT_GLOBAL_RED (1u << EVK_VARIANT_SHIFT) /* one scalar red.global.add.f32 per tap */
+#define EVK_VARIANT_VECTOR_RED (2u << EVK_VARIANT_SHIFT) /* one red.global.add.v4.f32 per tap pair, quad-layout workspace */
+#define EVK_VARIANT_SMEM_TILE (3u << EVK_VARIANT_SHIFT)  /* shared-memory tile privatisation + bulk reduce-store */
+#define EVK_VARIANT_WARP_AGG (4u << EVK_VARIANT_SHIFT)   /* warp-aggregated (match.any) global reds, for hot-spot streams */
+
+/* cmax flags */
+#define EVK_CMAX_WANT_GRAD 0x10u    /* also produce the analytic gradient */
+#define EVK_CMAX_ABS_POLARITY 0x20u /* use_polarity=False: p <- |p| (objectives.py:184-185) */
+#define EVK_CMAX_NO_CHANNEL_MIX 0x40u /* do NOT reproduce the 3-D blur channel mixing (objectives.py:253) */
+
+int evk_version(void);
+const char *evk_last_error(void);
+/* 0 if the current device is compute capability 10.x, EVK_E_DEVICE otherwise */
+int evk_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Voxel grid.  Replaces events_to_voxel_torch, lib/representations/voxel_grid.py:114-153
+ * (per-bin loop :136-151 -> events_to_image_torch image.py:88-95 -> index_put_).
+ *   tau = ((t - t0) / dt) * (B-1)   (f32, this order);  V[b, trunc(y), trunc(x)] += p*max(0,1-|tau-b|)
+ * t0, dt are explicit so that a sharded caller can pass the GLOBAL values (voxel_grid.py:133-134
+ * derives them from ts[0], ts[-1]).  x,y,t,p: n floats each (SoA), any 4-byte alignment.
+ * out: B*H*W floats, layout [B][H][W].
+ * With EVK_BILINEAR the spatial part is a 4-tap bilinear splat on the same (H,W) grid
+ * (trilinear voxel; an extension, not a reference function).
+ * workspace: evk_voxel_workspace_bytes() bytes (may be 0/NULL for the GLOBAL_RED variant).
+ * --------------------------------------------------------------------------------------------- */
+size_t evk_voxel_workspace_bytes(int B, int H, int W, unsigned flags);
+int evk_voxel_f32(const float *x, const float *y, const float *t, const float *p, int64_t n,
+                  float t0, float dt, int B, int H, int W, unsigned flags, float *out,
+                  void *workspace, size_t workspace_bytes, unsigned long long *oob, void *stream);
+
+/* Same, events given as one interleaved (N,4) [x,y,t,p] f32 array (the data-loader layout,
+ * lib/data_loaders/base_dataset.py:306,510); ev must be 16-byte aligned. */
+int evk_voxel_aos_f32(const float *ev, int64_t n, float t0, float dt, int B, int H, int W,
+                      unsigned flags, float *out, void *workspace, size_t workspace_bytes,
+                      unsigned long long *oob, void *stream);
+
+/* Batched windows (voxel_grids_fixed_n_torch, voxel_grid.py:37-57; BaseVoxelDataset windows,
+ * base_dataset.py:322-367): window w covers events [offsets[w], offsets[w+1]) and writes
+ * out[w] ([n_windows][B][H][W]); t0/dt per window are taken from the window's first / last
+ * timestamp exactly as voxel_grid.py:133-134 does.  offsets: n_windows+1 int64 on the device.
+ * n_events_hint: total number of events covered (0 = unknown), used only to size the launch. */
+int evk_voxel_windows_f32(const float *x, const float *y, const float *t, const float *p,
+                          const int64_t *offsets, int n_windows, int64_t n_events_hint, int B, int H,
+                          int W, unsigned flags, float *out, unsigned long long *oob, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Event image.  Replaces events_to_image_torch, lib/representations/image.py:46-100 and
+ * interpolate_to_image, image.py:102-115.
+ *   nearest : img[trunc(y)*m, trunc(x)*m] += p           (m = [x<clipx][y<clipy] with EVK_CLIP;
+ *             NOTE the weight is not masked, image.py:94-95)
+ *   bilinear: 4-tap splat of p*m at floor(x)*m, floor(y)*m with the unmasked fractions
+ * Himg, Wimg are the CANVAS sizes (sensor+1 when bilinear and padding, image.py:64-67); the
+ * caller derives clipx/clipy as image.py:73-74 does.  `fill` is the background (`default`).
+ * --------------------------------------------------------------------------------------------- */
+size_t evk_image_workspace_bytes(int Himg, int Wimg, unsigned flags);
+int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int Himg, int Wimg,
+                  float clipx, float clipy, unsigned flags, float fill, float *out,
+                  void *workspace, size_t workspace_bytes, unsigned long long *oob, void *stream);
+
+/* Integer-exact event-count image (nearest, weight +1 per event): out is u32 [Himg][Wimg].
+ * The bit-exact form of events_to_image(_torch) for ps == 1 (image.py:37-38, :95). */
+int evk_count_u32(const float *x, const float *y, int64_t n, int Himg, int Wimg, float clipx,
+                  float clipy, unsigned flags, unsigned int *out, unsigned long long *oob,
+                  void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The reference's lower-level splat / gather helpers, for callers that use them directly.
+ *   evk_splat_idx_f32       interpolate_to_image, lib/representations/image.py:102-115
+ *                           (in place on img [H][W]; px,py int64; dx,dy,w f32)
+ *   evk_splat_drv_idx_f32   interpolate_to_derivative_img, image.py:117-136
+ *                           (in place on dimg [K][H][W]; w1,w2 are [K][n])
+ *   evk_image_drv_f32       events_to_image_drv, image.py:162-217 after its f64->f32 casts
+ *                           (:179-183): x,y,p f32, Jacobians jx,jy [K][n] f32 (K may be 0),
+ *                           writes img [Himg][Wimg] and dimg [K][Himg][Wimg]
+ *   evk_gather_bilinear_f64 image_to_event_weights, image.py:138-160 (f64, img [H][W] f64)
+ * --------------------------------------------------------------------------------------------- */
+int evk_splat_idx_f32(const int64_t *px, const int64_t *py, const float *dx, const float *dy,
+                      const float *w, int64_t n, int H, int W, float *img, unsigned long long *oob,
+                      void *stream);
+int evk_splat_drv_idx_f32(const int64_t *px, const int64_t *py, const float *dx, const float *dy,
+                          const float *w1, const float *w2, int K, int64_t n, int H, int W,
+                          float *dimg, unsigned long long *oob, void *stream);
+int evk_image_drv_f32(const float *x, const float *y, const float *p, const float *jx, const float *jy,
+                      int K, int64_t n, int Himg, int Wimg, float clipx, float clipy, unsigned flags,
+                      float *img, float *dimg, unsigned long long *oob, void *stream);
+int evk_gather_bilinear_f64(const double *x, const double *y, int64_t n, const double *img, int H,
+                            int W, double *out, unsigned long long *oob, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense-flow warp.  Replaces warp_events_flow_torch, lib/transforms/optic_flow.py:5-46
+ * (F.grid_sample bilinear, align_corners=True, zero padding, :37-44).
+ * flow: [2][H][W] f32.  xw/yw: n floats.  x' = x + u(x,y)*(t-t0), y' = y + v(x,y)*(t-t0).
+ * --------------------------------------------------------------------------------------------- */
+int evk_warp_flow_f32(const float *x, const float *y, const float *t, int64_t n, const float *flow,
+                      int H, int W, float t0, float *xw, float *yw, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Contrast maximisation, fused: linvel warp -> bounds mask -> bilinear IWE (+ derivative
+ * images) -> Gaussian blur -> variance objective (+ analytic gradient).
+ * Replaces variance_objective.evaluate_function / evaluate_gradient,
+ * lib/contrast_max/objectives.py:211-264, i.e. get_iwe :165-199, linvel_warp.warp warps.py:51-61,
+ * events_bounds_mask event_util.py:15-28, events_to_image_drv image.py:162-217,
+ * scipy gaussian_filter + np.var / np.mean objectives.py:233-234,253-262.
+ *   x,y,t,p : n doubles each (the reference API hands f64 numpy arrays) -- `_f64`, parity mode
+ *             n floats each, t already relative to t_ref  -- `_f32`, fast mode
+ *   (Hm,Wm) : img_size of the bounds mask;  (Hs,Ws): sensor size of the IWE canvas, which is
+ *             (Hs+1)x(Ws+1); the reference always uses (180,240) (objectives.py:191-192).
+ *   result  : 8 doubles on the device: f, g[0], g[1], sum(IWE), #events indexing outside the
+ *             canvas (the reference's IndexError), var, and the un-mixed 2-D gradient (2)
+ *             (g = 0 without EVK_CMAX_WANT_GRAD)
+ *   iwe_out : optional (Hs+1)*(Ws+1) floats (the un-blurred IWE), diwe_out optional 2x that.
+ *   p_scale : polarity multiplier (1, or 100 for the adaptive-lifespan branch objectives.py:225)
+ *   workspace: evk_cmax_workspace_bytes(Hs,Ws) bytes of device scratch, 256-byte aligned.
+ * --------------------------------------------------------------------------------------------- */
+size_t evk_cmax_workspace_bytes(int Hs, int Ws);
+int evk_cmax_linvel_variance_f64(const double *x, const double *y, const double *t, const double *p,
+                                 int64_t n, double p_scale, double vx, double vy, double t_ref,
+                                 int Hm, int Wm, int Hs, int Ws, double sigma, unsigned flags,
+                                 double *result,
+                                 float *iwe_out, float *diwe_out, void *workspace,
+                                 size_t workspace_bytes, void *stream);
+int evk_cmax_linvel_variance_f32(const float *x, const float *y, const float *t_rel, const float *p,
+                                 int64_t n, float p_scale, float vx, float vy, int Hm, int Wm, int Hs,
+                                 int Ws,
+                                 double sigma, unsigned flags, double *result, float *iwe_out,
+                                 float *diwe_out, void *workspace, size_t workspace_bytes,
+                                 void *stream);
+
+/* The objective (and gradient) of a PRECOMPUTED image of warped events, i.e. the iwe= / d_iwe=
+ * form of evaluate_function / evaluate_gradient (objectives.py:211-264 with iwe given; used by
+ * grid_cmax, events_cmax.py:68-70).  iwe: [Hc][Wc] f32, diwe: [2][Hc][Wc] f32 or NULL. */
+int evk_variance_objective_f32(const float *iwe, const float *diwe, int Hc, int Wc, double sigma,
+                               unsigned flags, double *result, void *workspace,
+                               size_t workspace_bytes, void *stream);
+
+/* Objective only (f) for a dense-flow warp: warp_events_flow_torch + bilinear IWE
+ * (lib/visualization/draw_flow.py:18-21) + the variance objective.  flow: [2][Hs][Ws]. */
+int evk_cmax_flow_variance_f32(const float *x, const float *y, const float *t, const float *p,
+                               int64_t n, const float *flow, float t0, int Hs, int Ws, double sigma,
+                               unsigned flags, double *result, float *iwe_out, void *workspace,
+                               size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer pipeline: the same voxel build for events living in HOST memory (pinned memory
+ * gives full PCIe bandwidth).  Events are streamed in chunks through a double-buffered device
+ * staging area so the H2D copy of chunk k+1 overlaps the scatter of chunk k; the finished grid
+ * is copied back to `out_host`.  Synchronous (returns when out_host is complete).
+ * *oob_host receives the out-of-range event count.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct evk_pipeline evk_pipeline_t;
+int evk_pipeline_create(evk_pipeline_t **pipe, int64_t chunk_events);
+void evk_pipeline_destroy(evk_pipeline_t *pipe);
+int evk_voxel_host_f32(evk_pipeline_t *pipe, const float *x, const float *y, const float *t,
+                       const float *p, int64_t n, float t0, float dt, int B, int H, int W,
+                       unsigned flags, float *out_host, unsigned long long *oob_host);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVK_H_ */

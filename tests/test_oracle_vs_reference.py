@@ -1,0 +1,67 @@
+"""The oracle against the UNMODIFIED reference executed in this container (skipped where
+/root/reference does not exist, i.e. on the GPU box).  Larger, randomised companions of the
+committed golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close_to_max, make_events
+from oracle import ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_loader.load()
+
+
+@pytest.mark.parametrize("seed,n,B,H,W", [(1, 200000, 5, 260, 346), (2, 50000, 7, 180, 240), (3, 1000, 2, 10, 12)])
+def test_voxel_torch_bit_exact(ref, oracle, seed, n, B, H, W):
+    x, y, t, p = make_events(seed, n, H, W)
+    v = ref.voxel_grid.events_to_voxel_torch(*(torch.from_numpy(a) for a in (x, y, t, p)), B, sensor_size=(H, W)).numpy()
+    torch.set_num_threads(1)
+    assert_close_to_max(oracle.voxel_f32(x, y, t, p, B, (H, W)), v, 1e-6)
+
+
+def test_voxel_numpy(ref, oracle):
+    rng = np.random.default_rng(1234)
+    n = 100000
+    xs, ys = rng.integers(0, 346, n), rng.integers(0, 260, n)
+    ts = np.sort(rng.random(n))
+    ps = rng.integers(0, 2, n) * 2 - 1.0
+    v = ref.voxel_grid.events_to_voxel(xs, ys, ts, ps, 5, sensor_size=(260, 346))
+    assert_close_to_max(oracle.voxel_f64(xs, ys, ts, ps, 5, (260, 346)), v, 1e-12)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(interpolation='bilinear'), dict(padding=False),
+                                dict(interpolation='bilinear', padding=False), dict(clip_out_of_range=False)])
+def test_image_torch(ref, oracle, kw):
+    x, y, t, p = make_events(5, 100000, 180, 240, pol="real")
+    if kw.get("clip_out_of_range", True):
+        x[::7] += 4
+    a = ref.image.events_to_image_torch(torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(p), **kw).numpy()
+    assert_close_to_max(oracle.image_torch_f32(x, y, p, **kw), a, 2e-6)
+
+
+def test_flow(ref, oracle):
+    x, y, t, p = make_events(6, 50000, 180, 240)
+    flow = torch.randn(2, 180, 240) * 30
+    xw, yw = ref.optic_flow.warp_events_flow_torch(*(torch.from_numpy(a) for a in (x, y, t, p)), flow)
+    xo, yo = oracle.warp_flow_f32(x, y, t, flow.numpy())
+    assert_close_to_max(xo, xw.numpy(), 1e-6)
+    assert_close_to_max(yo, yw.numpy(), 1e-6)
+
+
+@pytest.mark.parametrize("sigma", [1.0, 0.0, 3.0])
+def test_cmax(ref, oracle, sigma):
+    x, y, t, p = make_events(7, 100000, 180, 240, dtype=np.float64)
+    obj, warp = ref.objectives.variance_objective(), ref.warps.linvel_warp()
+    for params in [(30.0, -20.0), (-400.0, 900.0)]:
+        f = obj.evaluate_function(params, x, y, t, p, warp, (180, 240), sigma)
+        g = obj.evaluate_gradient(params, x, y, t, p, warp, (180, 240), sigma)
+        fo, go = oracle.cmax_variance(params, x, y, t, p, blur_sigma=sigma)
+        assert abs(fo - f) <= 1e-6 * abs(f)
+        iwe, d = ref.objectives.get_iwe(params, x, y, t, p, warp, (180, 240), compute_gradient=True)
+        scale = np.sqrt(np.mean((2 * (iwe - iwe.mean())) ** 2) * np.mean(d ** 2))
+        assert np.abs(go - g).max() <= 1e-5 * scale
