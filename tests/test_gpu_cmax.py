@@ -1,0 +1,209 @@
+"""Parity of the fused contrast-maximisation kernel with the oracle and the reference goldens."""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import assert_close_to_max, golden, make_events
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _reset():
+    from event_utils_b200.contrast_max import objectives
+    objectives.precision = "f64"
+    objectives.clear_cache()
+    yield
+    objectives.precision = "f64"
+    objectives.clear_cache()
+
+
+def grad_scale(iwe, d):
+    """scale-normalised gradient tolerance of SURVEY.md section 8d"""
+    return np.sqrt(np.mean((2 * (iwe - iwe.mean())) ** 2) * np.mean(d.astype(np.float64) ** 2))
+
+
+def test_golden_f_and_g():
+    from event_utils_b200.contrast_max.objectives import variance_objective
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    g = golden("cmax")
+    obj, warp = variance_objective(), linvel_warp()
+    scenes = {0: "c9", 1: "lat"}
+    for row in g["evals"]:
+        s, vx, vy, sigma, f_ref, g0, g1 = row
+        tag = scenes[int(s)]
+        ev = [g[tag + k] for k in ("_x", "_y", "_t", "_p")]
+        f = obj.evaluate_function((vx, vy), *ev, warp, (180, 240), sigma)
+        gr = obj.evaluate_gradient((vx, vy), *ev, warp, (180, 240), sigma)
+        assert isinstance(f, float) and isinstance(gr, np.ndarray) and gr.shape == (2,)
+        assert abs(f - f_ref) <= 1e-5 * abs(f_ref) + 1e-12, (tag, vx, vy, sigma, f, f_ref)
+        gref = np.array([g0, g1])
+        # scale-normalised bound (1e-5 * sqrt(mean((2(I-mu))^2) mean(D^2))), plus the relative
+        # bound on the structured scene where |g| is not ~0
+        assert np.abs(gr - gref).max() <= 1e-5 * max(np.abs(gref).max(), 1e-4), (tag, vx, vy, sigma, gr, gref)
+    # keyword calling convention (grid_search_initial, events_cmax.py:301-302)
+    ev = [g["lat" + k] for k in ("_x", "_y", "_t", "_p")]
+    f_kw = obj.evaluate_function(params=(45.0, -20.0), xs=ev[0], ys=ev[1], ts=ev[2], ps=ev[3], warpfunc=warp,
+                                 img_size=(180, 240), blur_sigma=1.0)
+    f_pos = obj.evaluate_function((45.0, -20.0), *ev, warp, (180, 240), 1.0)
+    assert f_kw == f_pos
+    # default blur (blur_sigma=None -> default_blur = 1.0)
+    assert obj.evaluate_function((45.0, -20.0), *ev, warp, (180, 240), None) == f_pos
+
+
+def test_get_iwe_and_precomputed_forms():
+    from event_utils_b200.contrast_max.objectives import get_iwe, variance_objective
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    g = golden("cmax")
+    ev = [g["lat" + k] for k in ("_x", "_y", "_t", "_p")]
+    warp, obj = linvel_warp(), variance_objective()
+    iwe, d = get_iwe((45.0, -20.0), *ev, warp, (180, 240), compute_gradient=True)
+    assert iwe.dtype == np.float32 and iwe.shape == (181, 241) and d.shape == (2, 181, 241)
+    assert_close_to_max(iwe, g["lat_iwe"], 1e-5)
+    assert_close_to_max(d, g["lat_diwe"], 1e-5)
+    iwe0, d0 = get_iwe((45.0, -20.0), *ev, warp, (180, 240))
+    assert d0 is None
+    assert_close_to_max(iwe0, g["lat_iwe"], 1e-5)
+    iwe2, _ = get_iwe((45.0, -20.0), *ev, warp, (120, 200), use_polarity=False)
+    assert_close_to_max(iwe2, g["lat_iwe_abs_small"], 1e-5)
+    # generic (non-fused) path: a user-defined warp object without `fused_kind`
+    class my_warp(linvel_warp):
+        fused_kind = None
+    iwe3, d3, (xw, yw), contrast = get_iwe((45.0, -20.0), *ev, my_warp(), (180, 240), compute_gradient=True,
+                                           return_events=True, return_per_event_contrast=True)
+    assert_close_to_max(iwe3, g["lat_iwe"], 1e-5)
+    assert_close_to_max(d3, g["lat_diwe"], 1e-5)
+    assert xw.shape == ev[0].shape and contrast.shape == ev[0].shape
+    f3 = variance_objective().evaluate_function((45.0, -20.0), *ev, my_warp(), (180, 240), 1.0)
+    assert abs(f3 - obj.evaluate_function((45.0, -20.0), *ev, warp, (180, 240), 1.0)) <= 1e-5 * abs(f3)
+    # precomputed-image forms (grid_cmax, events_cmax.py:68-70)
+    assert abs(obj.evaluate_function(iwe=g["lat_iwe"], blur_sigma=1.0) - g["pre_f"]) <= 1e-5 * abs(g["pre_f"])
+    gp = obj.evaluate_gradient(iwe=g["lat_iwe"], d_iwe=g["lat_diwe"], blur_sigma=1.0)
+    assert np.abs(gp - g["pre_g"]).max() <= 1e-5 * np.abs(g["pre_g"]).max()
+    # img_size larger than the fixed 180x240 sensor (quirk B7)
+    c9 = [g["c9" + k] for k in ("_x", "_y", "_t", "_p")]
+    fb = obj.evaluate_function((30.0, -20.0), c9[0] * 2, c9[1] * 2, c9[2], c9[3], warp, (480, 640), 1.0)
+    assert abs(fb - g["c9_f_big"]) <= 1e-5 * abs(g["c9_f_big"])
+
+
+def test_adaptive_lifespan_and_object_protocol():
+    from event_utils_b200.contrast_max.objectives import variance_objective
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    g = golden("cmax")
+    ev = [g["lat" + k] for k in ("_x", "_y", "_t", "_p")]
+    o2 = variance_objective(adaptive_lifespan=True, minimum_events=5000)
+    assert o2.has_derivative and o2.name == "variance" and o2.default_blur == 1.0
+    o2.iter_update((60.0, -35.0))
+    fa = o2.evaluate_function((50.0, -30.0), *ev, linvel_warp(), (180, 240), 1.0)
+    ga = o2.evaluate_gradient((50.0, -30.0), *ev, linvel_warp(), (180, 240), 1.0)
+    assert o2.s_idx == int(g["adapt_sidx"])
+    assert abs(fa - g["adapt_f"]) <= 1e-5 * abs(g["adapt_f"])
+    assert np.abs(ga - g["adapt_g"]).max() <= 1e-5 * np.abs(g["adapt_g"]).max()
+    o3 = copy.deepcopy(o2)
+    o3.adaptive_lifespan = False
+    assert o3.s_idx == o2.s_idx and o3._memo is None
+    w = linvel_warp()
+    assert w.dims == 2 and w.name == "linvel_warp"
+    xw, yw, jx, jy = w.warp(ev[0], ev[1], ev[2], ev[3], ev[2][-1], (3.0, 4.0), compute_grad=True)
+    assert jx.shape == (2, len(ev[0])) and np.all(jx[1] == 0) and np.all(jy[0] == 0)
+
+
+@pytest.mark.parametrize("sigma", [1.0, 0.0, 3.0])
+def test_vs_oracle_random(oracle, sigma):
+    from event_utils_b200.contrast_max.objectives import get_iwe, variance_objective
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    x, y, t, p = make_events(7, 400000, 180, 240, dtype=np.float64)
+    obj, warp = variance_objective(), linvel_warp()
+    for params in [(30.0, -20.0), (-400.0, 900.0), (0.0, 0.0)]:
+        f = obj.evaluate_function(params, x, y, t, p, warp, (180, 240), sigma)
+        gr = obj.evaluate_gradient(params, x, y, t, p, warp, (180, 240), sigma)
+        fo, go = oracle.cmax_variance(params, x, y, t, p, blur_sigma=sigma)
+        assert abs(f - fo) <= 1e-5 * abs(fo)
+        iwe, d = oracle.iwe_linvel(params, x, y, t, p, (180, 240), True)
+        assert np.abs(gr - go).max() <= 1e-5 * grad_scale(iwe, d)
+
+
+def test_f32_fast_mode(oracle):
+    from event_utils_b200.contrast_max import objectives
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    g = golden("cmax")
+    ev = [g["lat" + k] for k in ("_x", "_y", "_t", "_p")]
+    objectives.precision = "f32"
+    obj = objectives.variance_objective()
+    f = obj.evaluate_function((45.0, -20.0), *ev, linvel_warp(), (180, 240), 1.0)
+    gr = obj.evaluate_gradient((45.0, -20.0), *ev, linvel_warp(), (180, 240), 1.0)
+    fo, go = oracle.cmax_variance((45.0, -20.0), *ev, blur_sigma=1.0)
+    assert abs(f - fo) <= 1e-5 * abs(fo)
+    iwe, d = oracle.iwe_linvel((45.0, -20.0), *ev, (180, 240), True)
+    assert np.abs(gr - go).max() <= 1e-4 * grad_scale(iwe, d)   # f32 warp: documented looser bound
+
+
+def test_bfgs_survives_scipy_calling_convention():
+    """the drop-in objective driven by scipy.optimize.fmin_bfgs exactly as
+    optimize_contrast does (events_cmax.py:340-345)."""
+    import scipy.optimize as opt
+    from event_utils_b200.contrast_max.objectives import variance_objective
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    g = golden("cmax")
+    ev = [g["lat" + k] for k in ("_x", "_y", "_t", "_p")]
+    obj, warp = variance_objective(), linvel_warp()
+    x0 = np.array([40.0, -20.0])
+    obj.iter_update(x0)
+    args = (*ev, warp, (180, 240), 1.0)
+    argmax = opt.fmin_bfgs(obj.evaluate_function, x0, fprime=obj.evaluate_gradient, args=args, disp=False,
+                           callback=obj.iter_update)
+    assert obj.evaluate_function(argmax, *args) < obj.evaluate_function(x0, *args)
+    argnum = opt.fmin_bfgs(obj.evaluate_function, x0, args=args, epsilon=1, disp=False, callback=obj.iter_update)
+    assert np.linalg.norm(argnum - np.array([60.0, -35.0])) < 5.0
+
+
+def test_flow_objective_c_abi(oracle):
+    """evk_cmax_flow_variance_f32 == flow warp + bilinear IWE + variance, composed from the oracle."""
+    import torch
+    from event_utils_b200 import _lib
+    L = _lib.lib()
+    x, y, t, p = make_events(21, 300000, 180, 240)
+    fl = (np.random.default_rng(2).standard_normal((2, 180, 240)) * 20).astype(np.float32)
+    X, Y, T, P, F = (torch.from_numpy(a).cuda() for a in (x, y, t, p, fl))
+    ws = torch.empty(L.evk_cmax_workspace_bytes(180, 240), dtype=torch.uint8, device="cuda")
+    res = torch.empty(8, dtype=torch.float64, device="cuda")
+    iwe = torch.empty((181, 241), device="cuda")
+    _lib.check(L.evk_cmax_flow_variance_f32(X.data_ptr(), Y.data_ptr(), T.data_ptr(), P.data_ptr(), x.shape[0],
+                                            F.data_ptr(), float(t[-1]), 180, 240, 1.0, 0, res.data_ptr(),
+                                            iwe.data_ptr(), ws.data_ptr(), ws.numel(), None))
+    torch.cuda.synchronize()
+    xw, yw = oracle.warp_flow_f32(x, y, t, fl)
+    ref_iwe = oracle.image_torch_f32(xw, yw, p, sensor_size=(180, 240), interpolation='bilinear')
+    assert_close_to_max(iwe.cpu().numpy(), ref_iwe, 1e-5)
+    assert abs(res[0].item() - oracle.variance_f(ref_iwe, 1.0)) <= 1e-5 * abs(oracle.variance_f(ref_iwe, 1.0))
+
+
+def test_full_size_properties():
+    """BASELINE config 3 size (50 M events): properties that do not need the CPU oracle."""
+    import torch
+    from event_utils_b200 import _lib
+    L = _lib.lib()
+    n = 50_000_000
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = (torch.rand(n, device="cuda", generator=gen, dtype=torch.float64) * 238 + 0.5)
+    y = (torch.rand(n, device="cuda", generator=gen, dtype=torch.float64) * 178 + 0.5)
+    t = torch.sort(torch.rand(n, device="cuda", generator=gen, dtype=torch.float64)).values * 0.05
+    p = torch.ones(n, device="cuda", dtype=torch.float64)
+    ws = torch.empty(L.evk_cmax_workspace_bytes(180, 240), dtype=torch.uint8, device="cuda")
+    res = torch.empty(8, dtype=torch.float64, device="cuda")
+
+    def run(vx, vy, flags=_lib.CMAX_WANT_GRAD):
+        _lib.check(L.evk_cmax_linvel_variance_f64(x.data_ptr(), y.data_ptr(), t.data_ptr(), p.data_ptr(), n, 1.0, vx, vy,
+                                                  float(t[-1].item()), 180, 240, 180, 240, 1.0, flags, res.data_ptr(),
+                                                  None, None, ws.data_ptr(), ws.numel(), None))
+        return res.cpu().numpy().copy()
+    r0 = run(0.0, 0.0)
+    # zero velocity: nothing leaves the sensor, bilinear weights sum to 1 -> sum(IWE) == N
+    assert abs(r0[3] - n) <= 1e-6 * n and r0[4] == 0
+    assert r0[0] < 0
+    r1 = run(0.0, 0.0)
+    assert abs(r1[0] - r0[0]) <= 1e-5 * abs(r0[0])       # order-of-summation noise only
+    # finite-difference check of the un-blurred, un-mixed gradient at a non-trivial point
+    rg = run(30.0, -20.0, _lib.CMAX_WANT_GRAD)
+    assert np.isfinite(rg).all() and rg[3] <= n

@@ -1,0 +1,176 @@
+"""Parity of the CUDA event-image / flow-warp / helper paths with the oracle and the goldens."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close_to_max, golden, make_events
+from test_oracle_golden import IMG_VARIANTS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _reset_variant():
+    import event_utils_b200 as eu
+    yield
+    eu.config.variant = None
+
+
+def dev(*arrs):
+    return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrs]
+
+
+@pytest.mark.parametrize("variant", [None, "global_red", "vector_red", "warp_agg"])
+def test_golden_variants(variant):
+    import event_utils_b200 as eu
+    from event_utils_b200.representations.image import events_to_image_torch
+    eu.config.variant = variant
+    g = golden("image")
+    hw = tuple(int(v) for v in g["ev_HW"])
+    x, y, p = dev(g["ev_x"], g["ev_y"], g["ev_p"])
+    for tag, kw in IMG_VARIANTS.items():
+        out = events_to_image_torch(x, y, p, sensor_size=hw, **kw)
+        assert out.shape == g["img_" + tag].shape
+        assert_close_to_max(out.cpu().numpy(), g["img_" + tag], 1e-5, tag)
+    x, y, p = dev(g["in_x"], g["in_y"], g["in_p"])
+    out = events_to_image_torch(x, y, p, sensor_size=hw, clip_out_of_range=False)
+    assert np.array_equal(out.cpu().numpy(), g["img_noclip_nearest"])  # +-1 weights: bit exact
+    out = events_to_image_torch(x, y, p, sensor_size=hw, clip_out_of_range=False, interpolation='bilinear')
+    assert_close_to_max(out.cpu().numpy(), g["img_noclip_bilinear"], 1e-5)
+
+
+def test_known_answers():
+    from event_utils_b200.representations.image import events_to_image_torch
+    g = golden("image")
+    x, y, p = dev(g["k1_x"], g["k1_y"], g["k1_p"])
+    assert np.array_equal(events_to_image_torch(x, y, p, sensor_size=(4, 6)).cpu().numpy(), g["k1_default"])
+    assert np.array_equal(events_to_image_torch(x, y, p, sensor_size=(4, 6), padding=False).cpu().numpy(), g["k1_nopad"])
+    assert np.array_equal(events_to_image_torch(x, y, p, sensor_size=(4, 6), clip_out_of_range=False).cpu().numpy(), g["k1_noclip"])
+    x, y, p = dev(g["k2_x"], g["k2_y"], g["k2_p"])
+    assert np.array_equal(events_to_image_torch(x, y, p, sensor_size=(4, 6), clip_out_of_range=False).cpu().numpy(), g["k2_noclip"])
+    with pytest.raises(IndexError):
+        events_to_image_torch(*dev(np.float32([6.0]), np.float32([0.0]), np.float32([1.0])), sensor_size=(4, 6), clip_out_of_range=False)
+    x, y, p = dev(g["k4_x"], g["k4_y"], g["k4_p"])
+    for variant in (None, "vector_red"):
+        import event_utils_b200 as eu
+        eu.config.variant = variant
+        out = events_to_image_torch(x, y, p, sensor_size=(4, 6), interpolation='bilinear').cpu().numpy()
+        assert_close_to_max(out, g["k4_bilinear"], 1e-6)
+    # CPU in -> CPU out, device= honoured
+    out = events_to_image_torch(torch.from_numpy(g["k1_x"]), torch.from_numpy(g["k1_y"]), torch.from_numpy(g["k1_p"]), sensor_size=(4, 6))
+    assert not out.is_cuda and np.array_equal(out.numpy(), g["k1_default"])
+
+
+@pytest.mark.parametrize("variant", ["global_red", "vector_red", "warp_agg"])
+@pytest.mark.parametrize("bil", [False, True])
+def test_vs_oracle_large(oracle, variant, bil):
+    import event_utils_b200 as eu
+    from event_utils_b200.representations.image import events_to_image_torch
+    eu.config.variant = variant
+    H, W = 720, 1280
+    x, y, t, p = make_events(3, 1000003, H, W, pol="real")
+    x[::13] += 3
+    kw = dict(interpolation='bilinear') if bil else dict()
+    out = events_to_image_torch(*dev(x, y, p), sensor_size=(H, W), **kw).cpu().numpy()
+    assert_close_to_max(out, oracle.image_torch_f32(x, y, p, sensor_size=(H, W), **kw), 1e-5)
+
+
+def zipf_events(seed, n, H, W, s=1.0):
+    rng = np.random.default_rng(seed)
+    npx = H * W
+    w = 1.0 / np.arange(1, npx + 1) ** s
+    cdf = np.cumsum(w) / w.sum()
+    ranks = np.searchsorted(cdf, rng.random(n))
+    perm = rng.permutation(npx)
+    pix = perm[np.minimum(ranks, npx - 1)]
+    return (pix % W).astype(np.float32), (pix // W).astype(np.float32)
+
+
+@pytest.mark.parametrize("variant", ["global_red", "warp_agg"])
+def test_hot_spot_counts_bit_exact(oracle, variant):
+    """Zipf-distributed pixels (BASELINE config 4, reduced N): count image must be bit exact."""
+    import event_utils_b200 as eu
+    from event_utils_b200 import _lib
+    from event_utils_b200.representations.image import events_to_image_torch
+    eu.config.variant = variant
+    H, W, n = 720, 1280, 4_000_000
+    x, y = zipf_events(99, n, H, W)
+    p = np.ones(n, np.float32)
+    ref = oracle.image_torch_f32(x, y, p, sensor_size=(H, W), clip_out_of_range=False)
+    X, Y, P = dev(x, y, p)
+    out = events_to_image_torch(X, Y, P, sensor_size=(H, W), clip_out_of_range=False).cpu().numpy()
+    assert np.array_equal(out, ref)
+    # integer entry point
+    L = _lib.lib()
+    cnt = torch.empty((H, W), dtype=torch.int32, device="cuda")
+    oob = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for v in (_lib.VARIANT_GLOBAL_RED, _lib.VARIANT_WARP_AGG):
+        _lib.check(L.evk_count_u32(X.data_ptr(), Y.data_ptr(), n, H, W, 0.0, 0.0, v, cnt.data_ptr(), oob.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(cnt.cpu().numpy().astype(np.float32), ref)
+        assert int(cnt.sum()) == n
+
+
+def test_numpy_flavour():
+    from event_utils_b200.representations.image import events_to_image
+    g = golden("image")
+    out = events_to_image(g["np_x"], g["np_y"], g["np_p"], sensor_size=(40, 56))
+    assert out.dtype == np.float64 and out.shape == (40, 56)
+    assert_close_to_max(out, g["np_nearest"], 1e-5)
+    out = events_to_image(g["np_x"], g["np_y"], g["np_p"], sensor_size=(40, 56), meanval=True, default=-1)
+    assert_close_to_max(out, g["np_meanval"], 1e-5)
+    with pytest.raises(TypeError):
+        events_to_image(np.float64([1.5]), np.float64([1.0]), np.float64([1.0]))
+
+
+def test_flow_warp(oracle):
+    from event_utils_b200.transforms.optic_flow import warp_events_flow_torch
+    g = golden("flow")
+    x, y, t, p, flow = dev(g["x"], g["y"], g["t"], g["p"], g["flow"])
+    x_before = x.clone()
+    xw, yw = warp_events_flow_torch(x, y, t, p, flow)
+    assert torch.equal(x, x_before)  # inputs not mutated
+    assert_close_to_max(xw.cpu().numpy(), g["xw"], 1e-5)
+    assert_close_to_max(yw.cpu().numpy(), g["yw"], 1e-5)
+    xw, yw = warp_events_flow_torch(x.unsqueeze(1), y.unsqueeze(1), t.unsqueeze(1), p.unsqueeze(1), flow.unsqueeze(0), t0=0.02)
+    assert xw.shape == (x.shape[0],)
+    assert_close_to_max(xw.cpu().numpy(), g["xw_t0"], 1e-5)
+    assert_close_to_max(yw.cpu().numpy(), g["yw_t0"], 1e-5)
+    xw, yw = warp_events_flow_torch(*dev(g["k_x"], g["k_y"], g["k_t"], g["k_t"], g["k_flow"]))
+    assert_close_to_max(xw.cpu().numpy(), g["k_xw"], 1e-6)
+    assert_close_to_max(yw.cpu().numpy(), g["k_yw"], 1e-6)
+    # large random case against the oracle
+    xe, ye, te, pe = make_events(8, 500000, 180, 240)
+    fl = (np.random.default_rng(1).standard_normal((2, 180, 240)) * 30).astype(np.float32)
+    xw, yw = warp_events_flow_torch(*dev(xe, ye, te, pe, fl))
+    xo, yo = oracle.warp_flow_f32(xe, ye, te, fl)
+    assert_close_to_max(xw.cpu().numpy(), xo, 1e-5)
+    assert_close_to_max(yw.cpu().numpy(), yo, 1e-5)
+
+
+def test_tap_helpers():
+    from event_utils_b200.representations.image import (events_to_image_drv, image_to_event_weights,
+                                                        interpolate_to_derivative_img, interpolate_to_image)
+    from event_utils_b200.util.event_util import events_bounds_mask
+    g = golden("taps")
+    img = torch.zeros(16, 22, device="cuda")
+    interpolate_to_image(*dev(g["px"], g["py"], g["dx"], g["dy"], g["w"]), img)
+    assert_close_to_max(img.cpu().numpy(), g["img"], 1e-5)
+    img_cpu = torch.zeros(16, 22)
+    interpolate_to_image(*(torch.from_numpy(g[k]) for k in ("px", "py", "dx", "dy", "w")), img_cpu)
+    assert_close_to_max(img_cpu.numpy(), g["img"], 1e-5)
+    dimg = torch.zeros(2, 16, 22, device="cuda")
+    px, py, dx, dy, w1, w2 = dev(g["px"], g["py"], g["dx"], g["dy"], g["w1"], g["w2"])
+    interpolate_to_derivative_img(px, py, dx, dy, dimg, w1, w2)
+    assert_close_to_max(dimg.cpu().numpy(), g["dimg"], 1e-5)
+    out = image_to_event_weights(g["g_x"], g["g_y"], g["g_img"])
+    assert out.dtype == np.float64
+    assert_close_to_max(out, g["g_out"], 1e-12)
+    assert np.array_equal(events_bounds_mask(g["m_x"], g["m_y"], 0, 240, 0, 180), g["m_out"])
+    i0, d0 = events_to_image_drv(g["drv_x"], g["drv_y"], g["drv_p"], g["drv_jx"], g["drv_jy"], compute_gradient=True)
+    assert i0.dtype == np.float32 and i0.shape == (181, 241) and d0.shape == (2, 181, 241)
+    assert_close_to_max(i0, g["drv_img"], 1e-5)
+    assert_close_to_max(d0, g["drv_dimg"], 1e-5)
+    i1, d1 = events_to_image_drv(g["drv_x"], g["drv_y"], g["drv_p"], None, None)
+    assert d1 is None
+    assert_close_to_max(i1, g["drv_img"], 1e-5)
