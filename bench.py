@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the event -> voxel-grid hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one voxel-grid build over one batch of synthetic events:
+  N=1 : BASELINE.json configs[1] -- 50 M uniform events -> 5-bin 640x480 grid, reference
+        semantics (events_to_voxel_torch: temporal bilinear x spatial truncation).
+  N>1 : BASELINE.json configs[4] shape -- every rank holds a contiguous 50 M-event time shard of a
+        N*50 M-event stream (weak scaling), global (t0, dt), one NCCL sum all-reduce of the grid.
+`value` is whole-job Mevents/s with the events resident in HBM, timed with CUDA events over
+exactly K steps, max over ranks.  `e2e` is the same metric through the public python API with
+pinned HOST tensors in and a host tensor out (H2D + D2H inside the timed region).
+`--impl reference` times the CPU port of the reference (oracle/ref_port.py) on the host cores.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_PER_GPU = int(os.environ.get("EVK_BENCH_EVENTS", 50_000_000))
+B, H, W = 5, 480, 640
+CPU_SAMPLE = int(os.environ.get("EVK_BENCH_CPU_SAMPLE", 5_000_000))
+METRIC = "Mevents/s voxel-grid build (B=5, 640x480)"
+HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_config(world):
+    return {
+        "workload": ("50M uniform events -> 5x480x640 voxel grid (events_to_voxel_torch semantics), 1xB200"
+                     if world == 1 else
+                     "%dM events -> 5x480x640 voxel grid sharded over %d GPUs (50M-event time shard per GPU), "
+                     "one NCCL all-reduce of the grid" % (50 * world, world)),
+        "events_per_gpu": N_PER_GPU, "bins": B, "height": H, "width": W,
+        "layout": "SoA f32 x,y,t,p (16 B/event)",
+        "seed": 2024,
+        "l2_policy": "inputs (800 MB/step) larger than L2 (126 MB); no explicit flush",
+        "parallelism": "events sharded x%d, global t0/dt agreed up front" % world,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.th = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.th = threading.Thread(target=pump, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [v.strip() for v in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic events (SURVEY.md section 8d config 2 generator)
+# ------------------------------------------------------------------------------------------------
+def make_shard(n, rank, world, device):
+    g = torch.Generator(device=device).manual_seed(2024 + rank)
+    x = torch.rand(n, device=device, generator=g) * (W - 1)
+    y = torch.rand(n, device=device, generator=g) * (H - 1)
+    t = torch.sort(torch.rand(n, device=device, generator=g)).values
+    t = (t + rank) / world                       # contiguous time shard of the global [0,1) stream
+    p = (torch.randint(0, 2, (n,), device=device, generator=g) * 2 - 1).float()
+    return x, y, t, p
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (the reference's library-op sequence, oracle/ref_port.py)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_events(n):
+    rng = np.random.default_rng(2024)
+    x = (rng.random(n) * (W - 1)).astype(np.float32)
+    y = (rng.random(n) * (H - 1)).astype(np.float32)
+    t = np.sort(rng.random(n)).astype(np.float32)
+    p = (rng.integers(0, 2, n) * 2 - 1).astype(np.float32)
+    return x, y, t, p
+
+
+def time_cpu_port(n, repeats):
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x, y, t, p = cpu_sample_events(n)
+    xt, yt, tt, pt = (torch.from_numpy(a) for a in (x, y, t, p))
+    ref_port.voxel_torch_cpu(xt[:100000], yt[:100000], tt[:100000], pt[:100000], B, (H, W))
+    best_t = float("inf")
+    for _ in range(repeats):
+        s = time.perf_counter()
+        ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W))
+        best_t = min(best_t, time.perf_counter() - s)
+    xi, yi = x.astype(np.int64), y.astype(np.int64)
+    t64, p64 = t.astype(np.float64), p.astype(np.float64)
+    best_n = float("inf")
+    for _ in range(max(1, repeats - 1)):
+        s = time.perf_counter()
+        ref_port.voxel_numpy(xi, yi, t64, p64, B, (H, W))
+        best_n = min(best_n, time.perf_counter() - s)
+    return {"torch_cpu_mevs": n / best_t / 1e6, "numpy_mevs": n / best_n / 1e6, "cores": cores,
+            "torch_threads": torch.get_num_threads()}
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU path (library-op port, see oracle/ref_port.py)."""
+    if rank != 0:
+        return
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = CPU_SAMPLE
+    x, y, t, p = cpu_sample_events(n)
+    xt, yt, tt, pt = (torch.from_numpy(a) for a in (x, y, t, p))
+    for _ in range(args.warmup):
+        ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W))
+    s = time.perf_counter()
+    for _ in range(args.steps):
+        ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W))
+    el = time.perf_counter() - s
+    value = n * args.steps / el / 1e6
+    sample = ("events_to_voxel_torch library-op port (torch CPU f32, %d threads) on a %d-event sample of the "
+              "50M-event workload per step; the reference itself is pure Python and cannot travel to the box"
+              % (torch.get_num_threads(), n))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mevents/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "Mevents/s", "cores": cores, "kind": "port", "sample": sample,
+                         "cpu": cpu_model()},
+        "e2e": {"value": value, "unit": "Mevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+    from event_utils_b200 import _lib
+    from event_utils_b200.parallel import global_time_span
+    from event_utils_b200.representations.voxel_grid import events_to_voxel_torch
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    L = _lib.lib()
+    n = N_PER_GPU
+    x, y, t, p = make_shard(n, rank, world, device)
+    t0, dt = global_time_span(t) if world > 1 else (float(t[0]), float((t[-1] - t[0]).item()))
+    out = torch.empty((B, H, W), dtype=torch.float32, device=device)
+    ws = torch.empty(L.evk_voxel_workspace_bytes(B, H, W, 0), dtype=torch.uint8, device=device)
+    oob = torch.zeros(1, dtype=torch.int64, device=device)
+    stream = _lib.stream()
+    variant = _lib.VARIANT_AUTO
+
+    def step():
+        _lib.check(L.evk_voxel_f32(x.data_ptr(), y.data_ptr(), t.data_ptr(), p.data_ptr(), n, t0, dt, B, H, W,
+                                   variant, out.data_ptr(), ws.data_ptr(), ws.numel(), oob.data_ptr(), stream))
+        if world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.evk_prof_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    kms, ktimed, klaunch = ctypes.c_double(0), ctypes.c_longlong(0), ctypes.c_longlong(0)
+    L.evk_prof_collect(ctypes.byref(kms), ctypes.byref(ktimed), ctypes.byref(klaunch))
+    L.evk_prof_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    assert int(oob.item()) == 0
+    # sanity inside the bench: every event deposits its polarity once
+    total = float(out.double().sum())
+    if world > 1:
+        el = torch.tensor([elapsed_ms], device=device)
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(el.item())
+        psum = p.double().sum()
+        dist.all_reduce(psum)
+        expect = float(psum)
+    else:
+        expect = float(p.double().sum())
+    assert abs(total - expect) <= 1e-6 * n * world + 4.0, (total, expect)
+
+    value = n * world * args.steps / elapsed_ms / 1e3          # Mevents/s, whole job
+    peak, peak_src = measured_peak()
+    alg_bytes = 16.0 * n + 4.0 * B * H * W                       # 16 B/event + the grid once
+    k_ms = kms.value / max(1, ktimed.value)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            traffic = json.load(f).get("voxel_scatter_dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- end to end through the public API: pinned host tensors in, host tensor out --------------
+    hx, hy, ht, hp = (torch.empty(n, dtype=torch.float32, pin_memory=True) for _ in range(4))
+    for h, d in ((hx, x), (hy, y), (ht, t), (hp, p)):
+        h.copy_(d)
+    torch.cuda.synchronize()
+    if world == 1:
+        def e2e_step():
+            return events_to_voxel_torch(hx, hy, ht, hp, B, sensor_size=(H, W))
+    else:
+        pipe = _lib.pipeline()
+        gdev = torch.empty((B, H, W), dtype=torch.float32, device=device)
+        ghost = torch.empty((B, H, W), dtype=torch.float32, pin_memory=True)
+        bad = ctypes.c_ulonglong(0)
+
+        def e2e_step():
+            _lib.check(L.evk_voxel_host_f32(pipe, hx.data_ptr(), hy.data_ptr(), ht.data_ptr(), hp.data_ptr(), n,
+                                            t0, dt, B, H, W, 0, gdev.data_ptr(), ctypes.byref(bad)))
+            dist.all_reduce(gdev, op=dist.ReduceOp.SUM)
+            ghost.copy_(gdev)
+            torch.cuda.synchronize()
+            return ghost
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        res = e2e_step()
+    barrier()
+    s = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - s
+    if world > 1:
+        el = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e_s = float(el.item())
+    assert abs(float(res.double().sum()) - expect) <= 1e-6 * n * world + 4.0
+    e2e_value = n * world * e2e_steps / e2e_s / 1e6
+    del hx, hy, ht, hp
+
+    extra, cpu = {}, None
+    if rank == 0 and world == 1:
+        cpu_t = time_cpu_port(CPU_SAMPLE, repeats=3)
+        best = max(cpu_t["torch_cpu_mevs"], cpu_t["numpy_mevs"])
+        cpu = {"value": best, "unit": "Mevents/s", "cores": cpu_t["cores"], "kind": "port",
+               "sample": "%d-event sample of the workload, best of 3; faster of torch-CPU events_to_voxel_torch port "
+                         "(%.1f Mev/s, %d threads) and numpy events_to_voxel port (%.1f Mev/s, 1 thread)"
+                         % (CPU_SAMPLE, cpu_t["torch_cpu_mevs"], cpu_t["torch_threads"], cpu_t["numpy_mevs"]),
+               "cpu": cpu_model()}
+        if not args.no_extra:
+            del x, y, t, p
+            torch.cuda.empty_cache()
+            extra = secondary_metrics(L, _lib, device, peak)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mevents/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": 16 * n,
+                    "d2h_bytes_per_step": 4 * B * H * W, "steps": e2e_steps,
+                    "api": "events_to_voxel_torch(pinned CPU tensors) -> CPU tensor" if world == 1 else
+                           "evk_voxel_host_f32 (pinned host shard) + NCCL all-reduce + D2H per rank"},
+            "gpu_launches": int(klaunch.value),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "kernel": "voxel_scatter_kernel<QUAD> (red.global.add.v4.f32)",
+                         "kernel_ms": k_ms, "launches_timed": int(ktimed.value),
+                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                         "step_frac": (alg_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak},
+            "cpu_baseline": cpu,
+        }
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def secondary_metrics(L, _lib, device, peak):
+    """Short, separately timed numbers for the rest of the hot path (reported, not the headline)."""
+    out = {}
+    n = N_PER_GPU
+
+    def best_of(fn, iters=3):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return min(ts)
+    # fused cmax, f64 parity mode, uniform scene (BASELINE configs[2] shape)
+    g = torch.Generator(device=device).manual_seed(7)
+    x = torch.rand(n, device=device, generator=g, dtype=torch.float64) * 239
+    y = torch.rand(n, device=device, generator=g, dtype=torch.float64) * 179
+    t = torch.sort(torch.rand(n, device=device, generator=g, dtype=torch.float64)).values * 0.05
+    p = (torch.randint(0, 2, (n,), device=device, generator=g) * 2 - 1).double()
+    ws = torch.empty(L.evk_cmax_workspace_bytes(180, 240), dtype=torch.uint8, device=device)
+    res = torch.empty(8, dtype=torch.float64, device=device)
+    tl = float(t[-1])
+    ms = best_of(lambda: _lib.check(L.evk_cmax_linvel_variance_f64(
+        x.data_ptr(), y.data_ptr(), t.data_ptr(), p.data_ptr(), n, 1.0, 45.0, -20.0, tl, 180, 240, 180, 240, 1.0,
+        _lib.CMAX_WANT_GRAD, res.data_ptr(), None, None, ws.data_ptr(), ws.numel(), _lib.stream())))
+    out["cmax_f64"] = {"iter_per_s": 1e3 / ms, "ms_per_iter": ms, "events": n, "what": "one fused (f, g) evaluation, "
+                       "linvel warp, 181x241 IWE, sigma=1, f64 inputs (32 B/event)",
+                       "roofline_frac": 32.0 * n / (ms * 1e-3) / 1e9 / peak}
+    # CPU port of one reference iteration (f then g) on a 1M-event sample
+    try:
+        from oracle import ref_port
+        m = 1_000_000
+        xs, ys, ts, ps = (a[:: n // m][:m].cpu().numpy() for a in (x, y, t, p))
+        ref_port.cmax_fg_cpu((45.0, -20.0), xs[:10000], ys[:10000], ts[:10000], ps[:10000])
+        s = time.perf_counter()
+        ref_port.cmax_fg_cpu((45.0, -20.0), xs, ys, ts, ps)
+        el = time.perf_counter() - s
+        out["cmax_cpu_port"] = {"iter_per_s_at_sample": 1.0 / el, "sample_events": m,
+                                "iter_per_s_extrapolated_to_workload": 1.0 / (el * n / m)}
+    except Exception as e:  # pragma: no cover
+        out["cmax_cpu_port"] = {"error": repr(e)}
+    del x, y, t, p
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary (cmax) numbers")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,10 @@ def _declare(L):
     L.evk_version.restype = ci
     L.evk_last_error.restype = c.c_char_p
     L.evk_device_check.restype = ci
+    L.evk_prof_enable.restype = ci
+    L.evk_prof_enable.argtypes = [ci]
+    L.evk_prof_collect.restype = ci
+    L.evk_prof_collect.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_longlong), c.POINTER(c.c_longlong)]
     L.evk_voxel_workspace_bytes.restype = sz
     L.evk_voxel_workspace_bytes.argtypes = [ci, ci, ci, cu]
     L.evk_voxel_f32.restype = ci

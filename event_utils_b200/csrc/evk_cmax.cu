@@ -357,9 +357,12 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, double *result, fl
     EVK_CUDA(cudaMemsetAsync(ws.sums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.sums), st));  // sums + oob are adjacent
     if (A.n > 0) {
         const int grid = grid_for(A.n, 256 * 8, 8);
+        ProfScope prof(st);
+        prof_count(1);
         if (grad) cmax_scatter_kernel<WARP, true><<<grid, 256, 0, st>>>(A);
         else cmax_scatter_kernel<WARP, false><<<grid, 256, 0, st>>>(A);
     }
+    prof_count(do_blur ? 4 : 3);
     const int g = (npix + 255) / 256;
     cmax_gather_kernel<<<g, 256, 0, st>>>(ws.acc, R, npix, ws.I, ws.D0, ws.D1, iwe_out, diwe_out, ws.sums);
     if (do_blur) cmax_blur_axis0_kernel<<<g, 256, 0, st>>>(ws.I, ws.tmp, A.Hc, A.Wc, taps);

@@ -31,6 +31,15 @@ int num_sms();  // SM count of the current device (cached)
         }                                           \
     } while (0)
 
+// measurement hooks (evk_core.cu): count a kernel launch / bracket a dominant kernel with events
+void prof_count(int launches);
+struct ProfScope {
+    cudaStream_t st;
+    int slot;
+    ProfScope(cudaStream_t s);
+    ~ProfScope();
+};
+
 static inline unsigned variant_of(unsigned flags) { return flags & EVK_VARIANT_MASK; }
 
 // Persistent-style launch geometry: a multiple of the SM count, capped by the work available.

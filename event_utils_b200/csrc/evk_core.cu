@@ -37,9 +37,62 @@ int num_sms()
     return cached_sms;
 }
 
+// ---- measurement hooks ---------------------------------------------------------------------
+static bool g_prof_on = false;
+static long long g_launches = 0;
+static const int kProfSlots = 4096;
+static cudaEvent_t g_prof_ev[kProfSlots][2];
+static int g_prof_used = 0, g_prof_created = 0;
+
+void prof_count(int launches)
+{
+    if (g_prof_on) g_launches += launches;
+}
+
+ProfScope::ProfScope(cudaStream_t s) : st(s), slot(-1)
+{
+    if (!g_prof_on || g_prof_used >= kProfSlots) return;
+    if (g_prof_used >= g_prof_created) {
+        if (cudaEventCreate(&g_prof_ev[g_prof_created][0]) != cudaSuccess) return;
+        if (cudaEventCreate(&g_prof_ev[g_prof_created][1]) != cudaSuccess) return;
+        ++g_prof_created;
+    }
+    slot = g_prof_used++;
+    cudaEventRecord(g_prof_ev[slot][0], st);
+}
+
+ProfScope::~ProfScope()
+{
+    if (slot >= 0) cudaEventRecord(g_prof_ev[slot][1], st);
+}
+
 }  // namespace evk
 
 extern "C" {
+
+int evk_prof_enable(int on)
+{
+    evk::g_prof_on = on != 0;
+    return EVK_OK;
+}
+
+int evk_prof_collect(double *ms, long long *timed, long long *launches)
+{
+    using namespace evk;
+    double total = 0.0;
+    for (int i = 0; i < g_prof_used; ++i) {
+        EVK_CUDA(cudaEventSynchronize(g_prof_ev[i][1]));
+        float f = 0.f;
+        EVK_CUDA(cudaEventElapsedTime(&f, g_prof_ev[i][0], g_prof_ev[i][1]));
+        total += f;
+    }
+    if (ms) *ms = total;
+    if (timed) *timed = g_prof_used;
+    if (launches) *launches = g_launches;
+    g_prof_used = 0;
+    g_launches = 0;
+    return EVK_OK;
+}
 
 int evk_version(void) { return EVK_VERSION; }
 

@@ -109,7 +109,7 @@ int evk_voxel_host_f32(evk_pipeline_t *p, const float *x, const float *y, const 
         done += m;
         ++k;
     }
-    EVK_CUDA(cudaMemcpyAsync(out_host, p->grid, grid_bytes, cudaMemcpyDeviceToHost, p->compute));
+    EVK_CUDA(cudaMemcpyAsync(out_host, p->grid, grid_bytes, cudaMemcpyDefault, p->compute));  // out may be host or device
     EVK_CUDA(cudaMemcpyAsync(p->oob_pinned, p->oob_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->compute));
     EVK_CUDA(cudaStreamSynchronize(p->compute));
     if (oob_host) *oob_host = *p->oob_pinned;

@@ -321,18 +321,23 @@ int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int
         A.ws = static_cast<float *>(workspace);
         EVK_CUDA(cudaMemsetAsync(A.ws, 0, need, st));
         if (n > 0) {
+            ProfScope prof(st);
+            prof_count(1);
             if (vec4) image_scatter_kernel<ISINK_QUAD, true, true><<<grid, kThreads, 0, st>>>(A);
             else image_scatter_kernel<ISINK_QUAD, true, false><<<grid, kThreads, 0, st>>>(A);
         }
         const int g2 = grid_for(npix, 256, 8);
+        prof_count(1);
         if (accum) image_fold_kernel<true><<<g2, 256, 0, st>>>(A.ws, out, Himg, Wimg, A.nqx, fill);
         else image_fold_kernel<false><<<g2, 256, 0, st>>>(A.ws, out, Himg, Wimg, A.nqx, fill);
     } else if (variant == EVK_VARIANT_GLOBAL_RED || variant == EVK_VARIANT_WARP_AGG) {
         if (!accum) {
             if (fill == 0.0f) EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)npix * sizeof(float), st));
-            else fill_kernel<<<grid_for(npix, 256, 8), 256, 0, st>>>(out, npix, fill);
+            else { prof_count(1); fill_kernel<<<grid_for(npix, 256, 8), 256, 0, st>>>(out, npix, fill); }
         }
         if (n > 0) {
+            ProfScope prof(st);
+            prof_count(1);
             if (bil) {
                 if (vec4) image_scatter_kernel<ISINK_SCALAR, true, true><<<grid, kThreads, 0, st>>>(A);
                 else image_scatter_kernel<ISINK_SCALAR, true, false><<<grid, kThreads, 0, st>>>(A);
@@ -365,6 +370,8 @@ int evk_count_u32(const float *x, const float *y, int64_t n, int Himg, int Wimg,
     if (!(flags & EVK_ACCUMULATE)) EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)Himg * Wimg * sizeof(unsigned), st));
     if (n > 0) {
         const int grid = grid_for(n, kThreads * 8, 8);
+        ProfScope prof(st);
+        prof_count(1);
         if (variant_of(flags) == EVK_VARIANT_GLOBAL_RED) count_kernel<false><<<grid, kThreads, 0, st>>>(A);
         else count_kernel<true><<<grid, kThreads, 0, st>>>(A);
     }
@@ -378,6 +385,7 @@ int evk_warp_flow_f32(const float *x, const float *y, const float *t, int64_t n,
     using namespace evk;
     if (n < 0 || H < 1 || W < 1 || !flow || (n > 0 && (!x || !y || !t || !xw || !yw))) { set_error("evk_warp_flow_f32: bad arguments"); return EVK_E_ARG; }
     if (n == 0) return EVK_OK;
+    prof_count(1);
     warp_flow_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, t, n, flow, H, W, t0, xw, yw);
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;

@@ -305,14 +305,19 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
         else if (layout == LAYOUT_SOA1) EVK_LAUNCH(S, BL, LAYOUT_SOA1); \
         else EVK_LAUNCH(S, BL, LAYOUT_AOS);                    \
     } while (0)
-        if (sink == SINK_QUAD) { if (bil) EVK_DISPATCH_L(SINK_QUAD, true); else EVK_DISPATCH_L(SINK_QUAD, false); }
-        else { if (bil) EVK_DISPATCH_L(SINK_SCALAR, true); else EVK_DISPATCH_L(SINK_SCALAR, false); }
+        {
+            ProfScope prof(st);
+            prof_count(1);
+            if (sink == SINK_QUAD) { if (bil) EVK_DISPATCH_L(SINK_QUAD, true); else EVK_DISPATCH_L(SINK_QUAD, false); }
+            else { if (bil) EVK_DISPATCH_L(SINK_SCALAR, true); else EVK_DISPATCH_L(SINK_SCALAR, false); }
+        }
 #undef EVK_DISPATCH_L
 #undef EVK_LAUNCH
         EVK_CUDA(cudaGetLastError());
     }
     if (sink == SINK_QUAD) {
         const int grid = grid_for(npix, 256, 8);
+        prof_count(1);
         if (accum) voxel_fold_kernel<true><<<grid, 256, 0, st>>>(A.ws, A.out, npix, A.B, A.nq);
         else voxel_fold_kernel<false><<<grid, 256, 0, st>>>(A.ws, A.out, npix, A.B, A.nq);
         EVK_CUDA(cudaGetLastError());
@@ -410,7 +415,11 @@ int evk_voxel_windows_f32(const float *x, const float *y, const float *t, const 
     if (slices > fill) slices = fill;
     if (slices < 1) slices = 1;
     if ((int64_t)n_windows * slices > 0x7fffffffLL) { set_error("evk_voxel_windows_f32: too many windows"); return EVK_E_ARG; }
-    voxel_windows_kernel<<<(unsigned)(n_windows * slices), kThreads, 0, st>>>(A, offsets, n_windows, (int)slices);
+    {
+        ProfScope prof(st);
+        prof_count(1);
+        voxel_windows_kernel<<<(unsigned)(n_windows * slices), kThreads, 0, st>>>(A, offsets, n_windows, (int)slices);
+    }
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

@@ -65,6 +65,17 @@ const char *evk_last_error(void);
 int evk_device_check(void);
 
 /* ---------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py).  With profiling enabled every DOMINANT kernel launch of the
+ * scatter entry points (voxel / image scatter, cmax scatter) is bracketed by a CUDA event pair
+ * recorded on the launching stream, and every kernel launch of the library is counted.
+ * evk_prof_collect() synchronises those events, returns the summed device time of the bracketed
+ * launches in *ms, their number in *timed and the total number of kernel launches in *launches,
+ * and resets the counters.
+ * --------------------------------------------------------------------------------------------- */
+int evk_prof_enable(int on);
+int evk_prof_collect(double *ms, long long *timed, long long *launches);
+
+/* ---------------------------------------------------------------------------------------------
  * Voxel grid.  Replaces events_to_voxel_torch, lib/representations/voxel_grid.py:114-153
  * (per-bin loop :136-151 -> events_to_image_torch image.py:88-95 -> index_put_).
  *   tau = ((t - t0) / dt) * (B-1)   (f32, this order);  V[b, trunc(y), trunc(x)] += p*max(0,1-|tau-b|)

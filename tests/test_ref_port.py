@@ -1,0 +1,30 @@
+"""The CPU baseline port (oracle/ref_port.py, what bench.py times as the reference arm) must
+compute what the reference computes: checked against the golden vectors of the real reference."""
+import numpy as np
+import torch
+
+from conftest import assert_close_to_max, golden
+from oracle import ref_port
+
+
+def test_voxel_ports():
+    g = golden("voxel_torch")
+    for tag in "abd":
+        out = ref_port.voxel_torch_cpu(*(torch.from_numpy(g[tag + k]) for k in ("_x", "_y", "_t", "_p")),
+                                       int(g[tag + "_B"]), tuple(int(v) for v in g[tag + "_HW"]))
+        assert_close_to_max(out.numpy(), g[tag + "_out"], 1e-6, tag)
+    g = golden("voxel_numpy")
+    for tag in "ab":
+        out = ref_port.voxel_numpy(g[tag + "_x"], g[tag + "_y"], g[tag + "_t"], g[tag + "_p"], int(g[tag + "_B"]),
+                                   tuple(int(v) for v in g[tag + "_HW"]))
+        assert_close_to_max(out, g[tag + "_out"], 1e-12, tag)
+
+
+def test_cmax_port():
+    g = golden("cmax")
+    for row in g["evals"][::5]:
+        s, vx, vy, sigma, f_ref, g0, g1 = row
+        tag = {0: "c9", 1: "lat"}[int(s)]
+        f, gr = ref_port.cmax_fg_cpu((vx, vy), g[tag + "_x"], g[tag + "_y"], g[tag + "_t"], g[tag + "_p"], (180, 240), sigma)
+        assert abs(f - f_ref) <= 1e-6 * abs(f_ref) + 1e-12
+        assert np.abs(gr - np.array([g0, g1])).max() <= 1e-5 * max(abs(g0), abs(g1)) + 1e-9
