@@ -69,51 +69,52 @@ def workload_config(world):
 # clocks during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons through NVML every ~2 ms while the timed region runs
+    (nvidia-smi -lms cannot sample a region that only lasts tens of milliseconds)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc, self.th = index, [], None, None
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop, self.th, self.err = threading.Event(), None, None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: map the torch device to its NVML handle through the UUID
+            try:
+                uuid = torch.cuda.get_device_properties(self.index).uuid
+                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self._stop.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.002)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
-            return
-        def pump():
-            for line in self.proc.stdout:
-                self.rows.append(line.strip())
-        self.th = threading.Thread(target=pump, daemon=True)
+        self.th = threading.Thread(target=self._run, daemon=True)
         self.th.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [v.strip() for v in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self.th is not None:
+            self.th.join(timeout=2)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(self.sm), "reasons": sorted(self.reasons)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -141,13 +142,35 @@ def cpu_sample_events(n):
     return x, y, t, p
 
 
+def best_torch_threads(fn, candidates):
+    """The reference's torch-CPU scatter (index_put_ accumulate) does not scale with threads and gets
+    much SLOWER with many; give the reference arm the thread count it runs fastest with."""
+    best, best_t = candidates[0], float("inf")
+    for c in candidates:
+        torch.set_num_threads(c)
+        fn()
+        s = time.perf_counter()
+        fn()
+        el = time.perf_counter() - s
+        if el < best_t:
+            best, best_t = c, el
+    torch.set_num_threads(best)
+    return best
+
+
+def thread_candidates():
+    cores = os.cpu_count() or 1
+    return sorted(set(c for c in (1, 4, 8, 16, 32, cores) if c <= cores))
+
+
 def time_cpu_port(n, repeats):
     from oracle import ref_port
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     x, y, t, p = cpu_sample_events(n)
     xt, yt, tt, pt = (torch.from_numpy(a) for a in (x, y, t, p))
-    ref_port.voxel_torch_cpu(xt[:100000], yt[:100000], tt[:100000], pt[:100000], B, (H, W))
+    m = min(n, 500_000)
+    threads = best_torch_threads(lambda: ref_port.voxel_torch_cpu(xt[:m], yt[:m], tt[:m], pt[:m], B, (H, W)),
+                                 thread_candidates())
     best_t = float("inf")
     for _ in range(repeats):
         s = time.perf_counter()
@@ -161,7 +184,7 @@ def time_cpu_port(n, repeats):
         ref_port.voxel_numpy(xi, yi, t64, p64, B, (H, W))
         best_n = min(best_n, time.perf_counter() - s)
     return {"torch_cpu_mevs": n / best_t / 1e6, "numpy_mevs": n / best_n / 1e6, "cores": cores,
-            "torch_threads": torch.get_num_threads()}
+            "torch_threads": threads}
 
 
 def cpu_model():
@@ -181,10 +204,11 @@ def run_reference(args, rank, world):
         return
     from oracle import ref_port
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     n = CPU_SAMPLE
     x, y, t, p = cpu_sample_events(n)
     xt, yt, tt, pt = (torch.from_numpy(a) for a in (x, y, t, p))
+    m = min(n, 500_000)
+    best_torch_threads(lambda: ref_port.voxel_torch_cpu(xt[:m], yt[:m], tt[:m], pt[:m], B, (H, W)), thread_candidates())
     for _ in range(args.warmup):
         ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W))
     s = time.perf_counter()
@@ -192,9 +216,9 @@ def run_reference(args, rank, world):
         ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W))
     el = time.perf_counter() - s
     value = n * args.steps / el / 1e6
-    sample = ("events_to_voxel_torch library-op port (torch CPU f32, %d threads) on a %d-event sample of the "
-              "50M-event workload per step; the reference itself is pure Python and cannot travel to the box"
-              % (torch.get_num_threads(), n))
+    sample = ("events_to_voxel_torch library-op port (torch CPU f32, %d threads = the fastest of %s on this host) "
+              "on a %d-event sample of the 50M-event workload per step; the reference itself is pure Python and "
+              "cannot travel to the box" % (torch.get_num_threads(), thread_candidates(), n))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mevents/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
@@ -399,11 +423,12 @@ def secondary_metrics(L, _lib, device, peak):
         from oracle import ref_port
         m = 1_000_000
         xs, ys, ts, ps = (a[:: n // m][:m].cpu().numpy() for a in (x, y, t, p))
-        ref_port.cmax_fg_cpu((45.0, -20.0), xs[:10000], ys[:10000], ts[:10000], ps[:10000])
+        k = 100_000
+        best_torch_threads(lambda: ref_port.cmax_fg_cpu((45.0, -20.0), xs[:k], ys[:k], ts[:k], ps[:k]), thread_candidates())
         s = time.perf_counter()
         ref_port.cmax_fg_cpu((45.0, -20.0), xs, ys, ts, ps)
         el = time.perf_counter() - s
-        out["cmax_cpu_port"] = {"iter_per_s_at_sample": 1.0 / el, "sample_events": m,
+        out["cmax_cpu_port"] = {"iter_per_s_at_sample": 1.0 / el, "sample_events": m, "torch_threads": torch.get_num_threads(),
                                 "iter_per_s_extrapolated_to_workload": 1.0 / (el * n / m)}
     except Exception as e:  # pragma: no cover
         out["cmax_cpu_port"] = {"error": repr(e)}
@@ -415,8 +440,8 @@ def secondary_metrics(L, _lib, device, peak):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary (cmax) numbers")
     args = ap.parse_args()
