@@ -56,9 +56,14 @@ enum { WARP_LINVEL_F64 = 0, WARP_LINVEL_F32 = 1, WARP_FLOW_F32 = 2 };
 
 // bilinear splat of weight w (and derivative weight a) at (xf, yf) on the canvas:
 // image.py:199-207 (IWE) and :131-135 (derivative images) with w1 = [a;0], w2 = [0;a].
-template <bool GRAD>
+// PAIR: two adjacent lanes carry the SAME event; lane parity `xt` picks the x tap (x0 or x0+1) and
+// the lane issues the two row taps of that column.  The two lanes of a pair then write 32
+// contiguous bytes (pixels x0, x0+1 of the interleaved accumulator) in the same instruction, which
+// the LSU merges into one L2 request per row: half the L2 tag look-ups of the one-lane-per-event
+// form (the measured limiter, lts__t_tag_requests ~75 % of peak).
+template <bool GRAD, bool PAIR>
 __device__ __forceinline__ void splat(const CmaxArgs &A, float *acc, float xf, float yf, float w, float a,
-                                      bool clip, unsigned &oob)
+                                      bool clip, unsigned &oob, int xt = 0)
 {
     const float clipx = (float)(A.Wc - 1), clipy = (float)(A.Hc - 1);
     float m2 = 1.0f;
@@ -68,11 +73,30 @@ __device__ __forceinline__ void splat(const CmaxArgs &A, float *acc, float xf, f
     int upx, upy, x0, x1, y0, y1;
     if (!trunc_checked(__fmul_rn(pxf, m2), upx) || !trunc_checked(__fmul_rn(pyf, m2), upy) ||
         !wrap_int_index(upx, A.Wc, x0) || !wrap_int_index(upx + 1, A.Wc, x1) ||
-        !wrap_int_index(upy, A.Hc, y0) || !wrap_int_index(upy + 1, A.Hc, y1)) { ++oob; return; }
+        !wrap_int_index(upy, A.Hc, y0) || !wrap_int_index(upy + 1, A.Hc, y1)) { if (xt == 0) ++oob; return; }
     const float wm = __fmul_rn(w, m2);
     const float am = GRAD ? __fmul_rn(a, wm) : 0.0f;  // jacobian * masked_ps (image.py:211-212)
     if (wm == 0.0f && am == 0.0f) return;
     const float ox = __fsub_rn(1.0f, dx), oy = __fsub_rn(1.0f, dy);
+    if (PAIR) {
+        // this lane's column: weight along x, the x index, and the sign pattern of image.py:131-135
+        const float wx = xt ? dx : ox;
+        const int xc = xt ? x1 : x0;
+        const float wc = __fmul_rn(wm, wx);
+        float4 r0, r1;
+        r0.x = __fmul_rn(wc, oy);
+        r1.x = __fmul_rn(wc, dy);
+        if (GRAD) {
+            r0.y = __fmul_rn(am, xt ? oy : -oy); r1.y = __fmul_rn(am, xt ? dy : -dy);
+            r0.z = __fmul_rn(am, -wx);           r1.z = __fmul_rn(am, wx);
+        } else {
+            r0.y = r1.y = r0.z = r1.z = 0.0f;
+        }
+        r0.w = r1.w = 0.0f;
+        red_add4(acc + ((int64_t)y0 * A.Wc + xc) * 4, r0);
+        red_add4(acc + ((int64_t)y1 * A.Wc + xc) * 4, r1);
+        return;
+    }
     const float wl = __fmul_rn(wm, ox), wr = __fmul_rn(wm, dx);
     float4 v00, v01, v10, v11;
     v00.x = __fmul_rn(wl, oy); v01.x = __fmul_rn(wr, oy); v10.x = __fmul_rn(wl, dy); v11.x = __fmul_rn(wr, dy);
@@ -95,8 +119,8 @@ __device__ __forceinline__ float flow_tap(const float *f, int H, int W, int yy, 
     return ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? __ldg(f + (int64_t)yy * W + xx) : 0.0f;
 }
 
-template <int WARP, bool GRAD>
-__device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, int64_t i, unsigned &oob)
+template <int WARP, bool GRAD, bool PAIR>
+__device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, int64_t i, unsigned &oob, int xt)
 {
     if (WARP == WARP_LINVEL_F64) {
         const double x = ld_stream((const double *)A.x + i), y = ld_stream((const double *)A.y + i);
@@ -110,7 +134,7 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, int64_
         // event_util.py:26-27: keep iff 0 < x' <= Wm and 0 < y' <= Hm (NaN compares false -> kept)
         const bool keep = !(xw <= 0.0 || xw > (double)A.Wm) && !(yw <= 0.0 || yw > (double)A.Hm);
         if (!keep) return;  // x,y,p,j all multiplied by 0: only exact zeros are added at (0,0)..(1,1)
-        splat<GRAD>(A, acc, (float)xw, (float)yw, (float)p, (float)(-d), true, oob);  // image.py:180-183 casts
+        splat<GRAD, PAIR>(A, acc, (float)xw, (float)yw, (float)p, (float)(-d), true, oob, xt);  // image.py:180-183 casts
     } else if (WARP == WARP_LINVEL_F32) {
         const float x = ld_stream((const float *)A.x + i), y = ld_stream((const float *)A.y + i);
         const float d = ld_stream((const float *)A.t + i);  // already t - t_ref
@@ -121,7 +145,7 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, int64_
         const float xw = __fsub_rn(x, __fmul_rn(d, vx)), yw = __fsub_rn(y, __fmul_rn(d, vy));
         const bool keep = !(xw <= 0.0f || xw > (float)A.Wm) && !(yw <= 0.0f || yw > (float)A.Hm);
         if (!keep) return;
-        splat<GRAD>(A, acc, xw, yw, p, -d, true, oob);
+        splat<GRAD, PAIR>(A, acc, xw, yw, p, -d, true, oob, xt);
     } else {
         // optic_flow.py:37-44 then events_to_image_torch(..., interpolation='bilinear') defaults
         const float xe = ld_stream((const float *)A.x + i), ye = ld_stream((const float *)A.y + i);
@@ -150,22 +174,25 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, int64_
             u = __fadd_rn(u, __fmul_rn(flow_tap(fu, H, W, y0 + 1, x0 + 1), se)); v = __fadd_rn(v, __fmul_rn(flow_tap(fv, H, W, y0 + 1, x0 + 1), se));
         }
         const float d = __fsub_rn(te, A.flow_t0);
-        splat<false>(A, acc, __fadd_rn(xe, __fmul_rn(u, d)), __fadd_rn(ye, __fmul_rn(v, d)), p, 0.0f, true, oob);
+        splat<false, PAIR>(A, acc, __fadd_rn(xe, __fmul_rn(u, d)), __fadd_rn(ye, __fmul_rn(v, d)), p, 0.0f, true, oob, xt);
     }
 }
 
-template <int WARP, bool GRAD>
+template <int WARP, bool GRAD, bool PAIR>
 __global__ void __launch_bounds__(256) cmax_scatter_kernel(const CmaxArgs A)
 {
     unsigned oob = 0;
     float *acc = A.acc + (int64_t)(blockIdx.x % A.replicas) * A.Hc * A.Wc * 4;
-    const int64_t stride = (int64_t)gridDim.x * 256;
-    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    // PAIR: two lanes per event (see splat), so a CTA covers 128 events per sweep
+    const int lanes_per_event = PAIR ? 2 : 1;
+    const int xt = PAIR ? (threadIdx.x & 1) : 0;
+    const int64_t stride = (int64_t)gridDim.x * (256 / lanes_per_event);
+    int64_t i = (int64_t)blockIdx.x * (256 / lanes_per_event) + threadIdx.x / lanes_per_event;
     for (; i + stride < A.n; i += 2 * stride) {
-        cmax_event<WARP, GRAD>(A, acc, i, oob);
-        cmax_event<WARP, GRAD>(A, acc, i + stride, oob);
+        cmax_event<WARP, GRAD, PAIR>(A, acc, i, oob, xt);
+        cmax_event<WARP, GRAD, PAIR>(A, acc, i + stride, oob, xt);
     }
-    if (i < A.n) cmax_event<WARP, GRAD>(A, acc, i, oob);
+    if (i < A.n) cmax_event<WARP, GRAD, PAIR>(A, acc, i, oob, xt);
     flush_oob(A.oob, oob);
 }
 
@@ -356,11 +383,14 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, double *result, fl
     EVK_CUDA(cudaMemsetAsync(ws.acc, 0, (size_t)R * npix * 4 * sizeof(float), st));
     EVK_CUDA(cudaMemsetAsync(ws.sums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.sums), st));  // sums + oob are adjacent
     if (A.n > 0) {
-        const int grid = grid_for(A.n, 256 * 8, 8);
         ProfScope prof(st);
         prof_count(1);
-        if (grad) cmax_scatter_kernel<WARP, true><<<grid, 256, 0, st>>>(A);
-        else cmax_scatter_kernel<WARP, false><<<grid, 256, 0, st>>>(A);
+        const bool pair = variant_of(flags) != EVK_VARIANT_GLOBAL_RED;  // GLOBAL_RED = one lane per event (A/B baseline)
+#define EVK_CMAX_LAUNCH(G, P) \
+    cmax_scatter_kernel<WARP, G, P><<<grid_for(cmax_scatter_kernel<WARP, G, P>, 256, A.n, 256 * 4), 256, 0, st>>>(A)
+        if (grad) { if (pair) EVK_CMAX_LAUNCH(true, true); else EVK_CMAX_LAUNCH(true, false); }
+        else { if (pair) EVK_CMAX_LAUNCH(false, true); else EVK_CMAX_LAUNCH(false, false); }
+#undef EVK_CMAX_LAUNCH
     }
     prof_count(do_blur ? 4 : 3);
     const int g = (npix + 255) / 256;

@@ -42,11 +42,26 @@ struct ProfScope {
 
 static inline unsigned variant_of(unsigned flags) { return flags & EVK_VARIANT_MASK; }
 
-// Persistent-style launch geometry: a multiple of the SM count, capped by the work available.
-static inline int grid_for(int64_t work_items, int items_per_cta, int ctas_per_sm)
+// Persistent-style launch geometry: exactly ONE wave -- SM count x the number of CTAs of this
+// kernel that are co-resident on an SM (occupancy query, cached per kernel) -- capped by the work
+// available.  A grid-stride kernel launched with more CTAs than are resident pays a partial
+// second wave (measured: 1184 CTAs at 5/SM cost 2 wave-times instead of 1.6).
+int resident_ctas_per_sm(const void *kernel, int threads, size_t dyn_smem);
+
+template <typename K>
+static inline int grid_for(K kernel, int threads, int64_t work_items, int items_per_cta, size_t dyn_smem = 0)
 {
     int64_t need = (work_items + items_per_cta - 1) / items_per_cta;
-    int64_t cap = (int64_t)num_sms() * ctas_per_sm;
+    int64_t cap = (int64_t)num_sms() * resident_ctas_per_sm((const void *)kernel, threads, dyn_smem);
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// plain elementwise kernels: enough CTAs to cover the items, at most 8 per SM
+static inline int grid_simple(int64_t work_items, int items_per_cta)
+{
+    int64_t need = (work_items + items_per_cta - 1) / items_per_cta;
+    int64_t cap = (int64_t)num_sms() * 8;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
 }
@@ -88,10 +103,29 @@ __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ double2 ld_stream2(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
 
-// no-return global reductions (SASS: REDG.E.ADD.F32 / .F32x2 / .F32x4)
-__device__ __forceinline__ void red_add(float *addr, float v) { atomicAdd(addr, v); }
-__device__ __forceinline__ void red_add4(float *addr16, float4 v) { atomicAdd(reinterpret_cast<float4 *>(addr16), v); }
-__device__ __forceinline__ void red_add2(float *addr8, float2 v) { atomicAdd(reinterpret_cast<float2 *>(addr8), v); }
+// no-return global reductions, spelled in PTX so that (a) the address space is explicit -- a
+// pointer read from a by-value argument struct is a GENERIC pointer and atomicAdd() on it compiles
+// to ATOM.E + shared-memory CAS fall-backs instead of REDG -- and (b) no return value is requested.
+// SASS: REDG.E.ADD.F32 / REDG.E.ADD.F32x2 / REDG.E.ADD.F32x4 (vector forms are sm_90+).
+__device__ __forceinline__ void red_add(float *addr, float v)
+{
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add4(float *addr16, float4 v)
+{
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(addr16)),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add2(float *addr8, float2 v)
+{
+    asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(addr8)), "f"(v.x), "f"(v.y)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_u32(unsigned *addr, unsigned v)
+{
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ void flush_oob(unsigned long long *oob, unsigned local)
 {

@@ -37,6 +37,22 @@ int num_sms()
     return cached_sms;
 }
 
+int resident_ctas_per_sm(const void *kernel, int threads, size_t dyn_smem)
+{
+    struct Entry { const void *k; int threads; size_t smem; int ctas; };
+    static thread_local Entry cache[64];
+    static thread_local int used = 0;
+    for (int i = 0; i < used; ++i)
+        if (cache[i].k == kernel && cache[i].threads == threads && cache[i].smem == dyn_smem) return cache[i].ctas;
+    int ctas = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, threads, dyn_smem) != cudaSuccess || ctas < 1) {
+        cudaGetLastError();
+        ctas = 1;
+    }
+    if (used < 64) cache[used++] = Entry{kernel, threads, dyn_smem, ctas};
+    return ctas;
+}
+
 // ---- measurement hooks ---------------------------------------------------------------------
 static bool g_prof_on = false;
 static long long g_launches = 0;

@@ -228,9 +228,9 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const ImageArgs A)
         if (AGG) {
             const unsigned long long key = ok ? (unsigned long long)cell : ~0ull - (threadIdx.x & 31);
             const unsigned peers = __match_any_sync(0xffffffffu, key);
-            if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(A.out_u32 + cell, (unsigned)__popc(peers));
+            if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) red_add_u32(A.out_u32 + cell, (unsigned)__popc(peers));
         } else {
-            if (ok) atomicAdd(A.out_u32 + cell, 1u);
+            if (ok) red_add_u32(A.out_u32 + cell, 1u);
         }
     }
     flush_oob(A.oob, oob);
@@ -311,7 +311,6 @@ int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int
     if (variant == EVK_VARIANT_WARP_AGG && bil) variant = EVK_VARIANT_GLOBAL_RED;
     const int64_t npix = (int64_t)Himg * Wimg;
     const bool vec4 = ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)p) & 15) == 0);
-    const int grid = grid_for(n, kThreads * 16, 8);
     if (variant == EVK_VARIANT_VECTOR_RED) {
         const size_t need = (size_t)Himg * A.nqx * 4 * sizeof(float);
         if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) {
@@ -323,30 +322,30 @@ int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int
         if (n > 0) {
             ProfScope prof(st);
             prof_count(1);
-            if (vec4) image_scatter_kernel<ISINK_QUAD, true, true><<<grid, kThreads, 0, st>>>(A);
-            else image_scatter_kernel<ISINK_QUAD, true, false><<<grid, kThreads, 0, st>>>(A);
+            if (vec4) image_scatter_kernel<ISINK_QUAD, true, true><<<grid_for(image_scatter_kernel<ISINK_QUAD, true, true>, kThreads, n, kThreads * 16), kThreads, 0, st>>>(A);
+            else image_scatter_kernel<ISINK_QUAD, true, false><<<grid_for(image_scatter_kernel<ISINK_QUAD, true, false>, kThreads, n, kThreads * 16), kThreads, 0, st>>>(A);
         }
-        const int g2 = grid_for(npix, 256, 8);
+        const int g2 = grid_simple(npix, 256);
         prof_count(1);
         if (accum) image_fold_kernel<true><<<g2, 256, 0, st>>>(A.ws, out, Himg, Wimg, A.nqx, fill);
         else image_fold_kernel<false><<<g2, 256, 0, st>>>(A.ws, out, Himg, Wimg, A.nqx, fill);
     } else if (variant == EVK_VARIANT_GLOBAL_RED || variant == EVK_VARIANT_WARP_AGG) {
         if (!accum) {
             if (fill == 0.0f) EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)npix * sizeof(float), st));
-            else { prof_count(1); fill_kernel<<<grid_for(npix, 256, 8), 256, 0, st>>>(out, npix, fill); }
+            else { prof_count(1); fill_kernel<<<grid_simple(npix, 256), 256, 0, st>>>(out, npix, fill); }
         }
         if (n > 0) {
             ProfScope prof(st);
             prof_count(1);
             if (bil) {
-                if (vec4) image_scatter_kernel<ISINK_SCALAR, true, true><<<grid, kThreads, 0, st>>>(A);
-                else image_scatter_kernel<ISINK_SCALAR, true, false><<<grid, kThreads, 0, st>>>(A);
+                if (vec4) image_scatter_kernel<ISINK_SCALAR, true, true><<<grid_for(image_scatter_kernel<ISINK_SCALAR, true, true>, kThreads, n, kThreads * 16), kThreads, 0, st>>>(A);
+                else image_scatter_kernel<ISINK_SCALAR, true, false><<<grid_for(image_scatter_kernel<ISINK_SCALAR, true, false>, kThreads, n, kThreads * 16), kThreads, 0, st>>>(A);
             } else if (variant == EVK_VARIANT_WARP_AGG) {
-                if (vec4) image_scatter_kernel<ISINK_WARPAGG, false, true><<<grid, kThreads, 0, st>>>(A);
-                else image_scatter_kernel<ISINK_WARPAGG, false, false><<<grid, kThreads, 0, st>>>(A);
+                if (vec4) image_scatter_kernel<ISINK_WARPAGG, false, true><<<grid_for(image_scatter_kernel<ISINK_WARPAGG, false, true>, kThreads, n, kThreads * 16), kThreads, 0, st>>>(A);
+                else image_scatter_kernel<ISINK_WARPAGG, false, false><<<grid_for(image_scatter_kernel<ISINK_WARPAGG, false, false>, kThreads, n, kThreads * 16), kThreads, 0, st>>>(A);
             } else {
-                if (vec4) image_scatter_kernel<ISINK_SCALAR, false, true><<<grid, kThreads, 0, st>>>(A);
-                else image_scatter_kernel<ISINK_SCALAR, false, false><<<grid, kThreads, 0, st>>>(A);
+                if (vec4) image_scatter_kernel<ISINK_SCALAR, false, true><<<grid_for(image_scatter_kernel<ISINK_SCALAR, false, true>, kThreads, n, kThreads * 16), kThreads, 0, st>>>(A);
+                else image_scatter_kernel<ISINK_SCALAR, false, false><<<grid_for(image_scatter_kernel<ISINK_SCALAR, false, false>, kThreads, n, kThreads * 16), kThreads, 0, st>>>(A);
             }
         }
     } else {
@@ -369,11 +368,10 @@ int evk_count_u32(const float *x, const float *y, int64_t n, int Himg, int Wimg,
     A.out_u32 = out; A.oob = oob;
     if (!(flags & EVK_ACCUMULATE)) EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)Himg * Wimg * sizeof(unsigned), st));
     if (n > 0) {
-        const int grid = grid_for(n, kThreads * 8, 8);
         ProfScope prof(st);
         prof_count(1);
-        if (variant_of(flags) == EVK_VARIANT_GLOBAL_RED) count_kernel<false><<<grid, kThreads, 0, st>>>(A);
-        else count_kernel<true><<<grid, kThreads, 0, st>>>(A);
+        if (variant_of(flags) == EVK_VARIANT_GLOBAL_RED) count_kernel<false><<<grid_for(count_kernel<false>, kThreads, n, kThreads * 8), kThreads, 0, st>>>(A);
+        else count_kernel<true><<<grid_for(count_kernel<true>, kThreads, n, kThreads * 8), kThreads, 0, st>>>(A);
     }
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;
@@ -386,7 +384,7 @@ int evk_warp_flow_f32(const float *x, const float *y, const float *t, int64_t n,
     if (n < 0 || H < 1 || W < 1 || !flow || (n > 0 && (!x || !y || !t || !xw || !yw))) { set_error("evk_warp_flow_f32: bad arguments"); return EVK_E_ARG; }
     if (n == 0) return EVK_OK;
     prof_count(1);
-    warp_flow_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, t, n, flow, H, W, t0, xw, yw);
+    warp_flow_kernel<<<grid_for(warp_flow_kernel, 256, n, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, t, n, flow, H, W, t0, xw, yw);
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

@@ -135,7 +135,7 @@ int evk_splat_idx_f32(const int64_t *px, const int64_t *py, const float *dx, con
     using namespace evk;
     if (n < 0 || H < 2 || W < 2 || !img || (n > 0 && (!px || !py || !dx || !dy || !w))) { set_error("evk_splat_idx_f32: bad arguments"); return EVK_E_ARG; }
     if (n == 0) return EVK_OK;
-    splat_idx_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    splat_idx_kernel<<<grid_for(splat_idx_kernel, 256, n, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         (const long long *)px, (const long long *)py, dx, dy, w, n, H, W, img, oob);
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;
@@ -148,7 +148,7 @@ int evk_splat_drv_idx_f32(const int64_t *px, const int64_t *py, const float *dx,
     using namespace evk;
     if (n < 0 || K < 1 || H < 2 || W < 2 || !dimg || (n > 0 && (!px || !py || !dx || !dy || !w1 || !w2))) { set_error("evk_splat_drv_idx_f32: bad arguments"); return EVK_E_ARG; }
     if (n == 0) return EVK_OK;
-    splat_drv_idx_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    splat_drv_idx_kernel<<<grid_for(splat_drv_idx_kernel, 256, n, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         (const long long *)px, (const long long *)py, dx, dy, w1, w2, K, n, H, W, dimg, oob);
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;
@@ -170,7 +170,7 @@ int evk_image_drv_f32(const float *x, const float *y, const float *p, const floa
         if (K > 0) EVK_CUDA(cudaMemsetAsync(dimg, 0, plane * K, st));
     }
     if (n > 0) {
-        image_drv_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, st>>>(x, y, p, jx, jy, K, n, Himg, Wimg,
+        image_drv_kernel<<<grid_for(image_drv_kernel, 256, n, 256 * 4), 256, 0, st>>>(x, y, p, jx, jy, K, n, Himg, Wimg,
                                                                   (flags & EVK_CLIP) ? 1 : 0, clipx, clipy, img, dimg, oob);
         EVK_CUDA(cudaGetLastError());
     }
@@ -183,7 +183,7 @@ int evk_gather_bilinear_f64(const double *x, const double *y, int64_t n, const d
     using namespace evk;
     if (n < 0 || H < 2 || W < 2 || !img || (n > 0 && (!x || !y || !out))) { set_error("evk_gather_bilinear_f64: bad arguments"); return EVK_E_ARG; }
     if (n == 0) return EVK_OK;
-    gather_bilinear_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, img, H, W, out, oob);
+    gather_bilinear_kernel<<<grid_for(gather_bilinear_kernel, 256, n, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, img, H, W, out, oob);
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

@@ -297,8 +297,9 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
     }
     if (A.n > 0) {
         const int per_thread = (layout == LAYOUT_SOA4) ? 4 : 1;
-        const int grid = grid_for(A.n, kThreads * per_thread * 4, 8);
-#define EVK_LAUNCH(S, BL, L) voxel_scatter_kernel<S, BL, L><<<grid, kThreads, 0, st>>>(A)
+#define EVK_LAUNCH(S, BL, L)                                                                                   \
+    voxel_scatter_kernel<S, BL, L><<<grid_for(voxel_scatter_kernel<S, BL, L>, kThreads, A.n, kThreads * per_thread * 4), \
+                                     kThreads, 0, st>>>(A)
 #define EVK_DISPATCH_L(S, BL)                                  \
     do {                                                       \
         if (layout == LAYOUT_SOA4) EVK_LAUNCH(S, BL, LAYOUT_SOA4); \
@@ -316,7 +317,7 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
         EVK_CUDA(cudaGetLastError());
     }
     if (sink == SINK_QUAD) {
-        const int grid = grid_for(npix, 256, 8);
+        const int grid = grid_simple(npix, 256);
         prof_count(1);
         if (accum) voxel_fold_kernel<true><<<grid, 256, 0, st>>>(A.ws, A.out, npix, A.B, A.nq);
         else voxel_fold_kernel<false><<<grid, 256, 0, st>>>(A.ws, A.out, npix, A.B, A.nq);

@@ -181,6 +181,31 @@ def test_flow_objective_c_abi(oracle):
     assert abs(res[0].item() - oracle.variance_f(ref_iwe, 1.0)) <= 1e-5 * abs(oracle.variance_f(ref_iwe, 1.0))
 
 
+def test_paired_and_single_lane_kernels_agree(oracle):
+    """The lane-paired scatter (default) and the one-lane-per-event scatter compute the same taps."""
+    import torch
+    from event_utils_b200 import _lib
+    L = _lib.lib()
+    x, y, t, p = make_events(33, 400001, 180, 240, dtype=np.float64, pol="real")
+    X, Y, T, P = (torch.from_numpy(a).cuda() for a in (x, y, t, p))
+    ws = torch.empty(L.evk_cmax_workspace_bytes(180, 240), dtype=torch.uint8, device="cuda")
+    res = torch.empty(8, dtype=torch.float64, device="cuda")
+    iwe = torch.empty((181, 241), device="cuda")
+    diwe = torch.empty((2, 181, 241), device="cuda")
+    ref_iwe, ref_d = oracle.iwe_linvel((25.0, 70.0), x, y, t, p, (180, 240), True)
+    out = []
+    for variant in (0, _lib.VARIANT_GLOBAL_RED):
+        _lib.check(L.evk_cmax_linvel_variance_f64(X.data_ptr(), Y.data_ptr(), T.data_ptr(), P.data_ptr(), x.shape[0], 1.0,
+                                                  25.0, 70.0, float(t[-1]), 180, 240, 180, 240, 1.0,
+                                                  _lib.CMAX_WANT_GRAD | variant, res.data_ptr(), iwe.data_ptr(),
+                                                  diwe.data_ptr(), ws.data_ptr(), ws.numel(), None))
+        torch.cuda.synchronize()
+        assert_close_to_max(iwe.cpu().numpy(), ref_iwe, 1e-5)
+        assert_close_to_max(diwe.cpu().numpy(), ref_d, 1e-5)
+        out.append(res.cpu().numpy().copy())
+    assert np.abs(out[0][:3] - out[1][:3]).max() <= 1e-6 * np.abs(out[1][:3]).max()
+
+
 def test_full_size_properties():
     """BASELINE config 3 size (50 M events): properties that do not need the CPU oracle."""
     import torch

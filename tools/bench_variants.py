@@ -143,7 +143,7 @@ for scene in ("uniform", "lattice"):
     res = torch.empty(8, dtype=torch.float64, device=dev)
     tl = float(t64[-1])
     for params in ((45.0, -20.0), (60.0, -35.0)):
-        for fl, nm in ((_lib.CMAX_WANT_GRAD, "f+g"), (0, "f")):
+        for fl, nm in ((_lib.CMAX_WANT_GRAD, "f+g paired"), (_lib.CMAX_WANT_GRAD | _lib.VARIANT_GLOBAL_RED, "f+g 1lane"), (0, "f paired")):
             def run(fl=fl, params=params):
                 _lib.check(L.evk_cmax_linvel_variance_f64(x64.data_ptr(), y64.data_ptr(), t64.data_ptr(), p64.data_ptr(), N, 1.0,
                                                           params[0], params[1], tl, 180, 240, 180, 240, 1.0, fl, res.data_ptr(),
