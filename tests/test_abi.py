@@ -1,0 +1,82 @@
+"""No-GPU checks of the boundary: libevk.so loads, exports every symbol include/evk.h declares,
+reports its version, and the host-side argument logic behaves."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "evk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(evk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from event_utils_b200 import _lib
+    L = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), "libevk.so does not export %s" % n
+    assert L.evk_version() == 100
+    assert isinstance(L.evk_last_error(), bytes)
+
+
+def test_workspace_queries_need_no_gpu():
+    from event_utils_b200 import _lib
+    L = _lib.load()
+    assert L.evk_voxel_workspace_bytes(5, 480, 640, 0) == 480 * 640 * 2 * 16   # two quads per pixel
+    assert L.evk_voxel_workspace_bytes(1, 10, 10, 0) == 10 * 10 * 16
+    assert L.evk_voxel_workspace_bytes(4, 10, 10, 0) == 10 * 10 * 16
+    assert L.evk_voxel_workspace_bytes(8, 10, 10, 0) == 10 * 10 * 3 * 16
+    assert L.evk_image_workspace_bytes(181, 241, _lib.BILINEAR) == 181 * 80 * 16
+    assert L.evk_image_workspace_bytes(181, 241, 0) == 0
+    assert L.evk_cmax_workspace_bytes(180, 240) >= 8 * 181 * 241 * 16
+
+
+def test_compute_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from event_utils_b200 import _lib
+    from event_utils_b200.representations.voxel_grid import events_to_voxel_torch
+    with pytest.raises(_lib.EvkError):
+        _lib.lib()
+    x = torch.zeros(4)
+    with pytest.raises(_lib.EvkError):
+        events_to_voxel_torch(x, x, torch.arange(4.0), x, 3)
+
+
+def test_host_side_argument_logic():
+    from event_utils_b200.representations import _events as E
+    from event_utils_b200.representations.image import _canvas_and_clip
+    from event_utils_b200.representations.voxel_grid import events_to_voxel_torch
+    # image.py:64-67, 73-74
+    assert _canvas_and_clip((180, 240), None, True) == ((180, 240), 239.0, 179.0)
+    assert _canvas_and_clip((180, 240), None, False) == ((180, 240), 240.0, 180.0)
+    assert _canvas_and_clip((180, 240), 'bilinear', True) == ((181, 241), 240.0, 180.0)
+    assert _canvas_and_clip((180, 240), 'bilinear', False) == ((180, 240), 239.0, 179.0)
+    # AoS detection
+    ev = torch.arange(40, dtype=torch.float32).reshape(10, 4)
+    assert E.aos_base(ev[:, 0], ev[:, 1], ev[:, 2], ev[:, 3]) is not None
+    assert E.aos_base(ev[:, 1], ev[:, 0], ev[:, 2], ev[:, 3]) is None
+    assert E.aos_base(ev[:, 0].clone(), ev[:, 1], ev[:, 2], ev[:, 3]) is None
+    # reference error conventions that do not need the GPU
+    x = torch.zeros(4)
+    with pytest.raises(AssertionError):
+        events_to_voxel_torch(x, x[:3], x, x, 3)
+    with pytest.raises(NotImplementedError):
+        events_to_voxel_torch(x, x, x, x, 3, temporal_bilinear=False)
+    with pytest.raises(IndexError):
+        events_to_voxel_torch(x[:0], x[:0], x[:0], x[:0], 3)
+
+
+def test_bounds_mask_known_answer():
+    from event_utils_b200.util.event_util import events_bounds_mask
+    m = events_bounds_mask(np.array([0, 1e-9, 240, 240.1]), np.array([5.0, 5, 5, 5]), 0, 240, 0, 180)
+    assert m.tolist() == [0.0, 1.0, 1.0, 0.0]
