@@ -4,6 +4,8 @@
 #include <float.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "evk.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -39,6 +41,11 @@ struct ProfScope {
     ProfScope(cudaStream_t s);
     ~ProfScope();
 };
+
+// evk_hot.cu: adaptive shared-memory write-combining scatter (mode 0 nearest f32, 1 bilinear f32, 2 count u32)
+int launch_image_hot(const float *x, const float *y, const float *p, int64_t n, int H, int W, int clip, float clipx,
+                     float clipy, int mode, int force_cache, float *out, unsigned *out_u32, unsigned long long *oob,
+                     cudaStream_t st);
 
 static inline unsigned variant_of(unsigned flags) { return flags & EVK_VARIANT_MASK; }
 

@@ -305,8 +305,11 @@ int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int
     A.out = out; A.oob = oob;
     A.nqx = quads_for_cols(Wimg);
     unsigned variant = variant_of(flags);
+    // AUTO: large nearest streams take the adaptive hot-spot kernel (it falls back to plain global
+    // reductions by itself when the stream is not contended); bilinear keeps the vector-red form.
     if (variant == EVK_VARIANT_AUTO)
-        variant = (bil && workspace && n >= ((int64_t)1 << 20)) ? EVK_VARIANT_VECTOR_RED : EVK_VARIANT_GLOBAL_RED;
+        variant = (bil && workspace && n >= ((int64_t)1 << 20)) ? EVK_VARIANT_VECTOR_RED
+                  : (!bil && n >= ((int64_t)1 << 18)) ? EVK_VARIANT_SMEM_TILE : EVK_VARIANT_GLOBAL_RED;
     if (variant == EVK_VARIANT_VECTOR_RED && !bil) variant = EVK_VARIANT_GLOBAL_RED;
     if (variant == EVK_VARIANT_WARP_AGG && bil) variant = EVK_VARIANT_GLOBAL_RED;
     const int64_t npix = (int64_t)Himg * Wimg;
@@ -348,6 +351,15 @@ int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int
                 else image_scatter_kernel<ISINK_SCALAR, false, false><<<grid_for(image_scatter_kernel<ISINK_SCALAR, false, false>, kThreads, n, kThreads * 16), kThreads, 0, st>>>(A);
             }
         }
+    } else if (variant == EVK_VARIANT_SMEM_TILE) {
+        if (!accum) {
+            if (fill == 0.0f) EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)npix * sizeof(float), st));
+            else { prof_count(1); fill_kernel<<<grid_simple(npix, 256), 256, 0, st>>>(out, npix, fill); }
+        }
+        // explicit request = cache always on; reached through AUTO = adaptive
+        const int force = variant_of(flags) == EVK_VARIANT_SMEM_TILE ? 1 : 0;
+        int rc = launch_image_hot(x, y, p, n, Himg, Wimg, A.clip, clipx, clipy, bil ? 1 : 0, force, out, nullptr, oob, st);
+        if (rc) return rc;
     } else {
         set_error("evk_image_f32: variant 0x%x not available", variant);
         return EVK_E_UNSUPPORTED;
@@ -367,7 +379,12 @@ int evk_count_u32(const float *x, const float *y, int64_t n, int Himg, int Wimg,
     A.clip = (flags & EVK_CLIP) ? 1 : 0; A.clipx = clipx; A.clipy = clipy;
     A.out_u32 = out; A.oob = oob;
     if (!(flags & EVK_ACCUMULATE)) EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)Himg * Wimg * sizeof(unsigned), st));
-    if (n > 0) {
+    const unsigned cvariant = variant_of(flags);
+    if (n > 0 && (cvariant == EVK_VARIANT_SMEM_TILE || cvariant == EVK_VARIANT_AUTO)) {
+        int rc = launch_image_hot(x, y, nullptr, n, Himg, Wimg, A.clip, clipx, clipy, 2, cvariant == EVK_VARIANT_SMEM_TILE ? 1 : 0,
+                                  nullptr, out, oob, st);
+        if (rc) return rc;
+    } else if (n > 0) {
         ProfScope prof(st);
         prof_count(1);
         if (variant_of(flags) == EVK_VARIANT_GLOBAL_RED) count_kernel<false><<<grid_for(count_kernel<false>, kThreads, n, kThreads * 8), kThreads, 0, st>>>(A);

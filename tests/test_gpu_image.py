@@ -20,7 +20,7 @@ def dev(*arrs):
     return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrs]
 
 
-@pytest.mark.parametrize("variant", [None, "global_red", "vector_red", "warp_agg"])
+@pytest.mark.parametrize("variant", [None, "global_red", "vector_red", "warp_agg", "smem_cache"])
 def test_golden_variants(variant):
     import event_utils_b200 as eu
     from event_utils_b200.representations.image import events_to_image_torch
@@ -61,7 +61,7 @@ def test_known_answers():
     assert not out.is_cuda and np.array_equal(out.numpy(), g["k1_default"])
 
 
-@pytest.mark.parametrize("variant", ["global_red", "vector_red", "warp_agg"])
+@pytest.mark.parametrize("variant", [None, "global_red", "vector_red", "warp_agg", "smem_cache"])
 @pytest.mark.parametrize("bil", [False, True])
 def test_vs_oracle_large(oracle, variant, bil):
     import event_utils_b200 as eu
@@ -86,7 +86,7 @@ def zipf_events(seed, n, H, W, s=1.0):
     return (pix % W).astype(np.float32), (pix // W).astype(np.float32)
 
 
-@pytest.mark.parametrize("variant", ["global_red", "warp_agg"])
+@pytest.mark.parametrize("variant", [None, "global_red", "warp_agg", "smem_cache"])
 def test_hot_spot_counts_bit_exact(oracle, variant):
     """Zipf-distributed pixels (BASELINE config 4, reduced N): count image must be bit exact."""
     import event_utils_b200 as eu
@@ -104,11 +104,28 @@ def test_hot_spot_counts_bit_exact(oracle, variant):
     L = _lib.lib()
     cnt = torch.empty((H, W), dtype=torch.int32, device="cuda")
     oob = torch.zeros(1, dtype=torch.int64, device="cuda")
-    for v in (_lib.VARIANT_GLOBAL_RED, _lib.VARIANT_WARP_AGG):
+    for v in (_lib.VARIANT_AUTO, _lib.VARIANT_GLOBAL_RED, _lib.VARIANT_WARP_AGG, _lib.VARIANT_SMEM_TILE):
         _lib.check(L.evk_count_u32(X.data_ptr(), Y.data_ptr(), n, H, W, 0.0, 0.0, v, cnt.data_ptr(), oob.data_ptr(), None))
         torch.cuda.synchronize()
         assert np.array_equal(cnt.cpu().numpy().astype(np.float32), ref)
         assert int(cnt.sum()) == n
+
+
+def test_hot_spot_bilinear_and_signed(oracle):
+    """Zipf stream with +-1 polarities and sub-pixel jitter through the bilinear cache path."""
+    import event_utils_b200 as eu
+    from event_utils_b200.representations.image import events_to_image_torch
+    H, W, n = 720, 1280, 2_000_000
+    x, y = zipf_events(7, n, H, W, s=1.2)
+    rng = np.random.default_rng(8)
+    x = x + rng.random(n).astype(np.float32) * 0.999
+    y = y + rng.random(n).astype(np.float32) * 0.999
+    p = (rng.integers(0, 2, n) * 2 - 1).astype(np.float32)
+    ref = oracle.image_torch_f32(x, y, p, sensor_size=(H, W), interpolation='bilinear')
+    for variant in ("smem_cache", "vector_red", "global_red"):
+        eu.config.variant = variant
+        out = events_to_image_torch(*dev(x, y, p), sensor_size=(H, W), interpolation='bilinear').cpu().numpy()
+        assert_close_to_max(out, ref, 1e-5, variant)
 
 
 def test_numpy_flavour():

@@ -101,21 +101,21 @@ for dist in ("uniform", "zipf1.0", "zipf1.2"):
         pi = torch.ones(N, device=dev)
     img = torch.empty((Hi + 1, Wi + 1), device=dev)
     wsi = torch.empty(max(256, L.evk_image_workspace_bytes(Hi + 1, Wi + 1, _lib.BILINEAR)), dtype=torch.uint8, device=dev)
-    for name, v in (("global_red", _lib.VARIANT_GLOBAL_RED), ("warp_agg", _lib.VARIANT_WARP_AGG)):
+    for name, v in (("global_red", _lib.VARIANT_GLOBAL_RED), ("warp_agg", _lib.VARIANT_WARP_AGG), ("smem_cache", _lib.VARIANT_SMEM_TILE), ("auto", 0)):
         def run(v=v):
             _lib.check(L.evk_image_f32(xi.data_ptr(), yi.data_ptr(), pi.data_ptr(), N, Hi, Wi, 0.0, 0.0, v, 0.0, img.data_ptr(),
                                        wsi.data_ptr(), wsi.numel(), oob.data_ptr(), None))
         best, avg = timeit(run, iters=3, warm=1)
         report("image nearest %s %s" % (dist, name), best, N, 12, 4 * Hi * Wi)
     cnt = torch.empty((Hi, Wi), dtype=torch.int32, device=dev)
-    for name, v in (("global_red", _lib.VARIANT_GLOBAL_RED), ("warp_agg", _lib.VARIANT_WARP_AGG)):
+    for name, v in (("global_red", _lib.VARIANT_GLOBAL_RED), ("warp_agg", _lib.VARIANT_WARP_AGG), ("smem_cache", _lib.VARIANT_SMEM_TILE), ("auto", 0)):
         def run(v=v):
             _lib.check(L.evk_count_u32(xi.data_ptr(), yi.data_ptr(), N, Hi, Wi, 0.0, 0.0, v, cnt.data_ptr(), oob.data_ptr(), None))
         best, avg = timeit(run, iters=3, warm=1)
         report("count u32 %s %s" % (dist, name), best, N, 8, 4 * Hi * Wi)
     xb = xi + torch.rand(N, device=dev) * 0.999 if dist != "uniform" else xi
     yb = yi + torch.rand(N, device=dev) * 0.999 if dist != "uniform" else yi
-    for name, v in (("global_red", _lib.VARIANT_GLOBAL_RED), ("vector_red", _lib.VARIANT_VECTOR_RED)):
+    for name, v in (("global_red", _lib.VARIANT_GLOBAL_RED), ("vector_red", _lib.VARIANT_VECTOR_RED), ("smem_cache", _lib.VARIANT_SMEM_TILE)):
         def run(v=v):
             _lib.check(L.evk_image_f32(xb.data_ptr(), yb.data_ptr(), pi.data_ptr(), N, Hi + 1, Wi + 1, float(Wi), float(Hi),
                                        v | _lib.BILINEAR | _lib.CLIP, 0.0, img.data_ptr(), wsi.data_ptr(), wsi.numel(), oob.data_ptr(), None))
