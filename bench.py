@@ -69,40 +69,46 @@ def workload_config(world):
 # clocks during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock and throttle reasons through NVML every ~2 ms while the timed region runs
-    (nvidia-smi -lms cannot sample a region that only lasts tens of milliseconds)."""
+    """Samples the SM clock and the throttle reasons through NVML in a background thread.  NVML is
+    initialised up front so that the first sample falls inside the (tens of ms) timed region; every
+    sample is time-stamped and `summary(t0, t1)` reports the ones taken inside a window."""
+
+    BITS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop, self.th, self.err = threading.Event(), None, None
-
-    def _run(self):
+        self.samples, self.max_mhz, self.err = [], None, None
+        self._stop, self.th, self.h, self.nv = threading.Event(), None, None, None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            # honour CUDA_VISIBLE_DEVICES: map the torch device to its NVML handle through the UUID
-            try:
-                uuid = torch.cuda.get_device_properties(self.index).uuid
-                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            try:   # honour CUDA_VISIBLE_DEVICES: go through the UUID of the torch device
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
             except Exception:
-                h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-            while not self._stop.is_set():
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for name, bit in bits.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.002)
+                self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.nv = nv
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
 
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, int(r)))
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                return
+            time.sleep(0.001)
+
     def start(self):
+        if self.nv is None:
+            return
         self.th = threading.Thread(target=self._run, daemon=True)
         self.th.start()
 
@@ -110,8 +116,12 @@ class ClockSampler:
         self._stop.set()
         if self.th is not None:
             self.th.join(timeout=2)
-        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
-               "samples": len(self.sm), "reasons": sorted(self.reasons)}
+
+    def summary(self, t0, t1):
+        rows = [s for s in self.samples if t0 <= s[0] <= t1]
+        reasons = sorted(n for n, b in self.BITS.items() if any(r[2] & b for r in rows))
+        out = {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(rows), "reasons": reasons}
         if self.err:
             out["error"] = self.err
         return out
@@ -275,16 +285,17 @@ def run_ours(args, rank, local_rank, world):
     L.evk_prof_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_dev0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    t_dev1 = time.perf_counter()
     elapsed_ms = e0.elapsed_time(e1)
     kms, ktimed, klaunch = ctypes.c_double(0), ctypes.c_longlong(0), ctypes.c_longlong(0)
     L.evk_prof_collect(ctypes.byref(kms), ctypes.byref(ktimed), ctypes.byref(klaunch))
     L.evk_prof_enable(0)
-    clocks = sampler.stop() if rank == 0 else None
     assert int(oob.item()) == 0
     # sanity inside the bench: every event deposits its polarity once
     total = float(out.double().sum())
@@ -341,6 +352,15 @@ def run_ours(args, rank, local_rank, world):
         res = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - s
+    clocks = None
+    if rank == 0:
+        sampler.stop()
+        clocks = sampler.summary(t_dev0, t_dev1)
+        clocks["e2e_region"] = sampler.summary(s, s + e2e_s)
+        if not clocks["samples"]:   # device region shorter than one NVML poll: fall back to the e2e region
+            for k in ("sm_mhz", "reasons"):
+                clocks[k] = clocks["e2e_region"][k]
+            clocks["note"] = "device-timed region too short for an NVML sample; values from the e2e region"
     if world > 1:
         el = torch.tensor([e2e_s], device=device, dtype=torch.float64)
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
@@ -433,6 +453,31 @@ def secondary_metrics(L, _lib, device, peak):
     except Exception as e:  # pragma: no cover
         out["cmax_cpu_port"] = {"error": repr(e)}
     del x, y, t, p
+    torch.cuda.empty_cache()
+    # event image on a hot-spot (Zipf) stream vs a uniform one (BASELINE configs[3] shape: 1280x720)
+    Hi, Wi = 720, 1280
+    g = torch.Generator(device=device).manual_seed(99)
+    npx = Hi * Wi
+    img = torch.empty((Hi, Wi), dtype=torch.float32, device=device)
+    oob = torch.zeros(1, dtype=torch.int64, device=device)
+    for name, s_exp in (("uniform", None), ("zipf_s1.0", 1.0), ("zipf_s1.2", 1.2)):
+        if s_exp is None:
+            xi = torch.rand(n, device=device, generator=g) * (Wi - 1)
+            yi = torch.rand(n, device=device, generator=g) * (Hi - 1)
+        else:
+            w = 1.0 / torch.arange(1, npx + 1, device=device, dtype=torch.float64) ** s_exp
+            cdf = torch.cumsum(w, 0) / w.sum()
+            ranks = torch.searchsorted(cdf, torch.rand(n, device=device, generator=g, dtype=torch.float64)).clamp_(max=npx - 1)
+            pix = torch.randperm(npx, device=device, generator=g)[ranks]
+            xi, yi = (pix % Wi).float(), (pix // Wi).float()
+            del w, cdf, ranks, pix
+        pi = torch.ones(n, device=device)
+        ms = best_of(lambda: _lib.check(L.evk_image_f32(xi.data_ptr(), yi.data_ptr(), pi.data_ptr(), n, Hi, Wi, 0.0, 0.0, 0, 0.0,
+                                                        img.data_ptr(), None, 0, oob.data_ptr(), _lib.stream())))
+        assert abs(float(img.double().sum()) - n) < 1.0      # count image: exact
+        out["image_nearest_" + name] = {"mevents_per_s": n / ms / 1e3, "ms": ms, "events": n,
+                                        "roofline_frac": (12.0 * n + 4.0 * npx) / (ms * 1e-3) / 1e9 / peak}
+        del xi, yi, pi
     torch.cuda.empty_cache()
     return out
 
