@@ -12,11 +12,16 @@
 //   warp_events_flow_torch + IWE  lib/transforms/optic_flow.py:37-44, lib/visualization/draw_flow.py:18-21
 //
 // B200 design:
-//   * ONE pass over the events.  The IWE and both derivative images are interleaved per pixel
-//     as float4 {I, D0, D1, 0}; each of the 4 bilinear taps of an event is ONE
-//     red.global.add.v4.f32 (REDG.E.ADD.F32x4) that updates all three images at once, so the
-//     gradient costs no extra reduction traffic.  The accumulator (181*241*16 B = 698 KB per
-//     replica, R replicas to spread same-address serialisation) never leaves L2.
+//   * ONE pass over the events.  The accumulator is an array of 64-byte BLOCKS, one per pixel:
+//     block (y,x) = {I[4], D0[4], D1[4], pad[4]} holds the four bilinear taps TL,TR,BL,BR of every
+//     event whose footprint is anchored at (y,x) (each pixel therefore lives in four blocks; a
+//     gather kernel folds them).  The whole 2x2 footprint of an event in one image is then ONE
+//     red.global.add.v4.f32 (REDG.E.ADD.F32x4): 1 vector reduction per event for f, 3 (in two
+//     32-byte sectors of one 128-byte line) for f and g, instead of 4 / 12 scalar ones.  The
+//     limiter is the number of 32-byte sectors the L2 atomic units touch per event (ncu: r1 layout
+//     with 3 sectors/event ran at the same sector rate as the voxel kernel).  The accumulator
+//     (181*241*64 B = 2.8 MB per replica, R <= 8 replicas against same-address serialisation) never
+//     leaves L2.
 //   * The reference blurs both derivative images and multiplies by the un-blurred IWE.  The
 //     reflect-boundary Gaussian is self-adjoint, so  sum(2(I-mu) * G(D_k)) == sum(G(2(I-mu)) * D_k)
 //     and G(2(I-mu)) = 2(G(I)-mu): ONE blur of ONE image (which f needs anyway) serves f and g.
@@ -31,6 +36,7 @@ namespace evk {
 
 constexpr int kMaxRadius = 64;
 constexpr int kMaxReplicas = 8;
+constexpr int kBlockFloats = 16;  // one 64-byte block per pixel: {I[4], D0[4], D1[4], pad[4]}
 
 struct BlurTaps {
     int r;
@@ -78,40 +84,44 @@ __device__ __forceinline__ void splat(const CmaxArgs &A, float *acc, float xf, f
     const float am = GRAD ? __fmul_rn(a, wm) : 0.0f;  // jacobian * masked_ps (image.py:211-212)
     if (wm == 0.0f && am == 0.0f) return;
     const float ox = __fsub_rn(1.0f, dx), oy = __fsub_rn(1.0f, dy);
-    if (PAIR) {
-        // this lane's column: weight along x, the x index, and the sign pattern of image.py:131-135
-        const float wx = xt ? dx : ox;
-        const int xc = xt ? x1 : x0;
-        const float wc = __fmul_rn(wm, wx);
-        float4 r0, r1;
-        r0.x = __fmul_rn(wc, oy);
-        r1.x = __fmul_rn(wc, dy);
-        if (GRAD) {
-            r0.y = __fmul_rn(am, xt ? oy : -oy); r1.y = __fmul_rn(am, xt ? dy : -dy);
-            r0.z = __fmul_rn(am, -wx);           r1.z = __fmul_rn(am, wx);
+    const float wl = __fmul_rn(wm, ox), wr = __fmul_rn(wm, dx);
+    // tap order inside a block: TL (y0,x0), TR (y0,x1), BL (y1,x0), BR (y1,x1)
+    const float4 ti = make_float4(__fmul_rn(wl, oy), __fmul_rn(wr, oy), __fmul_rn(wl, dy), __fmul_rn(wr, dy));
+    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+    if (GRAD) {
+        t0 = make_float4(__fmul_rn(am, -oy), __fmul_rn(am, oy), __fmul_rn(am, -dy), __fmul_rn(am, dy));   // d/dvx
+        t1 = make_float4(__fmul_rn(am, -ox), __fmul_rn(am, -dx), __fmul_rn(am, ox), __fmul_rn(am, dx));   // d/dvy
+    }
+    if (x1 == x0 + 1 && y1 == y0 + 1) {
+        // the whole 2x2 footprint is ONE block: a single 16-byte vector reduction per image
+        float *blk = acc + ((int64_t)y0 * A.Wc + x0) * kBlockFloats;
+        if (PAIR) {
+            // lane 0: I block (+0) then D1 block (+8); lane 1: D0 block (+4).  Lanes 0/1 of the
+            // first instruction write the two halves of one 32-byte sector.
+            if (xt == 0) {
+                red_add4(blk, ti);
+                if (GRAD) red_add4(blk + 8, t1);
+            } else if (GRAD) {
+                red_add4(blk + 4, t0);
+            }
         } else {
-            r0.y = r1.y = r0.z = r1.z = 0.0f;
+            red_add4(blk, ti);
+            if (GRAD) { red_add4(blk + 4, t0); red_add4(blk + 8, t1); }
         }
-        r0.w = r1.w = 0.0f;
-        red_add4(acc + ((int64_t)y0 * A.Wc + xc) * 4, r0);
-        red_add4(acc + ((int64_t)y1 * A.Wc + xc) * 4, r1);
         return;
     }
-    const float wl = __fmul_rn(wm, ox), wr = __fmul_rn(wm, dx);
-    float4 v00, v01, v10, v11;
-    v00.x = __fmul_rn(wl, oy); v01.x = __fmul_rn(wr, oy); v10.x = __fmul_rn(wl, dy); v11.x = __fmul_rn(wr, dy);
-    if (GRAD) {
-        v00.y = __fmul_rn(am, -oy); v01.y = __fmul_rn(am, oy); v10.y = __fmul_rn(am, -dy); v11.y = __fmul_rn(am, dy);
-        v00.z = __fmul_rn(am, -ox); v01.z = __fmul_rn(am, -dx); v10.z = __fmul_rn(am, ox); v11.z = __fmul_rn(am, dx);
-    } else {
-        v00.y = v01.y = v10.y = v11.y = 0.0f;
-        v00.z = v01.z = v10.z = v11.z = 0.0f;
+    // wrapped footprint (negative coordinates, only reachable without the bounds mask): every tap
+    // goes to the TL slot of its own block
+    if (xt != 0) return;
+    const float vi[4] = {ti.x, ti.y, ti.z, ti.w}, v0[4] = {t0.x, t0.y, t0.z, t0.w}, v1[4] = {t1.x, t1.y, t1.z, t1.w};
+    const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float *b = acc + ((int64_t)ys[k] * A.Wc + xs[k]) * kBlockFloats;
+        if (vi[k] != 0.0f) red_add(b, vi[k]);
+        if (GRAD && v0[k] != 0.0f) red_add(b + 4, v0[k]);
+        if (GRAD && v1[k] != 0.0f) red_add(b + 8, v1[k]);
     }
-    v00.w = v01.w = v10.w = v11.w = 0.0f;
-    red_add4(acc + ((int64_t)y0 * A.Wc + x0) * 4, v00);
-    red_add4(acc + ((int64_t)y0 * A.Wc + x1) * 4, v01);
-    red_add4(acc + ((int64_t)y1 * A.Wc + x0) * 4, v10);
-    red_add4(acc + ((int64_t)y1 * A.Wc + x1) * 4, v11);
 }
 
 __device__ __forceinline__ float flow_tap(const float *f, int H, int W, int yy, int xx)
@@ -182,7 +192,7 @@ template <int WARP, bool GRAD, bool PAIR>
 __global__ void __launch_bounds__(256) cmax_scatter_kernel(const CmaxArgs A)
 {
     unsigned oob = 0;
-    float *acc = A.acc + (int64_t)(blockIdx.x % A.replicas) * A.Hc * A.Wc * 4;
+    float *acc = A.acc + (int64_t)(blockIdx.x % A.replicas) * A.Hc * A.Wc * kBlockFloats;
     // PAIR: two lanes per event (see splat), so a CTA covers 128 events per sweep
     const int lanes_per_event = PAIR ? 2 : 1;
     const int xt = PAIR ? (threadIdx.x & 1) : 0;
@@ -213,17 +223,28 @@ __device__ __forceinline__ void block_add(double v, double *dst)
     }
 }
 
-__global__ void __launch_bounds__(256) cmax_gather_kernel(const float *__restrict__ acc, int replicas, int npix,
+// Blocks -> planar images.  Block (y,x) holds the 2x2 footprint anchored at (y,x) in tap order
+// TL,TR,BL,BR, so pixel (y,x) collects TL of block (y,x), TR of (y,x-1), BL of (y-1,x) and BR of
+// (y-1,x-1), over all replicas.
+__global__ void __launch_bounds__(256) cmax_gather_kernel(const float *__restrict__ acc, int replicas, int Hc, int Wc,
                                                           float *__restrict__ I, float *__restrict__ D0,
                                                           float *__restrict__ D1, float *__restrict__ iwe_out,
                                                           float *__restrict__ diwe_out, double *sums)
 {
+    const int npix = Hc * Wc;
     const int i = blockIdx.x * 256 + threadIdx.x;
     float a = 0.f, b = 0.f, c = 0.f;
     if (i < npix) {
+        const int y = i / Wc, x = i - y * Wc;
         for (int r = 0; r < replicas; ++r) {
-            const float4 v = reinterpret_cast<const float4 *>(acc)[(int64_t)r * npix + i];
-            a += v.x; b += v.y; c += v.z;
+            const float *base = acc + (int64_t)r * npix * kBlockFloats;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int by = y - (k >> 1), bx = x - (k & 1);
+                if (by < 0 || bx < 0) continue;
+                const float *blk = base + ((int64_t)by * Wc + bx) * kBlockFloats;
+                a += blk[k]; b += blk[4 + k]; c += blk[8 + k];
+            }
         }
         I[i] = a; D0[i] = b; D1[i] = c;
         if (iwe_out) iwe_out[i] = a;
@@ -317,7 +338,7 @@ static size_t carve(void *base, int Hs, int Ws, CmaxWorkspace *ws)
     size_t off = 0;
     char *b = static_cast<char *>(base);
     auto take = [&](size_t bytes) { char *p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
-    float *acc = (float *)take(npix * 4 * sizeof(float) * kMaxReplicas);
+    float *acc = (float *)take(npix * kBlockFloats * sizeof(float) * kMaxReplicas);
     float *I = (float *)take(npix * sizeof(float));
     float *D0 = (float *)take(npix * sizeof(float));
     float *D1 = (float *)take(npix * sizeof(float));
@@ -380,7 +401,7 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, double *result, fl
         if (rc) return rc;
         if (!(flags & EVK_CMAX_NO_CHANNEL_MIX)) mix_coeffs(taps, &mix_a, &mix_b);
     }
-    EVK_CUDA(cudaMemsetAsync(ws.acc, 0, (size_t)R * npix * 4 * sizeof(float), st));
+    EVK_CUDA(cudaMemsetAsync(ws.acc, 0, (size_t)R * npix * kBlockFloats * sizeof(float), st));
     EVK_CUDA(cudaMemsetAsync(ws.sums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.sums), st));  // sums + oob are adjacent
     if (A.n > 0) {
         ProfScope prof(st);
@@ -394,7 +415,7 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, double *result, fl
     }
     prof_count(do_blur ? 4 : 3);
     const int g = (npix + 255) / 256;
-    cmax_gather_kernel<<<g, 256, 0, st>>>(ws.acc, R, npix, ws.I, ws.D0, ws.D1, iwe_out, diwe_out, ws.sums);
+    cmax_gather_kernel<<<g, 256, 0, st>>>(ws.acc, R, A.Hc, A.Wc, ws.I, ws.D0, ws.D1, iwe_out, diwe_out, ws.sums);
     if (do_blur) cmax_blur_axis0_kernel<<<g, 256, 0, st>>>(ws.I, ws.tmp, A.Hc, A.Wc, taps);
     cmax_blur_axis1_sums_kernel<<<g, 256, 0, st>>>(ws.tmp, ws.I, ws.D0, ws.D1, A.Hc, A.Wc, taps, do_blur, ws.sums);
     cmax_final_kernel<<<1, 1, 0, st>>>(ws.sums, ws.oob, npix, mix_a, mix_b, grad ? 1 : 0, result);
@@ -409,12 +430,12 @@ __global__ void __launch_bounds__(256) cmax_pack_kernel(const float *__restrict_
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= npix) return;
-    float4 v;
-    v.x = iwe[i];
-    v.y = diwe ? diwe[i] : 0.0f;
-    v.z = diwe ? diwe[npix + i] : 0.0f;
-    v.w = 0.0f;
-    reinterpret_cast<float4 *>(acc)[i] = v;
+    float4 *blk = reinterpret_cast<float4 *>(acc + (int64_t)i * kBlockFloats);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    blk[0] = make_float4(iwe[i], 0.f, 0.f, 0.f);                      // TL slot of block i = pixel i
+    blk[1] = diwe ? make_float4(diwe[i], 0.f, 0.f, 0.f) : z;
+    blk[2] = diwe ? make_float4(diwe[npix + i], 0.f, 0.f, 0.f) : z;
+    blk[3] = z;
 }
 
 }  // namespace evk
@@ -496,7 +517,7 @@ int evk_variance_objective_f32(const float *iwe, const float *diwe, int Hc, int 
     EVK_CUDA(cudaMemsetAsync(ws.sums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.sums), st));
     const int g = (npix + 255) / 256;
     cmax_pack_kernel<<<g, 256, 0, st>>>(iwe, grad ? diwe : nullptr, npix, ws.acc);
-    cmax_gather_kernel<<<g, 256, 0, st>>>(ws.acc, 1, npix, ws.I, ws.D0, ws.D1, nullptr, nullptr, ws.sums);
+    cmax_gather_kernel<<<g, 256, 0, st>>>(ws.acc, 1, Hc, Wc, ws.I, ws.D0, ws.D1, nullptr, nullptr, ws.sums);
     if (do_blur) cmax_blur_axis0_kernel<<<g, 256, 0, st>>>(ws.I, ws.tmp, Hc, Wc, taps);
     cmax_blur_axis1_sums_kernel<<<g, 256, 0, st>>>(ws.tmp, ws.I, ws.D0, ws.D1, Hc, Wc, taps, do_blur, ws.sums);
     cmax_final_kernel<<<1, 1, 0, st>>>(ws.sums, ws.oob, npix, mix_a, mix_b, grad ? 1 : 0, result);

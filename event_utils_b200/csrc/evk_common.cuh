@@ -54,12 +54,13 @@ static inline unsigned variant_of(unsigned flags) { return flags & EVK_VARIANT_M
 // available.  A grid-stride kernel launched with more CTAs than are resident pays a partial
 // second wave (measured: 1184 CTAs at 5/SM cost 2 wave-times instead of 1.6).
 int resident_ctas_per_sm(const void *kernel, int threads, size_t dyn_smem);
+double grid_waves();  // waves of CTAs per launch (EVK_GRID_WAVES, default in evk_core.cu)
 
 template <typename K>
 static inline int grid_for(K kernel, int threads, int64_t work_items, int items_per_cta, size_t dyn_smem = 0)
 {
     int64_t need = (work_items + items_per_cta - 1) / items_per_cta;
-    int64_t cap = (int64_t)num_sms() * resident_ctas_per_sm((const void *)kernel, threads, dyn_smem);
+    int64_t cap = (int64_t)(num_sms() * resident_ctas_per_sm((const void *)kernel, threads, dyn_smem) * grid_waves());
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
 }

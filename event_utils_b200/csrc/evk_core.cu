@@ -1,6 +1,7 @@
 // evk_core.cu -- error reporting, version and device checks of libevk.so.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "evk_common.cuh"
 
@@ -35,6 +36,16 @@ int num_sms()
         }
     }
     return cached_sms;
+}
+
+double grid_waves()
+{
+    static double w = -1.0;
+    if (w < 0.0) {
+        const char *e = getenv("EVK_GRID_WAVES");
+        w = (e && atof(e) > 0.0) ? atof(e) : 4.0;  // measured on B200: 4 waves of small CTAs balance the tail best
+    }
+    return w;
 }
 
 int resident_ctas_per_sm(const void *kernel, int threads, size_t dyn_smem)

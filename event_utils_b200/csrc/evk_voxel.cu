@@ -156,9 +156,12 @@ __device__ __forceinline__ void voxel_event(const VoxelArgs &A, float x, float y
 }
 
 constexpr int kThreads = 256;
+#ifndef EVK_VOXEL_MIN_CTAS
+#define EVK_VOXEL_MIN_CTAS 8
+#endif
 
 template <int SINK, bool BIL, int LAYOUT>
-__global__ void __launch_bounds__(kThreads) voxel_scatter_kernel(const VoxelArgs A)
+__global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_kernel(const VoxelArgs A)
 {
     unsigned oob = 0;
     const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;

@@ -91,6 +91,8 @@ for name, v in (("global_red", _lib.VARIANT_GLOBAL_RED), ("vector_red", _lib.VAR
 best, _ = timeit(lambda: (x.sum(), y.sum(), t.sum(), p.sum()))
 report("(torch .sum() of the 4 arrays: read-only)", best, N, 16)
 
+if os.environ.get("ONLY") == "voxel":
+    sys.exit(0)
 print("== event image %d events -> 720x1280" % N)
 Hi, Wi = 720, 1280
 for dist in ("uniform", "zipf1.0", "zipf1.2"):
