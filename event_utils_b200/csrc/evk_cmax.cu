@@ -129,13 +129,33 @@ __device__ __forceinline__ float flow_tap(const float *f, int H, int W, int yy, 
     return ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? __ldg(f + (int64_t)yy * W + xx) : 0.0f;
 }
 
+// One event's four components as loaded (f64 in parity mode, f32 otherwise).
+template <int WARP> struct EvT { using type = float; };
+template <> struct EvT<WARP_LINVEL_F64> { using type = double; };
+
+template <int WARP>
+struct Event {
+    typename EvT<WARP>::type x, y, t, p;
+};
+
+template <int WARP>
+__device__ __forceinline__ Event<WARP> load_event(const CmaxArgs &A, int64_t i)
+{
+    using T = typename EvT<WARP>::type;
+    Event<WARP> e;
+    e.x = ld_stream((const T *)A.x + i);
+    e.y = ld_stream((const T *)A.y + i);
+    e.t = ld_stream((const T *)A.t + i);
+    e.p = ld_stream((const T *)A.p + i);
+    return e;
+}
+
 template <int WARP, bool GRAD, bool PAIR>
-__device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, int64_t i, unsigned &oob, int xt)
+__device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const Event<WARP> &e, unsigned &oob, int xt)
 {
     if (WARP == WARP_LINVEL_F64) {
-        const double x = ld_stream((const double *)A.x + i), y = ld_stream((const double *)A.y + i);
-        const double t = ld_stream((const double *)A.t + i);
-        double p = ld_stream((const double *)A.p + i);
+        const double x = e.x, y = e.y, t = e.t;
+        double p = e.p;
         if (A.p_scale != 1.0) p = __dmul_rn(p, A.p_scale);
         if (A.abs_polarity) p = fabs(p);
         const double d = __dsub_rn(t, A.t_ref);
@@ -146,9 +166,9 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, int64_
         if (!keep) return;  // x,y,p,j all multiplied by 0: only exact zeros are added at (0,0)..(1,1)
         splat<GRAD, PAIR>(A, acc, (float)xw, (float)yw, (float)p, (float)(-d), true, oob, xt);  // image.py:180-183 casts
     } else if (WARP == WARP_LINVEL_F32) {
-        const float x = ld_stream((const float *)A.x + i), y = ld_stream((const float *)A.y + i);
-        const float d = ld_stream((const float *)A.t + i);  // already t - t_ref
-        float p = ld_stream((const float *)A.p + i);
+        const float x = e.x, y = e.y;
+        const float d = e.t;  // already t - t_ref
+        float p = e.p;
         if (A.p_scale != 1.0) p = __fmul_rn(p, (float)A.p_scale);
         if (A.abs_polarity) p = fabsf(p);
         const float vx = (float)A.vx, vy = (float)A.vy;
@@ -158,9 +178,8 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, int64_
         splat<GRAD, PAIR>(A, acc, xw, yw, p, -d, true, oob, xt);
     } else {
         // optic_flow.py:37-44 then events_to_image_torch(..., interpolation='bilinear') defaults
-        const float xe = ld_stream((const float *)A.x + i), ye = ld_stream((const float *)A.y + i);
-        const float te = ld_stream((const float *)A.t + i);
-        float p = ld_stream((const float *)A.p + i);
+        const float xe = e.x, ye = e.y, te = e.t;
+        float p = e.p;
         if (A.abs_polarity) p = fabsf(p);
         const int H = A.Hc - 1, W = A.Wc - 1;
         const float *fu = A.flow, *fv = A.flow + (int64_t)H * W;
@@ -188,6 +207,12 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, int64_
     }
 }
 
+// The event pass.  Memory-level parallelism matters as much as the reductions here: each thread
+// first issues the loads of kBatch events (16 independent loads in flight), then warps and
+// splats them (a load -> compute -> red chain per event ran at ~0.9 ms / 50 M events whatever
+// the number of reductions).
+constexpr int kBatch = 4;
+
 template <int WARP, bool GRAD, bool PAIR>
 __global__ void __launch_bounds__(256) cmax_scatter_kernel(const CmaxArgs A)
 {
@@ -198,11 +223,14 @@ __global__ void __launch_bounds__(256) cmax_scatter_kernel(const CmaxArgs A)
     const int xt = PAIR ? (threadIdx.x & 1) : 0;
     const int64_t stride = (int64_t)gridDim.x * (256 / lanes_per_event);
     int64_t i = (int64_t)blockIdx.x * (256 / lanes_per_event) + threadIdx.x / lanes_per_event;
-    for (; i + stride < A.n; i += 2 * stride) {
-        cmax_event<WARP, GRAD, PAIR>(A, acc, i, oob, xt);
-        cmax_event<WARP, GRAD, PAIR>(A, acc, i + stride, oob, xt);
+    for (; i + (kBatch - 1) * stride < A.n; i += kBatch * stride) {
+        Event<WARP> ev[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) ev[k] = load_event<WARP>(A, i + k * stride);
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) cmax_event<WARP, GRAD, PAIR>(A, acc, ev[k], oob, xt);
     }
-    if (i < A.n) cmax_event<WARP, GRAD, PAIR>(A, acc, i, oob, xt);
+    for (; i < A.n; i += stride) cmax_event<WARP, GRAD, PAIR>(A, acc, load_event<WARP>(A, i), oob, xt);
     flush_oob(A.oob, oob);
 }
 

@@ -115,24 +115,24 @@ __device__ __forceinline__ double2 ld_stream2(const double *p) { return __ldcs(r
 // pointer read from a by-value argument struct is a GENERIC pointer and atomicAdd() on it compiles
 // to ATOM.E + shared-memory CAS fall-backs instead of REDG -- and (b) no return value is requested.
 // SASS: REDG.E.ADD.F32 / REDG.E.ADD.F32x2 / REDG.E.ADD.F32x4 (vector forms are sm_90+).
+// No "memory" clobber on purpose: the reductions are relaxed, nothing in the same kernel reads the
+// accumulators back, and the compiler must stay free to hoist the next events' loads above them.
 __device__ __forceinline__ void red_add(float *addr, float v)
 {
-    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "f"(v) : "memory");
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "f"(v));
 }
 __device__ __forceinline__ void red_add4(float *addr16, float4 v)
 {
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(addr16)),
-                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
 __device__ __forceinline__ void red_add2(float *addr8, float2 v)
 {
-    asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(addr8)), "f"(v.x), "f"(v.y)
-                 : "memory");
+    asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(addr8)), "f"(v.x), "f"(v.y));
 }
 __device__ __forceinline__ void red_add_u32(unsigned *addr, unsigned v)
 {
-    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "r"(v) : "memory");
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "r"(v));
 }
 
 __device__ __forceinline__ void flush_oob(unsigned long long *oob, unsigned local)
