@@ -12,16 +12,17 @@
 //   warp_events_flow_torch + IWE  lib/transforms/optic_flow.py:37-44, lib/visualization/draw_flow.py:18-21
 //
 // B200 design:
-//   * ONE pass over the events.  The accumulator is an array of 64-byte BLOCKS, one per pixel:
-//     block (y,x) = {I[4], D0[4], D1[4], pad[4]} holds the four bilinear taps TL,TR,BL,BR of every
-//     event whose footprint is anchored at (y,x) (each pixel therefore lives in four blocks; a
-//     gather kernel folds them).  The whole 2x2 footprint of an event in one image is then ONE
-//     red.global.add.v4.f32 (REDG.E.ADD.F32x4): 1 vector reduction per event for f, 3 (in two
-//     32-byte sectors of one 128-byte line) for f and g, instead of 4 / 12 scalar ones.  The
-//     limiter is the number of 32-byte sectors the L2 atomic units touch per event (ncu: r1 layout
-//     with 3 sectors/event ran at the same sector rate as the voxel kernel).  The accumulator
-//     (181*241*64 B = 2.8 MB per replica, R <= 8 replicas against same-address serialisation) never
-//     leaves L2.
+//   * ONE pass over the events.  The accumulator is an array of 32-byte BLOCKS, one per pixel:
+//     block (y,x) = {I_TL, I_TR, I_BL, I_BR, a, b, c, d} collects every event whose bilinear
+//     footprint is anchored at (y,x) (each pixel therefore lives in four blocks; a gather kernel
+//     folds them).  The 2x2 IWE footprint of an event is ONE red.global.add.v4.f32
+//     (REDG.E.ADD.F32x4); the 8 derivative taps have only 4 free values (the taps of a derivative
+//     image come in +/- pairs, image.py:131-135), so both derivative images are ONE more vector
+//     reduction: 1 RED per event for f, 2 for f and g, instead of 4 / 12 scalar ones.  Measured:
+//     every scatter kernel on B200 costs ~0.25 ms per RED lane-operation per 50 M events,
+//     whatever its width (scalar, v2, v4) and whether or not lanes share a sector -- the count of
+//     reduction operations is what has to be minimised.  The accumulator (181*241*32 B = 1.4 MB
+//     per replica, R <= 8 replicas against same-address serialisation) never leaves L2.
 //   * The reference blurs both derivative images and multiplies by the un-blurred IWE.  The
 //     reflect-boundary Gaussian is self-adjoint, so  sum(2(I-mu) * G(D_k)) == sum(G(2(I-mu)) * D_k)
 //     and G(2(I-mu)) = 2(G(I)-mu): ONE blur of ONE image (which f needs anyway) serves f and g.
@@ -36,7 +37,7 @@ namespace evk {
 
 constexpr int kMaxRadius = 64;
 constexpr int kMaxReplicas = 8;
-constexpr int kBlockFloats = 16;  // one 64-byte block per pixel: {I[4], D0[4], D1[4], pad[4]}
+constexpr int kBlockFloats = 8;   // one 32-byte block (= one L2 sector) per pixel: {I_TL, I_TR, I_BL, I_BR, a, b, c, d}
 
 struct BlurTaps {
     int r;
@@ -67,9 +68,9 @@ enum { WARP_LINVEL_F64 = 0, WARP_LINVEL_F32 = 1, WARP_FLOW_F32 = 2 };
 // contiguous bytes (pixels x0, x0+1 of the interleaved accumulator) in the same instruction, which
 // the LSU merges into one L2 request per row: half the L2 tag look-ups of the one-lane-per-event
 // form (the measured limiter, lts__t_tag_requests ~75 % of peak).
-template <bool GRAD, bool PAIR>
+template <bool GRAD>
 __device__ __forceinline__ void splat(const CmaxArgs &A, float *acc, float xf, float yf, float w, float a,
-                                      bool clip, unsigned &oob, int xt = 0)
+                                      bool clip, unsigned &oob)
 {
     const float clipx = (float)(A.Wc - 1), clipy = (float)(A.Hc - 1);
     float m2 = 1.0f;
@@ -79,7 +80,7 @@ __device__ __forceinline__ void splat(const CmaxArgs &A, float *acc, float xf, f
     int upx, upy, x0, x1, y0, y1;
     if (!trunc_checked(__fmul_rn(pxf, m2), upx) || !trunc_checked(__fmul_rn(pyf, m2), upy) ||
         !wrap_int_index(upx, A.Wc, x0) || !wrap_int_index(upx + 1, A.Wc, x1) ||
-        !wrap_int_index(upy, A.Hc, y0) || !wrap_int_index(upy + 1, A.Hc, y1)) { if (xt == 0) ++oob; return; }
+        !wrap_int_index(upy, A.Hc, y0) || !wrap_int_index(upy + 1, A.Hc, y1)) { ++oob; return; }
     const float wm = __fmul_rn(w, m2);
     const float am = GRAD ? __fmul_rn(a, wm) : 0.0f;  // jacobian * masked_ps (image.py:211-212)
     if (wm == 0.0f && am == 0.0f) return;
@@ -87,40 +88,30 @@ __device__ __forceinline__ void splat(const CmaxArgs &A, float *acc, float xf, f
     const float wl = __fmul_rn(wm, ox), wr = __fmul_rn(wm, dx);
     // tap order inside a block: TL (y0,x0), TR (y0,x1), BL (y1,x0), BR (y1,x1)
     const float4 ti = make_float4(__fmul_rn(wl, oy), __fmul_rn(wr, oy), __fmul_rn(wl, dy), __fmul_rn(wr, dy));
-    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
-    if (GRAD) {
-        t0 = make_float4(__fmul_rn(am, -oy), __fmul_rn(am, oy), __fmul_rn(am, -dy), __fmul_rn(am, dy));   // d/dvx
-        t1 = make_float4(__fmul_rn(am, -ox), __fmul_rn(am, -dx), __fmul_rn(am, ox), __fmul_rn(am, dx));   // d/dvy
-    }
+    // image.py:131-135 with w1 = [am;0], w2 = [0;am]:
+    //   D0 taps = am*{-oy, +oy, -dy, +dy}   -> TL = -TR, BL = -BR : two free values a = am*oy, b = am*dy
+    //   D1 taps = am*{-ox, -dx, +ox, +dx}   -> TL = -BL, TR = -BR : two free values c = am*ox, d = am*dx
+    // (negation is exact and commutes with the sums, so accumulating a,b,c,d and restoring the
+    // signs in the fold gives the same images) -> both derivative images are ONE vector reduction.
+    float4 td = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (GRAD) td = make_float4(__fmul_rn(am, oy), __fmul_rn(am, dy), __fmul_rn(am, ox), __fmul_rn(am, dx));
     if (x1 == x0 + 1 && y1 == y0 + 1) {
-        // the whole 2x2 footprint is ONE block: a single 16-byte vector reduction per image
         float *blk = acc + ((int64_t)y0 * A.Wc + x0) * kBlockFloats;
-        if (PAIR) {
-            // lane 0: I block (+0) then D1 block (+8); lane 1: D0 block (+4).  Lanes 0/1 of the
-            // first instruction write the two halves of one 32-byte sector.
-            if (xt == 0) {
-                red_add4(blk, ti);
-                if (GRAD) red_add4(blk + 8, t1);
-            } else if (GRAD) {
-                red_add4(blk + 4, t0);
-            }
-        } else {
-            red_add4(blk, ti);
-            if (GRAD) { red_add4(blk + 4, t0); red_add4(blk + 8, t1); }
-        }
+        red_add4(blk, ti);
+        if (GRAD) red_add4(blk + 4, td);
         return;
     }
     // wrapped footprint (negative coordinates, only reachable without the bounds mask): every tap
-    // goes to the TL slot of its own block
-    if (xt != 0) return;
-    const float vi[4] = {ti.x, ti.y, ti.z, ti.w}, v0[4] = {t0.x, t0.y, t0.z, t0.w}, v1[4] = {t1.x, t1.y, t1.z, t1.w};
+    // becomes the TL tap of its own pixel's block (TL of D0 is -a, TL of D1 is -c)
+    const float vi[4] = {ti.x, ti.y, ti.z, ti.w};
+    const float v0[4] = {-td.x, td.x, -td.y, td.y}, v1[4] = {-td.z, -td.w, td.z, td.w};
     const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        float *b = acc + ((int64_t)ys[k] * A.Wc + xs[k]) * kBlockFloats;
-        if (vi[k] != 0.0f) red_add(b, vi[k]);
-        if (GRAD && v0[k] != 0.0f) red_add(b + 4, v0[k]);
-        if (GRAD && v1[k] != 0.0f) red_add(b + 8, v1[k]);
+        float *bk = acc + ((int64_t)ys[k] * A.Wc + xs[k]) * kBlockFloats;
+        if (vi[k] != 0.0f) red_add(bk, vi[k]);
+        if (GRAD && v0[k] != 0.0f) red_add(bk + 4, -v0[k]);
+        if (GRAD && v1[k] != 0.0f) red_add(bk + 6, -v1[k]);
     }
 }
 
@@ -150,8 +141,8 @@ __device__ __forceinline__ Event<WARP> load_event(const CmaxArgs &A, int64_t i)
     return e;
 }
 
-template <int WARP, bool GRAD, bool PAIR>
-__device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const Event<WARP> &e, unsigned &oob, int xt)
+template <int WARP, bool GRAD>
+__device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const Event<WARP> &e, unsigned &oob)
 {
     if (WARP == WARP_LINVEL_F64) {
         const double x = e.x, y = e.y, t = e.t;
@@ -164,7 +155,7 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const 
         // event_util.py:26-27: keep iff 0 < x' <= Wm and 0 < y' <= Hm (NaN compares false -> kept)
         const bool keep = !(xw <= 0.0 || xw > (double)A.Wm) && !(yw <= 0.0 || yw > (double)A.Hm);
         if (!keep) return;  // x,y,p,j all multiplied by 0: only exact zeros are added at (0,0)..(1,1)
-        splat<GRAD, PAIR>(A, acc, (float)xw, (float)yw, (float)p, (float)(-d), true, oob, xt);  // image.py:180-183 casts
+        splat<GRAD>(A, acc, (float)xw, (float)yw, (float)p, (float)(-d), true, oob);  // image.py:180-183 casts
     } else if (WARP == WARP_LINVEL_F32) {
         const float x = e.x, y = e.y;
         const float d = e.t;  // already t - t_ref
@@ -175,7 +166,7 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const 
         const float xw = __fsub_rn(x, __fmul_rn(d, vx)), yw = __fsub_rn(y, __fmul_rn(d, vy));
         const bool keep = !(xw <= 0.0f || xw > (float)A.Wm) && !(yw <= 0.0f || yw > (float)A.Hm);
         if (!keep) return;
-        splat<GRAD, PAIR>(A, acc, xw, yw, p, -d, true, oob, xt);
+        splat<GRAD>(A, acc, xw, yw, p, -d, true, oob);
     } else {
         // optic_flow.py:37-44 then events_to_image_torch(..., interpolation='bilinear') defaults
         const float xe = e.x, ye = e.y, te = e.t;
@@ -203,7 +194,7 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const 
             u = __fadd_rn(u, __fmul_rn(flow_tap(fu, H, W, y0 + 1, x0 + 1), se)); v = __fadd_rn(v, __fmul_rn(flow_tap(fv, H, W, y0 + 1, x0 + 1), se));
         }
         const float d = __fsub_rn(te, A.flow_t0);
-        splat<false, PAIR>(A, acc, __fadd_rn(xe, __fmul_rn(u, d)), __fadd_rn(ye, __fmul_rn(v, d)), p, 0.0f, true, oob, xt);
+        splat<false>(A, acc, __fadd_rn(xe, __fmul_rn(u, d)), __fadd_rn(ye, __fmul_rn(v, d)), p, 0.0f, true, oob);
     }
 }
 
@@ -213,24 +204,21 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const 
 // the number of reductions).
 constexpr int kBatch = 4;
 
-template <int WARP, bool GRAD, bool PAIR>
+template <int WARP, bool GRAD>
 __global__ void __launch_bounds__(256) cmax_scatter_kernel(const CmaxArgs A)
 {
     unsigned oob = 0;
     float *acc = A.acc + (int64_t)(blockIdx.x % A.replicas) * A.Hc * A.Wc * kBlockFloats;
-    // PAIR: two lanes per event (see splat), so a CTA covers 128 events per sweep
-    const int lanes_per_event = PAIR ? 2 : 1;
-    const int xt = PAIR ? (threadIdx.x & 1) : 0;
-    const int64_t stride = (int64_t)gridDim.x * (256 / lanes_per_event);
-    int64_t i = (int64_t)blockIdx.x * (256 / lanes_per_event) + threadIdx.x / lanes_per_event;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     for (; i + (kBatch - 1) * stride < A.n; i += kBatch * stride) {
         Event<WARP> ev[kBatch];
 #pragma unroll
         for (int k = 0; k < kBatch; ++k) ev[k] = load_event<WARP>(A, i + k * stride);
 #pragma unroll
-        for (int k = 0; k < kBatch; ++k) cmax_event<WARP, GRAD, PAIR>(A, acc, ev[k], oob, xt);
+        for (int k = 0; k < kBatch; ++k) cmax_event<WARP, GRAD>(A, acc, ev[k], oob);
     }
-    for (; i < A.n; i += stride) cmax_event<WARP, GRAD, PAIR>(A, acc, load_event<WARP>(A, i), oob, xt);
+    for (; i < A.n; i += stride) cmax_event<WARP, GRAD>(A, acc, load_event<WARP>(A, i), oob);
     flush_oob(A.oob, oob);
 }
 
@@ -271,7 +259,10 @@ __global__ void __launch_bounds__(256) cmax_gather_kernel(const float *__restric
                 const int by = y - (k >> 1), bx = x - (k & 1);
                 if (by < 0 || bx < 0) continue;
                 const float *blk = base + ((int64_t)by * Wc + bx) * kBlockFloats;
-                a += blk[k]; b += blk[4 + k]; c += blk[8 + k];
+                a += blk[k];
+                // D0 block = {-a, +a, -b, +b}, D1 block = {-c, -d, +c, +d} (see splat)
+                b += (k == 0) ? -blk[4] : (k == 1) ? blk[4] : (k == 2) ? -blk[5] : blk[5];
+                c += (k == 0) ? -blk[6] : (k == 1) ? -blk[7] : (k == 2) ? blk[6] : blk[7];
             }
         }
         I[i] = a; D0[i] = b; D1[i] = c;
@@ -434,12 +425,8 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, double *result, fl
     if (A.n > 0) {
         ProfScope prof(st);
         prof_count(1);
-        const bool pair = variant_of(flags) != EVK_VARIANT_GLOBAL_RED;  // GLOBAL_RED = one lane per event (A/B baseline)
-#define EVK_CMAX_LAUNCH(G, P) \
-    cmax_scatter_kernel<WARP, G, P><<<grid_for(cmax_scatter_kernel<WARP, G, P>, 256, A.n, 256 * 4), 256, 0, st>>>(A)
-        if (grad) { if (pair) EVK_CMAX_LAUNCH(true, true); else EVK_CMAX_LAUNCH(true, false); }
-        else { if (pair) EVK_CMAX_LAUNCH(false, true); else EVK_CMAX_LAUNCH(false, false); }
-#undef EVK_CMAX_LAUNCH
+        if (grad) cmax_scatter_kernel<WARP, true><<<grid_for(cmax_scatter_kernel<WARP, true>, 256, A.n, 256 * 4), 256, 0, st>>>(A);
+        else cmax_scatter_kernel<WARP, false><<<grid_for(cmax_scatter_kernel<WARP, false>, 256, A.n, 256 * 4), 256, 0, st>>>(A);
     }
     prof_count(do_blur ? 4 : 3);
     const int g = (npix + 255) / 256;
@@ -459,11 +446,9 @@ __global__ void __launch_bounds__(256) cmax_pack_kernel(const float *__restrict_
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= npix) return;
     float4 *blk = reinterpret_cast<float4 *>(acc + (int64_t)i * kBlockFloats);
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    blk[0] = make_float4(iwe[i], 0.f, 0.f, 0.f);                      // TL slot of block i = pixel i
-    blk[1] = diwe ? make_float4(diwe[i], 0.f, 0.f, 0.f) : z;
-    blk[2] = diwe ? make_float4(diwe[npix + i], 0.f, 0.f, 0.f) : z;
-    blk[3] = z;
+    blk[0] = make_float4(iwe[i], 0.f, 0.f, 0.f);   // TL slot of block i = pixel i
+    // TL of the D0 block is -a, TL of the D1 block is -c
+    blk[1] = diwe ? make_float4(-diwe[i], 0.f, -diwe[npix + i], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 }  // namespace evk

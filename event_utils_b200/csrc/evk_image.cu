@@ -8,10 +8,10 @@
 //
 // Variants:
 //   GLOBAL_RED : one red.global.add.f32 per tap straight into out.
-//   VECTOR_RED : (bilinear) the two taps of an image row are adjacent; rows are kept in a
-//                "quad" workspace where quad q holds columns 3q..3q+3 (overlap of one column, so
-//                every (x, x+1) pair is inside one 16-byte aligned quad) -> 2 vector reds per
-//                event instead of 4 scalar ones, then a fold epilogue.
+//   VECTOR_RED : (bilinear) a "block" workspace ws[H][W][4]: block (y,x) collects the four taps
+//                TL,TR,BL,BR of every event whose 2x2 footprint is anchored at (y,x), so an event is
+//                ONE red.global.add.v4.f32 instead of 4 scalar reds; a fold kernel sums the four
+//                blocks each pixel lives in.
 //   WARP_AGG   : lanes of a warp that hit the same cell are combined with match.any before the
 //                red (hot-spot / Zipf streams, where same-address serialisation in L2 dominates).
 #include "evk_common.cuh"
@@ -98,35 +98,17 @@ __device__ __forceinline__ void image_event(const ImageArgs &A, float x, float y
         const float v00 = __fmul_rn(wl, oy), v01 = __fmul_rn(wr, oy);
         const float v10 = __fmul_rn(wl, dy), v11 = __fmul_rn(wr, dy);
         if (SINK == ISINK_QUAD) {
-            if (x1 == x0 + 1) {
-                int q = x0 / 3;
-                if (q > A.nqx - 1) q = A.nqx - 1;
-                const int s = x0 - 3 * q;  // 0..2 (x0+1 <= W-1 guarantees s+1 <= 3)
-                if (v00 != 0.0f || v01 != 0.0f) {
-                    float4 v;
-                    v.x = (s == 0) ? v00 : 0.0f;
-                    v.y = (s == 1) ? v00 : ((s == 0) ? v01 : 0.0f);
-                    v.z = (s == 2) ? v00 : ((s == 1) ? v01 : 0.0f);
-                    v.w = (s == 2) ? v01 : 0.0f;
-                    red_add4(A.ws + ((int64_t)y0 * A.nqx + q) * 4, v);
-                }
-                if (v10 != 0.0f || v11 != 0.0f) {
-                    float4 v;
-                    v.x = (s == 0) ? v10 : 0.0f;
-                    v.y = (s == 1) ? v10 : ((s == 0) ? v11 : 0.0f);
-                    v.z = (s == 2) ? v10 : ((s == 1) ? v11 : 0.0f);
-                    v.w = (s == 2) ? v11 : 0.0f;
-                    red_add4(A.ws + ((int64_t)y1 * A.nqx + q) * 4, v);
-                }
+            // block workspace ws[H][W][4]: the whole 2x2 footprint anchored at (y0,x0) is ONE
+            // red.global.add.v4.f32 {TL,TR,BL,BR}; image_fold_kernel sums the four blocks a pixel is in
+            if (v00 == 0.0f && v01 == 0.0f && v10 == 0.0f && v11 == 0.0f) return;
+            if (x1 == x0 + 1 && y1 == y0 + 1) {
+                red_add4(A.ws + ((int64_t)y0 * A.W + x0) * 4, make_float4(v00, v01, v10, v11));
             } else {
-                // wrapped pair (negative px): scalar taps into the quad rows
-                auto tap = [&](int yy, int xx, float v) {
-                    if (v == 0.0f) return;
-                    int q = xx / 3;
-                    if (q > A.nqx - 1) q = A.nqx - 1;
-                    red_add(A.ws + ((int64_t)yy * A.nqx + q) * 4 + (xx - 3 * q), v);
-                };
-                tap(y0, x0, v00); tap(y0, x1, v01); tap(y1, x0, v10); tap(y1, x1, v11);
+                // wrapped footprint (negative px / py): each tap is the TL tap of its own pixel's block
+                if (v00 != 0.0f) red_add(A.ws + ((int64_t)y0 * A.W + x0) * 4, v00);
+                if (v01 != 0.0f) red_add(A.ws + ((int64_t)y0 * A.W + x1) * 4, v01);
+                if (v10 != 0.0f) red_add(A.ws + ((int64_t)y1 * A.W + x0) * 4, v10);
+                if (v11 != 0.0f) red_add(A.ws + ((int64_t)y1 * A.W + x1) * 4, v11);
             }
         } else {
             if (v00 != 0.0f) red_add(A.out + (int64_t)y0 * A.W + x0, v00);
@@ -183,21 +165,20 @@ __global__ void __launch_bounds__(256) fill_kernel(float *out, int64_t n, float 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
 }
 
-// quad rows -> out[H][W] (+ fill).  Column x lives in quad x/3 slot x%3 and, when x%3==0 and
-// x>0, also in quad x/3-1 slot 3.
+// block workspace -> out[H][W] (+ fill): pixel (y,x) = TL of block (y,x) + TR of (y,x-1) + BL of
+// (y-1,x) + BR of (y-1,x-1)
 template <bool ACCUM>
 __global__ void __launch_bounds__(256) image_fold_kernel(const float *__restrict__ ws, float *__restrict__ out,
-                                                         int H, int W, int nqx, float fill)
+                                                         int H, int W, float fill)
 {
     const int64_t npix = (int64_t)H * W;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
         const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
-        const float *row = ws + (int64_t)y * nqx * 4;
-        int q = x / 3;
-        float v = 0.0f;
-        if (q < nqx) v = row[q * 4 + (x - 3 * q)];
-        if (x > 0 && x % 3 == 0) v += row[(x / 3 - 1) * 4 + 3];
+        float v = ws[i * 4];
+        if (x > 0) v += ws[(i - 1) * 4 + 1];
+        if (y > 0) v += ws[(i - W) * 4 + 2];
+        if (x > 0 && y > 0) v += ws[(i - W - 1) * 4 + 3];
         out[i] = ACCUM ? (out[i] + v) : (fill + v);
     }
 }
@@ -284,7 +265,7 @@ extern "C" {
 size_t evk_image_workspace_bytes(int Himg, int Wimg, unsigned flags)
 {
     if (Himg < 1 || Wimg < 1 || !(flags & EVK_BILINEAR)) return 0;
-    return (size_t)Himg * evk::quads_for_cols(Wimg) * 4 * sizeof(float);
+    return (size_t)Himg * Wimg * 4 * sizeof(float);
 }
 
 int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int Himg, int Wimg, float clipx,
@@ -315,7 +296,7 @@ int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int
     const int64_t npix = (int64_t)Himg * Wimg;
     const bool vec4 = ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)p) & 15) == 0);
     if (variant == EVK_VARIANT_VECTOR_RED) {
-        const size_t need = (size_t)Himg * A.nqx * 4 * sizeof(float);
+        const size_t need = (size_t)Himg * Wimg * 4 * sizeof(float);
         if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) {
             set_error("evk_image_f32: 16-byte aligned workspace of %zu bytes required", need);
             return EVK_E_WORKSPACE;
@@ -330,8 +311,8 @@ int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int
         }
         const int g2 = grid_simple(npix, 256);
         prof_count(1);
-        if (accum) image_fold_kernel<true><<<g2, 256, 0, st>>>(A.ws, out, Himg, Wimg, A.nqx, fill);
-        else image_fold_kernel<false><<<g2, 256, 0, st>>>(A.ws, out, Himg, Wimg, A.nqx, fill);
+        if (accum) image_fold_kernel<true><<<g2, 256, 0, st>>>(A.ws, out, Himg, Wimg, fill);
+        else image_fold_kernel<false><<<g2, 256, 0, st>>>(A.ws, out, Himg, Wimg, fill);
     } else if (variant == EVK_VARIANT_GLOBAL_RED || variant == EVK_VARIANT_WARP_AGG) {
         if (!accum) {
             if (fill == 0.0f) EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)npix * sizeof(float), st));

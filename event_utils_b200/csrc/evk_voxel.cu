@@ -85,6 +85,35 @@ __device__ __noinline__ void add_all_bins_slow(const VoxelArgs &A, int64_t pix, 
     }
 }
 
+// Trilinear extension, one temporal bin: the 2x2 spatial footprint of weight pw in bin b.
+// Vector sink: the workspace is an array of 16-byte BLOCKS ws[B][H][W][4]; block (b,y,x) collects
+// the taps TL,TR,BL,BR of every event whose footprint is anchored at (y,x), so the whole footprint
+// is ONE red.global.add.v4.f32 (each pixel lives in four blocks; voxel_fold_blocks_kernel sums them).
+template <int SINK>
+__device__ __forceinline__ void tri_bin(const VoxelArgs &A, int b, float pw, int x0, int x1, int y0, int y1, float ox,
+                                        float dx, float oy, float dy)
+{
+    const float wl = __fmul_rn(pw, ox), wr = __fmul_rn(pw, dx);
+    const float v00 = __fmul_rn(wl, oy), v01 = __fmul_rn(wr, oy), v10 = __fmul_rn(wl, dy), v11 = __fmul_rn(wr, dy);
+    if (v00 == 0.0f && v01 == 0.0f && v10 == 0.0f && v11 == 0.0f) return;
+    const int64_t plane = (int64_t)b * A.H * A.W;
+    if (SINK == SINK_SCALAR) {
+        float *o = A.out + plane;
+        if (v00 != 0.0f) red_add(o + (int64_t)y0 * A.W + x0, v00);
+        if (v01 != 0.0f) red_add(o + (int64_t)y0 * A.W + x1, v01);
+        if (v10 != 0.0f) red_add(o + (int64_t)y1 * A.W + x0, v10);
+        if (v11 != 0.0f) red_add(o + (int64_t)y1 * A.W + x1, v11);
+    } else if (x1 == x0 + 1 && y1 == y0 + 1) {
+        red_add4(A.ws + (plane + (int64_t)y0 * A.W + x0) * 4, make_float4(v00, v01, v10, v11));
+    } else {
+        // wrapped footprint: each tap is the TL tap of its own pixel's block
+        if (v00 != 0.0f) red_add(A.ws + (plane + (int64_t)y0 * A.W + x0) * 4, v00);
+        if (v01 != 0.0f) red_add(A.ws + (plane + (int64_t)y0 * A.W + x1) * 4, v01);
+        if (v10 != 0.0f) red_add(A.ws + (plane + (int64_t)y1 * A.W + x0) * 4, v10);
+        if (v11 != 0.0f) red_add(A.ws + (plane + (int64_t)y1 * A.W + x1) * 4, v11);
+    }
+}
+
 template <int SINK, bool SPATIAL_BILINEAR>
 __device__ __forceinline__ void voxel_event(const VoxelArgs &A, float x, float y, float t, float p,
                                             unsigned &oob)
@@ -114,44 +143,22 @@ __device__ __forceinline__ void voxel_event(const VoxelArgs &A, float x, float y
             !wrap_int_index(upx, A.W, x0) || !wrap_int_index(upx + 1, A.W, x1) ||
             !wrap_int_index(upy, A.H, y0) || !wrap_int_index(upy + 1, A.H, y1)) { ++oob; return; }
         if (m == 0.0f && finite) return;  // masked events only add zeros at pixel (0,0)..(1,1)
-        float wb0, wb1;
-        int b0;
         const float ox = __fsub_rn(1.0f, dx), oy = __fsub_rn(1.0f, dy);
         if (!finite) {
             // keep NaN semantics: every bin, every tap
             for (int b = 0; b < A.B; ++b) {
                 float w = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, (float)b)));
                 float wb = (w != w) ? w : (w > 0.0f ? w : 0.0f);
-                float pw = __fmul_rn(__fmul_rn(p, wb), m);
-                float *o = (SINK == SINK_SCALAR) ? A.out + (int64_t)b * A.H * A.W : nullptr;
-                float v00 = __fmul_rn(__fmul_rn(pw, ox), oy), v01 = __fmul_rn(__fmul_rn(pw, dx), oy);
-                float v10 = __fmul_rn(__fmul_rn(pw, ox), dy), v11 = __fmul_rn(__fmul_rn(pw, dx), dy);
-                if (SINK == SINK_SCALAR) {
-                    if (v00 != 0.0f) red_add(o + (int64_t)y0 * A.W + x0, v00);
-                    if (v01 != 0.0f) red_add(o + (int64_t)y0 * A.W + x1, v01);
-                    if (v10 != 0.0f) red_add(o + (int64_t)y1 * A.W + x0, v10);
-                    if (v11 != 0.0f) red_add(o + (int64_t)y1 * A.W + x1, v11);
-                } else {
-                    int q = b / 3;
-                    if (q > A.nq - 1) q = A.nq - 1;
-                    int s = b - 3 * q;
-                    if (v00 != 0.0f) red_add(A.ws + (((int64_t)y0 * A.W + x0) * A.nq + q) * 4 + s, v00);
-                    if (v01 != 0.0f) red_add(A.ws + (((int64_t)y0 * A.W + x1) * A.nq + q) * 4 + s, v01);
-                    if (v10 != 0.0f) red_add(A.ws + (((int64_t)y1 * A.W + x0) * A.nq + q) * 4 + s, v10);
-                    if (v11 != 0.0f) red_add(A.ws + (((int64_t)y1 * A.W + x1) * A.nq + q) * 4 + s, v11);
-                }
+                tri_bin<SINK>(A, b, __fmul_rn(__fmul_rn(p, wb), m), x0, x1, y0, y1, ox, dx, oy, dy);
             }
             return;
         }
         const float fl = floorf(tn);
-        b0 = (int)fl;
-        wb0 = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fl)));
-        wb1 = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fl + 1.0f)));
-        const float pw0 = __fmul_rn(__fmul_rn(p, wb0), m), pw1 = __fmul_rn(__fmul_rn(p, wb1), m);
-        add_bin_pair<SINK>(A, (int64_t)y0 * A.W + x0, b0, __fmul_rn(__fmul_rn(pw0, ox), oy), __fmul_rn(__fmul_rn(pw1, ox), oy));
-        add_bin_pair<SINK>(A, (int64_t)y0 * A.W + x1, b0, __fmul_rn(__fmul_rn(pw0, dx), oy), __fmul_rn(__fmul_rn(pw1, dx), oy));
-        add_bin_pair<SINK>(A, (int64_t)y1 * A.W + x0, b0, __fmul_rn(__fmul_rn(pw0, ox), dy), __fmul_rn(__fmul_rn(pw1, ox), dy));
-        add_bin_pair<SINK>(A, (int64_t)y1 * A.W + x1, b0, __fmul_rn(__fmul_rn(pw0, dx), dy), __fmul_rn(__fmul_rn(pw1, dx), dy));
+        const int b0 = (int)fl;
+        const float wb0 = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fl)));
+        const float wb1 = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fl + 1.0f)));
+        if ((unsigned)b0 < (unsigned)A.B) tri_bin<SINK>(A, b0, __fmul_rn(__fmul_rn(p, wb0), m), x0, x1, y0, y1, ox, dx, oy, dy);
+        if ((unsigned)(b0 + 1) < (unsigned)A.B) tri_bin<SINK>(A, b0 + 1, __fmul_rn(__fmul_rn(p, wb1), m), x0, x1, y0, y1, ox, dx, oy, dy);
     }
 }
 
@@ -270,6 +277,24 @@ __global__ void __launch_bounds__(kThreads) voxel_windows_kernel(const VoxelArgs
     flush_oob(A.oob, oob);
 }
 
+// block workspace ws[B][H][W][4] -> out[B][H][W]: pixel (y,x) = TL of block (y,x) + TR of (y,x-1)
+// + BL of (y-1,x) + BR of (y-1,x-1)
+template <bool ACCUM>
+__global__ void __launch_bounds__(256) voxel_fold_blocks_kernel(const float *__restrict__ ws, float *__restrict__ out,
+                                                                int B, int H, int W)
+{
+    const int64_t total = (int64_t)B * H * W;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int x = (int)(i % W), y = (int)((i / W) % H);
+        float v = ws[i * 4];
+        if (x > 0) v += ws[(i - 1) * 4 + 1];
+        if (y > 0) v += ws[(i - W) * 4 + 2];
+        if (x > 0 && y > 0) v += ws[(i - W - 1) * 4 + 3];
+        out[i] = ACCUM ? (out[i] + v) : v;
+    }
+}
+
 static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStream_t st,
                         void *workspace, size_t workspace_bytes)
 {
@@ -287,7 +312,7 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
     const int sink = (variant == EVK_VARIANT_VECTOR_RED) ? SINK_QUAD : SINK_SCALAR;
     A.nq = quads_for_bins(A.B);
     if (sink == SINK_QUAD) {
-        const size_t need = (size_t)npix * A.nq * 4 * sizeof(float);
+        const size_t need = bil ? (size_t)npix * A.B * 4 * sizeof(float) : (size_t)npix * A.nq * 4 * sizeof(float);
         if (workspace == nullptr || workspace_bytes < need) {
             set_error("evk_voxel: workspace of %zu bytes required, %zu given", need, workspace_bytes);
             return EVK_E_WORKSPACE;
@@ -322,8 +347,13 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
     if (sink == SINK_QUAD) {
         const int grid = grid_simple(npix, 256);
         prof_count(1);
-        if (accum) voxel_fold_kernel<true><<<grid, 256, 0, st>>>(A.ws, A.out, npix, A.B, A.nq);
-        else voxel_fold_kernel<false><<<grid, 256, 0, st>>>(A.ws, A.out, npix, A.B, A.nq);
+        if (bil) {
+            if (accum) voxel_fold_blocks_kernel<true><<<grid, 256, 0, st>>>(A.ws, A.out, A.B, A.H, A.W);
+            else voxel_fold_blocks_kernel<false><<<grid, 256, 0, st>>>(A.ws, A.out, A.B, A.H, A.W);
+        } else {
+            if (accum) voxel_fold_kernel<true><<<grid, 256, 0, st>>>(A.ws, A.out, npix, A.B, A.nq);
+            else voxel_fold_kernel<false><<<grid, 256, 0, st>>>(A.ws, A.out, npix, A.B, A.nq);
+        }
         EVK_CUDA(cudaGetLastError());
     }
     return EVK_OK;
@@ -345,9 +375,9 @@ extern "C" {
 
 size_t evk_voxel_workspace_bytes(int B, int H, int W, unsigned flags)
 {
-    (void)flags;
     if (B < 1 || H < 1 || W < 1) return 0;
-    return (size_t)H * W * evk::quads_for_bins(B) * 4 * sizeof(float);
+    if (flags & EVK_BILINEAR) return (size_t)B * H * W * 4 * sizeof(float);   // 2x2 blocks per bin
+    return (size_t)H * W * evk::quads_for_bins(B) * 4 * sizeof(float);      // temporal quads per pixel
 }
 
 int evk_voxel_f32(const float *x, const float *y, const float *t, const float *p, int64_t n, float t0,

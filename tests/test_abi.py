@@ -35,7 +35,8 @@ def test_workspace_queries_need_no_gpu():
     assert L.evk_voxel_workspace_bytes(1, 10, 10, 0) == 10 * 10 * 16
     assert L.evk_voxel_workspace_bytes(4, 10, 10, 0) == 10 * 10 * 16
     assert L.evk_voxel_workspace_bytes(8, 10, 10, 0) == 10 * 10 * 3 * 16
-    assert L.evk_image_workspace_bytes(181, 241, _lib.BILINEAR) == 181 * 80 * 16
+    assert L.evk_image_workspace_bytes(181, 241, _lib.BILINEAR) == 181 * 241 * 16
+    assert L.evk_voxel_workspace_bytes(5, 481, 641, _lib.BILINEAR) == 5 * 481 * 641 * 16
     assert L.evk_image_workspace_bytes(181, 241, 0) == 0
     assert L.evk_cmax_workspace_bytes(180, 240) >= 8 * 181 * 241 * 16
 

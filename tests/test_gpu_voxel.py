@@ -188,7 +188,7 @@ def test_c_abi_direct_trilinear_and_windows(oracle):
     ref = np.stack([oracle.image_torch_f32(x, y, p * np.maximum(0, 1 - np.abs(tn - b)).astype(np.float32),
                                            sensor_size=(H, W), interpolation='bilinear') for b in range(B)])
     out3 = torch.empty((B, H + 1, W + 1), device="cuda")
-    ws3 = torch.empty(L.evk_voxel_workspace_bytes(B, H + 1, W + 1, 0), dtype=torch.uint8, device="cuda")
+    ws3 = torch.empty(L.evk_voxel_workspace_bytes(B, H + 1, W + 1, _lib.BILINEAR), dtype=torch.uint8, device="cuda")
     for variant in (_lib.VARIANT_GLOBAL_RED, _lib.VARIANT_VECTOR_RED):
         _lib.check(L.evk_voxel_f32(X.data_ptr(), Y.data_ptr(), T.data_ptr(), P.data_ptr(), x.shape[0], t0, dt, B,
                                    H + 1, W + 1, variant | _lib.BILINEAR | _lib.CLIP, out3.data_ptr(), ws3.data_ptr(),

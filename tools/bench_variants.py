@@ -80,7 +80,7 @@ for name, v in (("global_red", _lib.VARIANT_GLOBAL_RED), ("vector_red", _lib.VAR
     report("voxel AoS " + name, best, N, 16, 4 * B * H * W)
 del ev
 out3 = torch.empty((B, H + 1, W + 1), device=dev)
-ws3 = torch.empty(L.evk_voxel_workspace_bytes(B, H + 1, W + 1, 0), dtype=torch.uint8, device=dev)
+ws3 = torch.empty(L.evk_voxel_workspace_bytes(B, H + 1, W + 1, _lib.BILINEAR), dtype=torch.uint8, device=dev)
 for name, v in (("global_red", _lib.VARIANT_GLOBAL_RED), ("vector_red", _lib.VARIANT_VECTOR_RED)):
     def run(v=v):
         _lib.check(L.evk_voxel_f32(x.data_ptr(), y.data_ptr(), t.data_ptr(), p.data_ptr(), N, t0, dt, B, H + 1, W + 1,
@@ -145,7 +145,7 @@ for scene in ("uniform", "lattice"):
     res = torch.empty(8, dtype=torch.float64, device=dev)
     tl = float(t64[-1])
     for params in ((45.0, -20.0), (60.0, -35.0)):
-        for fl, nm in ((_lib.CMAX_WANT_GRAD, "f+g paired"), (_lib.CMAX_WANT_GRAD | _lib.VARIANT_GLOBAL_RED, "f+g 1lane"), (0, "f paired")):
+        for fl, nm in ((_lib.CMAX_WANT_GRAD, "f+g"), (0, "f")):
             def run(fl=fl, params=params):
                 _lib.check(L.evk_cmax_linvel_variance_f64(x64.data_ptr(), y64.data_ptr(), t64.data_ptr(), p64.data_ptr(), N, 1.0,
                                                           params[0], params[1], tl, 180, 240, 180, 240, 1.0, fl, res.data_ptr(),
