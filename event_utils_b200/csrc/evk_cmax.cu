@@ -438,17 +438,22 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, double *result, fl
     return EVK_OK;
 }
 
-// planar iwe / diwe -> the interleaved single-replica accumulator, so that the precomputed-image
-// entry point shares the whole image-space tail
-__global__ void __launch_bounds__(256) cmax_pack_kernel(const float *__restrict__ iwe, const float *__restrict__ diwe,
-                                                        int npix, float *__restrict__ acc)
+// precomputed planar iwe / diwe -> the planar working images + their sums (the block accumulator is
+// bypassed: a block value stands for taps of TWO pixels, planar images cannot be packed into it)
+__global__ void __launch_bounds__(256) cmax_planar_kernel(const float *__restrict__ iwe, const float *__restrict__ diwe,
+                                                          int npix, float *__restrict__ I, float *__restrict__ D0,
+                                                          float *__restrict__ D1, double *sums)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= npix) return;
-    float4 *blk = reinterpret_cast<float4 *>(acc + (int64_t)i * kBlockFloats);
-    blk[0] = make_float4(iwe[i], 0.f, 0.f, 0.f);   // TL slot of block i = pixel i
-    // TL of the D0 block is -a, TL of the D1 block is -c
-    blk[1] = diwe ? make_float4(-diwe[i], 0.f, -diwe[npix + i], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float a = 0.f, b = 0.f, c = 0.f;
+    if (i < npix) {
+        a = iwe[i];
+        if (diwe) { b = diwe[i]; c = diwe[npix + i]; }
+        I[i] = a; D0[i] = b; D1[i] = c;
+    }
+    block_add((double)a, sums + 0);
+    block_add((double)b, sums + 5);
+    block_add((double)c, sums + 6);
 }
 
 }  // namespace evk
@@ -529,8 +534,7 @@ int evk_variance_objective_f32(const float *iwe, const float *diwe, int Hc, int 
     }
     EVK_CUDA(cudaMemsetAsync(ws.sums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.sums), st));
     const int g = (npix + 255) / 256;
-    cmax_pack_kernel<<<g, 256, 0, st>>>(iwe, grad ? diwe : nullptr, npix, ws.acc);
-    cmax_gather_kernel<<<g, 256, 0, st>>>(ws.acc, 1, Hc, Wc, ws.I, ws.D0, ws.D1, nullptr, nullptr, ws.sums);
+    cmax_planar_kernel<<<g, 256, 0, st>>>(iwe, grad ? diwe : nullptr, npix, ws.I, ws.D0, ws.D1, ws.sums);
     if (do_blur) cmax_blur_axis0_kernel<<<g, 256, 0, st>>>(ws.I, ws.tmp, Hc, Wc, taps);
     cmax_blur_axis1_sums_kernel<<<g, 256, 0, st>>>(ws.tmp, ws.I, ws.D0, ws.D1, Hc, Wc, taps, do_blur, ws.sums);
     cmax_final_kernel<<<1, 1, 0, st>>>(ws.sums, ws.oob, npix, mix_a, mix_b, grad ? 1 : 0, result);
