@@ -112,20 +112,42 @@ def test_hot_spot_counts_bit_exact(oracle, variant):
 
 
 def test_hot_spot_bilinear_and_signed(oracle):
-    """Zipf stream with +-1 polarities and sub-pixel jitter through the bilinear cache path."""
+    """Zipf stream with +-1 polarities and sub-pixel jitter through the bilinear paths.
+    The hottest pixel receives ~10^5 taps: f32 accumulation is then order dependent beyond 1e-5
+    (the sequential f32 oracle itself is ~sqrt(n) eps away from the exact sum), so every variant --
+    and the oracle -- is compared with an f64 accumulation of the same f32 tap weights, within the
+    random-walk bound 2 sqrt(n_max) eps32 * max|image| (n_max = taps on the hottest pixel)."""
     import event_utils_b200 as eu
     from event_utils_b200.representations.image import events_to_image_torch
     H, W, n = 720, 1280, 2_000_000
     x, y = zipf_events(7, n, H, W, s=1.2)
     rng = np.random.default_rng(8)
-    x = x + rng.random(n).astype(np.float32) * 0.999
-    y = y + rng.random(n).astype(np.float32) * 0.999
+    x = x + rng.random(n).astype(np.float32) * np.float32(0.999)
+    y = y + rng.random(n).astype(np.float32) * np.float32(0.999)
     p = (rng.integers(0, 2, n) * 2 - 1).astype(np.float32)
+    # f32 tap weights exactly as image.py:79-86,111-114 computes them, accumulated in f64
+    px, py = np.floor(x), np.floor(y)
+    dx, dy = x - px, y - py
+    keep = ((x < W) & (y < H)).astype(np.float32)
+    ix, iy = (px * keep).astype(np.int64), (py * keep).astype(np.int64)
+    w = p * keep
+    one = np.float32(1.0)
+    exact = np.zeros((H + 1, W + 1), np.float64)
+    cnt = np.zeros((H + 1, W + 1), np.int64)
+    for oy_, ox_, tap in ((0, 0, w * (one - dx) * (one - dy)), (0, 1, w * dx * (one - dy)),
+                          (1, 0, w * (one - dx) * dy), (1, 1, w * dx * dy)):
+        np.add.at(exact, (iy + oy_, ix + ox_), tap.astype(np.float64))
+        np.add.at(cnt, (iy + oy_, ix + ox_), 1)
+    bound = 2.0 * np.sqrt(cnt.max()) * np.finfo(np.float32).eps * np.abs(exact).max()
     ref = oracle.image_torch_f32(x, y, p, sensor_size=(H, W), interpolation='bilinear')
-    for variant in ("smem_cache", "vector_red", "global_red"):
+    assert np.abs(ref - exact).max() <= bound
+    for variant in ("smem_cache", "vector_red", "global_red", None):
         eu.config.variant = variant
         out = events_to_image_torch(*dev(x, y, p), sensor_size=(H, W), interpolation='bilinear').cpu().numpy()
-        assert_close_to_max(out, ref, 1e-5, variant)
+        assert np.abs(out - exact).max() <= bound, (variant, np.abs(out - exact).max(), bound)
+        # away from the hot pixels the 1e-5 bar holds as usual
+        cold = cnt < 2000
+        assert np.abs(out - ref)[cold].max() <= 1e-5 * np.abs(ref).max()
 
 
 def test_numpy_flavour():
