@@ -17,11 +17,13 @@ SO_PATH = os.environ.get("EVK_LIB") or os.path.join(_HERE, "libevk.so")  # EVK_L
 ACCUMULATE = 0x1
 BILINEAR = 0x2
 CLIP = 0x4
+NEGPOS_TRUTHY = 0x8
 VARIANT_AUTO = 0 << 8
 VARIANT_GLOBAL_RED = 1 << 8
 VARIANT_VECTOR_RED = 2 << 8
 VARIANT_SMEM_TILE = 3 << 8
 VARIANT_WARP_AGG = 4 << 8
+TS_REVERSE = 0x80
 CMAX_WANT_GRAD = 0x10
 CMAX_ABS_POLARITY = 0x20
 CMAX_NO_CHANNEL_MIX = 0x40
@@ -48,6 +50,8 @@ def _declare(L):
     L.evk_voxel_workspace_bytes.argtypes = [ci, ci, ci, cu]
     L.evk_voxel_f32.restype = ci
     L.evk_voxel_f32.argtypes = [vp, vp, vp, vp, i64, f32, f32, ci, ci, ci, cu, vp, vp, sz, vp, vp]
+    L.evk_voxel_negpos_f32.restype = ci
+    L.evk_voxel_negpos_f32.argtypes = [vp, vp, vp, vp, i64, f32, f32, ci, ci, ci, cu, vp, vp, sz, vp, vp]
     L.evk_voxel_aos_f32.restype = ci
     L.evk_voxel_aos_f32.argtypes = [vp, i64, f32, f32, ci, ci, ci, cu, vp, vp, sz, vp, vp]
     L.evk_voxel_windows_f32.restype = ci
@@ -56,6 +60,10 @@ def _declare(L):
     L.evk_image_workspace_bytes.argtypes = [ci, ci, cu]
     L.evk_image_f32.restype = ci
     L.evk_image_f32.argtypes = [vp, vp, vp, i64, ci, ci, f32, f32, cu, f32, vp, vp, sz, vp, vp]
+    L.evk_timestamp_image_workspace_bytes.restype = sz
+    L.evk_timestamp_image_workspace_bytes.argtypes = [ci, ci]
+    L.evk_timestamp_image_f32.restype = ci
+    L.evk_timestamp_image_f32.argtypes = [vp, vp, vp, vp, i64, f32, f32, ci, ci, f32, f32, cu, vp, vp, vp, sz, vp, vp]
     L.evk_count_u32.restype = ci
     L.evk_count_u32.argtypes = [vp, vp, i64, ci, ci, f32, f32, cu, vp, vp, vp]
     L.evk_splat_idx_f32.restype = ci

@@ -44,8 +44,8 @@ struct ProfScope {
 
 // evk_hot.cu: adaptive shared-memory write-combining scatter (mode 0 nearest f32, 1 bilinear f32, 2 count u32)
 int launch_image_hot(const float *x, const float *y, const float *p, int64_t n, int H, int W, int clip, float clipx,
-                     float clipy, int mode, int force_cache, float *out, unsigned *out_u32, unsigned long long *oob,
-                     cudaStream_t st);
+                     float clipy, int mode, int force_cache, float *out, float *ws, unsigned *out_u32,
+                     unsigned long long *oob, cudaStream_t st);
 
 static inline unsigned variant_of(unsigned flags) { return flags & EVK_VARIANT_MASK; }
 

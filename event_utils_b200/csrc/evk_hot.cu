@@ -24,6 +24,7 @@ struct HotArgs {
     int clip;
     float clipx, clipy;
     float *out;
+    float *ws;         // bilinear only: block workspace ws[H][W][4] (TL,TR,BL,BR); NULL -> taps go to `out`
     unsigned *out_u32;
     unsigned long long *oob;
     int force_cache;  // 0 adaptive, 1 always on
@@ -33,11 +34,12 @@ constexpr int kHotLog2 = 12;
 constexpr int kHotSlots = 1 << kHotLog2;  // 4096 slots: 16 KB keys + 16 KB values
 constexpr unsigned kEmpty = 0xffffffffu;
 
-__device__ __forceinline__ void global_add(float *out, unsigned cell, float v) { red_add(out + cell, v); }
-__device__ __forceinline__ void global_add(unsigned *out, unsigned cell, unsigned v) { red_add_u32(out + cell, v); }
+// `gs` = element stride of a cell in the global target (4 when the target is the TL slot of a block)
+__device__ __forceinline__ void global_add(float *out, unsigned cell, float v, int gs) { red_add(out + (size_t)cell * gs, v); }
+__device__ __forceinline__ void global_add(unsigned *out, unsigned cell, unsigned v, int gs) { red_add_u32(out + (size_t)cell * gs, v); }
 
 template <typename V>
-__device__ __forceinline__ void hot_add(unsigned *keys, V *vals, V *gout, bool use_cache, unsigned cell, V v)
+__device__ __forceinline__ void hot_add(unsigned *keys, V *vals, V *gout, bool use_cache, unsigned cell, V v, int gs = 1)
 {
     if (use_cache) {
         const unsigned slot = (cell * 2654435761u) >> (32 - kHotLog2);
@@ -51,7 +53,7 @@ __device__ __forceinline__ void hot_add(unsigned *keys, V *vals, V *gout, bool u
             return;
         }
     }
-    global_add(gout, cell, v);
+    global_add(gout, cell, v, gs);
 }
 
 enum { HOT_NEAREST = 0, HOT_BILINEAR = 1, HOT_COUNT = 2 };
@@ -63,7 +65,8 @@ __global__ void __launch_bounds__(256) image_hot_kernel(const HotArgs A)
     __shared__ unsigned keys[kHotSlots];
     __shared__ V vals[kHotSlots];
     __shared__ int dup_lanes;
-    V *gout = (MODE == HOT_COUNT) ? (V *)A.out_u32 : (V *)A.out;
+    V *gout = (MODE == HOT_COUNT) ? (V *)A.out_u32 : (MODE == HOT_BILINEAR && A.ws) ? (V *)A.ws : (V *)A.out;
+    const int gs = (MODE == HOT_BILINEAR && A.ws) ? 4 : 1;
 
     for (int s = threadIdx.x; s < kHotSlots; s += 256) { keys[s] = kEmpty; vals[s] = (V)0; }
     if (threadIdx.x == 0) dup_lanes = 0;
@@ -120,31 +123,37 @@ __global__ void __launch_bounds__(256) image_hot_kernel(const HotArgs A)
             const float wl = __fmul_rn(w, ox), wr = __fmul_rn(w, dx);
             const float v00 = __fmul_rn(wl, oy), v01 = __fmul_rn(wr, oy), v10 = __fmul_rn(wl, dy), v11 = __fmul_rn(wr, dy);
             const unsigned r0 = (unsigned)y0 * (unsigned)A.W, r1 = (unsigned)y1 * (unsigned)A.W;
-            if (v00 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x0, (V)v00);
-            if (v01 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x1, (V)v01);
-            if (v10 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x0, (V)v10);
-            if (v11 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x1, (V)v11);
+            if (!use_cache && A.ws && x1 == x0 + 1 && y1 == y0 + 1) {
+                // uncontended stream: the whole footprint as ONE vector reduction into its block
+                if (v00 != 0.0f || v01 != 0.0f || v10 != 0.0f || v11 != 0.0f)
+                    red_add4(A.ws + ((size_t)r0 + x0) * 4, make_float4(v00, v01, v10, v11));
+            } else {
+                if (v00 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x0, (V)v00, gs);
+                if (v01 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x1, (V)v01, gs);
+                if (v10 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x0, (V)v10, gs);
+                if (v11 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x1, (V)v11, gs);
+            }
         }
     }
     __syncthreads();
     if (use_cache) {
         for (int s = threadIdx.x; s < kHotSlots; s += 256) {
             const unsigned k = keys[s];
-            if (k != kEmpty && vals[s] != (V)0) global_add(gout, k, vals[s]);
+            if (k != kEmpty && vals[s] != (V)0) global_add(gout, k, vals[s], gs);
         }
     }
     flush_oob(A.oob, oob);
 }
 
 int launch_image_hot(const float *x, const float *y, const float *p, int64_t n, int H, int W, int clip, float clipx,
-                     float clipy, int mode, int force_cache, float *out, unsigned *out_u32, unsigned long long *oob,
-                     cudaStream_t st)
+                     float clipy, int mode, int force_cache, float *out, float *ws, unsigned *out_u32,
+                     unsigned long long *oob, cudaStream_t st)
 {
     if ((int64_t)H * W >= 0xffffffffLL) { set_error("hot-spot variant: image too large for 32-bit cell ids"); return EVK_E_UNSUPPORTED; }
     HotArgs A{};
     A.x = x; A.y = y; A.p = p; A.n = n; A.H = H; A.W = W;
     A.clip = clip; A.clipx = clipx; A.clipy = clipy;
-    A.out = out; A.out_u32 = out_u32; A.oob = oob; A.force_cache = force_cache;
+    A.out = out; A.ws = ws; A.out_u32 = out_u32; A.oob = oob; A.force_cache = force_cache;
     if (n <= 0) return EVK_OK;
     ProfScope prof(st);
     prof_count(1);

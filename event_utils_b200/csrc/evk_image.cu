@@ -288,9 +288,9 @@ int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int
     unsigned variant = variant_of(flags);
     // AUTO: large nearest streams take the adaptive hot-spot kernel (it falls back to plain global
     // reductions by itself when the stream is not contended); bilinear keeps the vector-red form.
+    const bool have_ws = workspace && workspace_bytes >= (size_t)Himg * Wimg * 4 * sizeof(float) && !((uintptr_t)workspace & 15);
     if (variant == EVK_VARIANT_AUTO)
-        variant = (bil && workspace && n >= ((int64_t)1 << 20)) ? EVK_VARIANT_VECTOR_RED
-                  : (!bil && n >= ((int64_t)1 << 18)) ? EVK_VARIANT_SMEM_TILE : EVK_VARIANT_GLOBAL_RED;
+        variant = (n >= ((int64_t)1 << 18)) ? EVK_VARIANT_SMEM_TILE : (bil && have_ws) ? EVK_VARIANT_VECTOR_RED : EVK_VARIANT_GLOBAL_RED;
     if (variant == EVK_VARIANT_VECTOR_RED && !bil) variant = EVK_VARIANT_GLOBAL_RED;
     if (variant == EVK_VARIANT_WARP_AGG && bil) variant = EVK_VARIANT_GLOBAL_RED;
     const int64_t npix = (int64_t)Himg * Wimg;
@@ -333,14 +333,23 @@ int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int
             }
         }
     } else if (variant == EVK_VARIANT_SMEM_TILE) {
-        if (!accum) {
+        // explicit request = cache always on; reached through AUTO = adaptive (per-CTA contention probe)
+        const int force = variant_of(flags) == EVK_VARIANT_SMEM_TILE ? 1 : 0;
+        float *blocks = (bil && have_ws) ? static_cast<float *>(workspace) : nullptr;
+        if (blocks) {
+            EVK_CUDA(cudaMemsetAsync(blocks, 0, (size_t)npix * 4 * sizeof(float), st));
+        } else if (!accum) {
             if (fill == 0.0f) EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)npix * sizeof(float), st));
             else { prof_count(1); fill_kernel<<<grid_simple(npix, 256), 256, 0, st>>>(out, npix, fill); }
         }
-        // explicit request = cache always on; reached through AUTO = adaptive
-        const int force = variant_of(flags) == EVK_VARIANT_SMEM_TILE ? 1 : 0;
-        int rc = launch_image_hot(x, y, p, n, Himg, Wimg, A.clip, clipx, clipy, bil ? 1 : 0, force, out, nullptr, oob, st);
+        int rc = launch_image_hot(x, y, p, n, Himg, Wimg, A.clip, clipx, clipy, bil ? 1 : 0, force, out, blocks, nullptr, oob, st);
         if (rc) return rc;
+        if (blocks) {
+            const int g2 = grid_simple(npix, 256);
+            prof_count(1);
+            if (accum) image_fold_kernel<true><<<g2, 256, 0, st>>>(blocks, out, Himg, Wimg, fill);
+            else image_fold_kernel<false><<<g2, 256, 0, st>>>(blocks, out, Himg, Wimg, fill);
+        }
     } else {
         set_error("evk_image_f32: variant 0x%x not available", variant);
         return EVK_E_UNSUPPORTED;
@@ -363,7 +372,7 @@ int evk_count_u32(const float *x, const float *y, int64_t n, int Himg, int Wimg,
     const unsigned cvariant = variant_of(flags);
     if (n > 0 && (cvariant == EVK_VARIANT_SMEM_TILE || cvariant == EVK_VARIANT_AUTO)) {
         int rc = launch_image_hot(x, y, nullptr, n, Himg, Wimg, A.clip, clipx, clipy, 2, cvariant == EVK_VARIANT_SMEM_TILE ? 1 : 0,
-                                  nullptr, out, oob, st);
+                                  nullptr, nullptr, out, oob, st);
         if (rc) return rc;
     } else if (n > 0) {
         ProfScope prof(st);

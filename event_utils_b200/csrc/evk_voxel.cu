@@ -26,6 +26,8 @@ struct VoxelArgs {
     int64_t head;  // SoA vec4 layout: scalar events before the 16-byte aligned body
     float t0, dt, bm1;
     int B, H, W, nq;
+    int negpos;  // 0: weights = p.  1: two grids, [p>0] -> grid 0, [p<=0] -> grid 1 (voxel_grid.py:172-175).
+                 // 2: numpy truthiness, [p!=0] -> grid 0, [p==0] -> grid 1 (voxel_grid.py:234-235)
     int clip;  // trilinear only
     float clipx, clipy;
     float *out;  // [B][H][W]
@@ -40,12 +42,12 @@ static inline int quads_for_bins(int B) { return B <= 1 ? 1 : (B - 1 + 2) / 3; }
 
 // Add the temporal tap pair (value v0 at bin b0, v1 at bin b0+1) of one pixel.
 template <int SINK>
-__device__ __forceinline__ void add_bin_pair(const VoxelArgs &A, int64_t pix, int b0, float v0, float v1)
+__device__ __forceinline__ void add_bin_pair(const VoxelArgs &A, float *out, float *ws, int64_t pix, int b0, float v0, float v1)
 {
     if (SINK == SINK_SCALAR) {
         const int64_t plane = (int64_t)A.H * A.W;
-        if ((unsigned)b0 < (unsigned)A.B && v0 != 0.0f) red_add(A.out + (int64_t)b0 * plane + pix, v0);
-        if ((unsigned)(b0 + 1) < (unsigned)A.B && v1 != 0.0f) red_add(A.out + (int64_t)(b0 + 1) * plane + pix, v1);
+        if ((unsigned)b0 < (unsigned)A.B && v0 != 0.0f) red_add(out + (int64_t)b0 * plane + pix, v0);
+        if ((unsigned)(b0 + 1) < (unsigned)A.B && v1 != 0.0f) red_add(out + (int64_t)(b0 + 1) * plane + pix, v1);
     } else {
         int lo = b0 < 0 ? 0 : b0;
         int hi = (b0 + 1 > A.B - 1) ? A.B - 1 : b0 + 1;
@@ -61,14 +63,14 @@ __device__ __forceinline__ void add_bin_pair(const VoxelArgs &A, int64_t pix, in
         v.y = (s == 1) ? a : ((s == 0) ? b : 0.0f);
         v.z = (s == 2) ? a : ((s == 1) ? b : 0.0f);
         v.w = (s == 3) ? a : ((s == 2) ? b : 0.0f);
-        red_add4(A.ws + (pix * A.nq + q) * 4, v);
+        red_add4(ws + (pix * A.nq + q) * 4, v);
     }
 }
 
 // Rare path: non-finite tau or polarity.  Literal restatement of voxel_grid.py:138-139 for
 // every bin so that NaN propagation matches (dt == 0 -> NaN in V[:, y, x]).
 template <int SINK>
-__device__ __noinline__ void add_all_bins_slow(const VoxelArgs &A, int64_t pix, float tn, float p)
+__device__ __noinline__ void add_all_bins_slow(const VoxelArgs &A, float *out, float *ws, int64_t pix, float tn, float p)
 {
     for (int b = 0; b < A.B; ++b) {
         float w = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, (float)b)));
@@ -76,11 +78,11 @@ __device__ __noinline__ void add_all_bins_slow(const VoxelArgs &A, int64_t pix, 
         float v = __fmul_rn(p, wb);
         if (v == 0.0f) continue;
         if (SINK == SINK_SCALAR) {
-            red_add(A.out + ((int64_t)b * A.H * A.W) + pix, v);
+            red_add(out + ((int64_t)b * A.H * A.W) + pix, v);
         } else {
             int q = b / 3;
             if (q > A.nq - 1) q = A.nq - 1;
-            red_add(A.ws + (pix * A.nq + q) * 4 + (b - 3 * q), v);
+            red_add(ws + (pix * A.nq + q) * 4 + (b - 3 * q), v);
         }
     }
 }
@@ -126,11 +128,23 @@ __device__ __forceinline__ void voxel_event(const VoxelArgs &A, float x, float y
         int xi, yi;
         if (!wrap_trunc_index(x, A.W, xi) || !wrap_trunc_index(y, A.H, yi)) { ++oob; return; }
         const int64_t pix = (int64_t)yi * A.W + xi;
-        if (!finite) { add_all_bins_slow<SINK>(A, pix, tn, p); return; }
+        float *out = A.out, *ws = A.ws;
+        if (A.negpos) {
+            // fused neg/pos split: the event goes to exactly one of two grids with weight 1
+            const bool pos = (A.negpos == 1) ? (p > 0.0f) : (p != 0.0f);
+            const bool neg = (A.negpos == 1) ? (p <= 0.0f) : (p == 0.0f);
+            if (!pos && !neg) return;  // NaN polarity: weight 0 in both (torch.where on NaN)
+            if (neg) {
+                const int64_t cells = (int64_t)A.H * A.W;
+                if (SINK == SINK_SCALAR) out += cells * A.B; else ws += cells * A.nq * 4;
+            }
+            p = 1.0f;
+        }
+        if (!((fabsf(tn) < 1.0e9f) && (fabsf(p) <= FLT_MAX))) { add_all_bins_slow<SINK>(A, out, ws, pix, tn, p); return; }
         const float fl = floorf(tn);
         const float w0 = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fl)));         // bin floor(tau)
         const float w1 = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fl + 1.0f)));  // bin floor(tau)+1
-        add_bin_pair<SINK>(A, pix, (int)fl, __fmul_rn(p, w0), __fmul_rn(p, w1));
+        add_bin_pair<SINK>(A, out, ws, pix, (int)fl, __fmul_rn(p, w0), __fmul_rn(p, w1));
     } else {
         // trilinear extension: per-bin events_to_image_torch(..., interpolation='bilinear')
         // (image.py:78-86,102-115) with the bin weight folded into the polarity.
@@ -299,6 +313,7 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
                         void *workspace, size_t workspace_bytes)
 {
     VoxelArgs A = A0;
+    const int grids = A.negpos ? 2 : 1;  // neg/pos mode writes out[2][B][H][W]
     const bool bil = (flags & EVK_BILINEAR) != 0;
     const bool accum = (flags & EVK_ACCUMULATE) != 0;
     const int64_t npix = (int64_t)A.H * A.W;
@@ -312,7 +327,7 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
     const int sink = (variant == EVK_VARIANT_VECTOR_RED) ? SINK_QUAD : SINK_SCALAR;
     A.nq = quads_for_bins(A.B);
     if (sink == SINK_QUAD) {
-        const size_t need = bil ? (size_t)npix * A.B * 4 * sizeof(float) : (size_t)npix * A.nq * 4 * sizeof(float);
+        const size_t need = (bil ? (size_t)npix * A.B * 4 * sizeof(float) : (size_t)npix * A.nq * 4 * sizeof(float)) * grids;
         if (workspace == nullptr || workspace_bytes < need) {
             set_error("evk_voxel: workspace of %zu bytes required, %zu given", need, workspace_bytes);
             return EVK_E_WORKSPACE;
@@ -321,7 +336,7 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
         A.ws = static_cast<float *>(workspace);
         EVK_CUDA(cudaMemsetAsync(A.ws, 0, need, st));
     } else if (!accum) {
-        EVK_CUDA(cudaMemsetAsync(A.out, 0, (size_t)npix * A.B * sizeof(float), st));
+        EVK_CUDA(cudaMemsetAsync(A.out, 0, (size_t)npix * A.B * sizeof(float) * grids, st));
     }
     if (A.n > 0) {
         const int per_thread = (layout == LAYOUT_SOA4) ? 4 : 1;
@@ -351,8 +366,13 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
             if (accum) voxel_fold_blocks_kernel<true><<<grid, 256, 0, st>>>(A.ws, A.out, A.B, A.H, A.W);
             else voxel_fold_blocks_kernel<false><<<grid, 256, 0, st>>>(A.ws, A.out, A.B, A.H, A.W);
         } else {
-            if (accum) voxel_fold_kernel<true><<<grid, 256, 0, st>>>(A.ws, A.out, npix, A.B, A.nq);
-            else voxel_fold_kernel<false><<<grid, 256, 0, st>>>(A.ws, A.out, npix, A.B, A.nq);
+            for (int g = 0; g < grids; ++g) {
+                const float *wsg = A.ws + (size_t)g * npix * A.nq * 4;
+                float *og = A.out + (size_t)g * npix * A.B;
+                if (g) prof_count(1);
+                if (accum) voxel_fold_kernel<true><<<grid, 256, 0, st>>>(wsg, og, npix, A.B, A.nq);
+                else voxel_fold_kernel<false><<<grid, 256, 0, st>>>(wsg, og, npix, A.B, A.nq);
+            }
         }
         EVK_CUDA(cudaGetLastError());
     }
@@ -456,6 +476,31 @@ int evk_voxel_windows_f32(const float *x, const float *y, const float *t, const 
     }
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;
+}
+
+int evk_voxel_negpos_f32(const float *x, const float *y, const float *t, const float *p, int64_t n, float t0, float dt,
+                         int B, int H, int W, unsigned flags, float *out_pos_neg, void *workspace, size_t workspace_bytes,
+                         unsigned long long *oob, void *stream)
+{
+    using namespace evk;
+    int rc = check_common(n, B, H, W, out_pos_neg);
+    if (rc) return rc;
+    if (n > 0 && (!x || !y || !t || !p)) { set_error("evk_voxel_negpos_f32: null event array"); return EVK_E_ARG; }
+    if (flags & EVK_BILINEAR) { set_error("evk_voxel_negpos_f32: spatial bilinear is not available in neg/pos mode"); return EVK_E_UNSUPPORTED; }
+    VoxelArgs A{};
+    A.x = x; A.y = y; A.t = t; A.p = p; A.n = n;
+    A.t0 = t0; A.dt = dt; A.bm1 = (float)(B - 1);
+    A.B = B; A.H = H; A.W = W;
+    A.negpos = (flags & EVK_NEGPOS_TRUTHY) ? 2 : 1;
+    A.out = out_pos_neg; A.oob = oob;
+    const uintptr_t ax = (uintptr_t)x & 15, ay = (uintptr_t)y & 15, at = (uintptr_t)t & 15, ap = (uintptr_t)p & 15;
+    int layout = LAYOUT_SOA1;
+    if (ax == ay && ay == at && at == ap && (ax & 3) == 0) {
+        layout = LAYOUT_SOA4;
+        A.head = ((16 - ax) & 15) >> 2;
+        if (A.head > n) A.head = n;
+    }
+    return launch_voxel(A, flags, layout, static_cast<cudaStream_t>(stream), workspace, workspace_bytes);
 }
 
 }  // extern "C"

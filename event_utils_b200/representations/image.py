@@ -182,6 +182,71 @@ def image_to_event_weights(xs, ys, img):
         return out.cpu().numpy()
 
 
+def _timestamp_images(x, y, t, p, t_first, t_last, sensor_size, clip_out_of_range, interpolation, padding, reverse):
+    L = _lib.lib()
+    dev = x.device
+    if padding:
+        img_size = (int(sensor_size[0]) + 1, int(sensor_size[1]) + 1)
+    else:
+        img_size = (int(sensor_size[0]), int(sensor_size[1]))
+    clipx = img_size[1] if interpolation is None and padding == False else img_size[1] - 1  # noqa: E712
+    clipy = img_size[0] if interpolation is None and padding == False else img_size[0] - 1  # noqa: E712
+    with torch.cuda.device(dev):
+        pos = torch.empty(img_size, dtype=torch.float32, device=dev)
+        neg = torch.empty(img_size, dtype=torch.float32, device=dev)
+        ws = _lib.scratch("tsimg_ws", L.evk_timestamp_image_workspace_bytes(*img_size), dev)
+        oob = _lib.oob_counter(dev)
+        flags = (_lib.CLIP if clip_out_of_range else 0) | (_lib.TS_REVERSE if reverse else 0)
+        _lib.check(L.evk_timestamp_image_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), x.shape[0], t_first, t_last,
+                                             img_size[0], img_size[1], float(clipx), float(clipy), flags, _lib.ptr(pos),
+                                             _lib.ptr(neg), _lib.ptr(ws), ws.numel(), _lib.ptr(oob), _lib.stream()))
+        E.raise_if_oob(oob, "timestamp image", img_size)
+    return pos, neg
+
+
+def events_to_timestamp_image_torch(xs, ys, ts, ps,
+        device=None, sensor_size=(180, 240), clip_out_of_range=True,
+        interpolation='bilinear', padding=True, timestamp_reverse=False):
+    """
+    Average-timestamp images (Zhu et al. 2019) of the positive and negative events; drop-in for
+    image.py:286-353.  Quirks kept: the count images start at one, and a clipped event keeps its
+    weight (only its index is zeroed).
+    @returns img_pos, img_neg (canvas (H+1,W+1) with padding)
+    """
+    xs_t = E.as_tensor(xs)
+    if device is None:
+        device = xs_t.device
+    device = torch.device(device)
+    dev = E.compute_device(xs, ys, ts, ps)
+    x, y, t, p = (E.as_tensor(a).squeeze().reshape(-1).to(dev).to(torch.float32).contiguous() for a in (xs, ys, ts, ps))
+    fl = torch.stack((t[0], t[-1])).tolist()
+    pos, neg = _timestamp_images(x, y, t, p, fl[0], fl[1], sensor_size, clip_out_of_range, interpolation, padding,
+                                 timestamp_reverse)
+    if pos.device != device:
+        pos, neg = pos.to(device), neg.to(device)
+    return pos, neg
+
+
+def events_to_timestamp_image(xn, yn, ts, pn,
+        device=None, sensor_size=(180, 240), clip_out_of_range=True,
+        interpolation='bilinear', padding=True, normalize_timestamps=True):
+    """
+    numpy flavour; drop-in for image.py:219-284 (numpy in, numpy float32 out).  Timestamps are made
+    relative to ts[0] in float64 before the cast to float32, like the reference (:241-243).
+    """
+    if not normalize_timestamps:
+        raise NotImplementedError("normalize_timestamps=False is not provided by the GPU path")
+    dev = E.compute_device()
+    ts = np.asarray(ts, dtype=np.float64).reshape(-1)
+    rel = ts - ts[0]
+    x, y, p = (torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).to(dev).float().contiguous() for a in (xn, yn, pn))
+    t = torch.from_numpy(rel).to(dev).float().contiguous()
+    # the reference divides by (ts[-1] + 1e-6) of the RELATIVE stamps (image.py:261): first = 0
+    pos, neg = _timestamp_images(x, y, t, p, 0.0, float(np.float32(rel[-1])), sensor_size, clip_out_of_range,
+                                 interpolation, padding, False)
+    return pos.cpu().numpy(), neg.cpu().numpy()
+
+
 def events_to_image_drv(xn, yn, pn, jacobian_xn, jacobian_yn,
         device=None, sensor_size=(180, 240), clip_out_of_range=True,
         interpolation='bilinear', padding=True, compute_gradient=False):

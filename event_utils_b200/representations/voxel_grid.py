@@ -121,22 +121,35 @@ def events_to_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240)
 def events_to_neg_pos_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240), temporal_bilinear=True):
     """
     Positive and negative events in separate voxel grids; drop-in for voxel_grid.py:155-182
-    (weights [p>0] and [p<=0]).
+    (weights [p>0] and [p<=0]).  The reference runs the whole voxel build twice; here both grids
+    come out of ONE pass over the events (evk_voxel_negpos_f32).
     @returns (voxel_pos, voxel_neg)
     """
-    ps_t = E.as_tensor(ps)
-    dev = E.compute_device(xs, ys, ts, ps)
-    psd = ps_t.to(dev)
-    pos = (psd > 0).to(torch.float32)
-    neg = (psd <= 0).to(torch.float32)
-    xs_d, ys_d, ts_d = (E.as_tensor(a).to(dev) for a in (xs, ys, ts))
+    assert(len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps))
+    if not temporal_bilinear:
+        raise NotImplementedError("temporal_bilinear=False is undefined in the reference "
+                                  "(voxel_grid.py:144-147 raises NameError)")
+    if len(xs) == 0:
+        raise IndexError("index -1 is out of bounds for dimension 0 with size 0")
+    L = _lib.lib()
     if device is None:
         device = E.as_tensor(xs).device
-    vp = events_to_voxel_torch(xs_d, ys_d, ts_d, pos, B, device=device, sensor_size=sensor_size,
-                               temporal_bilinear=temporal_bilinear)
-    vn = events_to_voxel_torch(xs_d, ys_d, ts_d, neg, B, device=device, sensor_size=sensor_size,
-                               temporal_bilinear=temporal_bilinear)
-    return vp, vn
+    device = torch.device(device)
+    dev = E.compute_device(xs, ys, ts, ps)
+    H, W, B = int(sensor_size[0]), int(sensor_size[1]), int(B)
+    with torch.cuda.device(dev):
+        t, t0, dt = _times_f32(ts, dev)
+        x, y, p = E.coords_f32(xs, dev), E.coords_f32(ys, dev), E.weights_f32(ps, dev)
+        out = torch.empty((2, B, H, W), dtype=torch.float32, device=dev)
+        flags = E.variant_flag()
+        ws = _lib.scratch("voxel_ws", 2 * L.evk_voxel_workspace_bytes(B, H, W, flags), dev)
+        oob = _lib.oob_counter(dev)
+        _lib.check(L.evk_voxel_negpos_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), x.shape[0], t0, dt, B, H, W,
+                                          flags, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.ptr(oob), _lib.stream()))
+        E.raise_if_oob(oob, "voxel grid", (B, H, W))
+    if out.device != device:
+        out = out.to(device)
+    return out[0], out[1]
 
 
 def events_to_voxel(xs, ys, ts, ps, B, sensor_size=(180, 240), temporal_bilinear=True):

@@ -45,6 +45,7 @@ extern "C" {
 #define EVK_ACCUMULATE 0x1u   /* add into `out` instead of overwriting it */
 #define EVK_BILINEAR 0x2u     /* spatial 4-tap bilinear splat instead of nearest (truncate) */
 #define EVK_CLIP 0x4u         /* events_to_image_torch(clip_out_of_range=True) semantics */
+#define EVK_NEGPOS_TRUTHY 0x8u /* neg/pos split on numpy truthiness (p != 0) instead of p > 0 */
 /* kernel variant selection, bits 8..11 (0 = pick automatically) */
 #define EVK_VARIANT_SHIFT 8
 #define EVK_VARIANT_MASK (0xFu << EVK_VARIANT_SHIFT)
@@ -53,6 +54,8 @@ extern "C" {
 #define EVK_VARIANT_VECTOR_RED (2u << EVK_VARIANT_SHIFT) /* one red.global.add.v4.f32 per tap pair, quad-layout workspace */
 #define EVK_VARIANT_SMEM_TILE (3u << EVK_VARIANT_SHIFT)  /* shared-memory tile privatisation + bulk reduce-store */
 #define EVK_VARIANT_WARP_AGG (4u << EVK_VARIANT_SHIFT)   /* warp-aggregated (match.any) global reds, for hot-spot streams */
+
+#define EVK_TS_REVERSE 0x80u  /* timestamp images: timestamp_reverse=True (image.py:318-319) */
 
 /* cmax flags */
 #define EVK_CMAX_WANT_GRAD 0x10u    /* also produce the analytic gradient */
@@ -91,6 +94,17 @@ int evk_voxel_f32(const float *x, const float *y, const float *t, const float *p
                   float t0, float dt, int B, int H, int W, unsigned flags, float *out,
                   void *workspace, size_t workspace_bytes, unsigned long long *oob, void *stream);
 
+/* Positive and negative events into separate grids in ONE pass.  Replaces
+ * events_to_neg_pos_voxel_torch, lib/representations/voxel_grid.py:155-182 (two full
+ * events_to_voxel_torch calls with weights [p>0] and [p<=0], :172-175); with EVK_NEGPOS_TRUTHY the
+ * numpy flavour's split np.where(ps,1,0) / np.where(ps,0,1) (:234-235).
+ * out_pos_neg: 2*B*H*W floats, [0] = positive grid, [1] = negative grid.
+ * workspace: 2 * evk_voxel_workspace_bytes(B,H,W,flags) bytes. */
+int evk_voxel_negpos_f32(const float *x, const float *y, const float *t, const float *p, int64_t n,
+                         float t0, float dt, int B, int H, int W, unsigned flags, float *out_pos_neg,
+                         void *workspace, size_t workspace_bytes, unsigned long long *oob,
+                         void *stream);
+
 /* Same, events given as one interleaved (N,4) [x,y,t,p] f32 array (the data-loader layout,
  * lib/data_loaders/base_dataset.py:306,510); ev must be 16-byte aligned. */
 int evk_voxel_aos_f32(const float *ev, int64_t n, float t0, float dt, int B, int H, int W,
@@ -119,6 +133,17 @@ size_t evk_image_workspace_bytes(int Himg, int Wimg, unsigned flags);
 int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int Himg, int Wimg,
                   float clipx, float clipy, unsigned flags, float fill, float *out,
                   void *workspace, size_t workspace_bytes, unsigned long long *oob, void *stream);
+
+/* Average-timestamp images of the positive / negative events.  Replaces
+ * events_to_timestamp_image_torch, lib/representations/image.py:286-353 (and the numpy flavour
+ * :219-284 after its casts).  t_first / t_last are ts[0] / ts[-1]; Himg, Wimg the canvas
+ * (sensor+1 with padding); clipx/clipy as image.py:311-312.  out_pos / out_neg: Himg*Wimg floats.
+ * workspace: evk_timestamp_image_workspace_bytes() bytes, 16-byte aligned. */
+size_t evk_timestamp_image_workspace_bytes(int Himg, int Wimg);
+int evk_timestamp_image_f32(const float *x, const float *y, const float *t, const float *p, int64_t n,
+                            float t_first, float t_last, int Himg, int Wimg, float clipx, float clipy,
+                            unsigned flags, float *out_pos, float *out_neg, void *workspace,
+                            size_t workspace_bytes, unsigned long long *oob, void *stream);
 
 /* Integer-exact event-count image (nearest, weight +1 per event): out is u32 [Himg][Wimg].
  * The bit-exact form of events_to_image(_torch) for ps == 1 (image.py:37-38, :95). */

@@ -378,3 +378,52 @@ EVO_API void evo_bounds_mask_f64(const double *x, const double *y, int64_t n, do
         mask[i] = m;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * image.py:286-353 events_to_timestamp_image_torch (and :219-284, same arithmetic after its
+ * casts): average-timestamp images of the positive / negative events.
+ *   tn = (t - t_first) / (t_last - t_first + 1e-6)        (reverse: (-t + t_last) / (...))
+ *   four bilinear accumulations: tn*[p>0], [p>0], tn*[p<=0], [p<=0]; the two count images
+ *   start at ONE (image.py:333,335); the clip mask zeroes the INDEX only, never the weights
+ *   (masked_ps is computed but unused, image.py:330); result = sum / count with count==0 -> 1.
+ * out: pos then neg, each Himg*Wimg.
+ * ------------------------------------------------------------------------------------------ */
+EVO_API int64_t evo_timestamp_image_f32(const float *x, const float *y, const float *t, const float *p, int64_t n,
+                                        float t_first, float t_last, int reverse, int Himg, int Wimg, int clip,
+                                        float clipx, float clipy, float *out)
+{
+    const int64_t np_ = (int64_t)Himg * Wimg;
+    float *acc = (float *)calloc((size_t)np_ * 4, sizeof(float)); /* Tpos, Cpos, Tneg, Cneg */
+    int64_t oob = 0;
+    const float denom = (t_last - t_first) + 1e-6f;
+    for (int64_t i = 0; i < np_; ++i) { acc[np_ + i] = 1.0f; acc[3 * np_ + i] = 1.0f; }
+    for (int64_t i = 0; i < n; ++i) {
+        float m = 1.0f;
+        if (clip) m = (x[i] >= clipx ? 0.0f : 1.0f) * (y[i] >= clipy ? 0.0f : 1.0f);
+        float pxf = floorf(x[i]), pyf = floorf(y[i]);
+        float dx = x[i] - pxf, dy = y[i] - pyf;
+        int64_t px = trunc_to_long(pxf * m), py = trunc_to_long(pyf * m);
+        int64_t x0, x1, y0, y1;
+        if (!wrap_index(px, Wimg, &x0) || !wrap_index(px + 1, Wimg, &x1) ||
+            !wrap_index(py, Himg, &y0) || !wrap_index(py + 1, Himg, &y1)) { ++oob; continue; }
+        float tn = reverse ? ((-t[i] + t_last) / denom) : ((t[i] - t_first) / denom);
+        float pm = (p[i] > 0.0f) ? 1.0f : 0.0f, nm = (p[i] <= 0.0f) ? 1.0f : 0.0f;
+        float w[4] = {tn * pm, pm, tn * nm, nm};
+        float ox = 1.0f - dx, oy = 1.0f - dy;
+        for (int k = 0; k < 4; ++k) {
+            float *im = acc + k * np_;
+            im[y0 * Wimg + x0] += (w[k] * ox) * oy;
+            im[y0 * Wimg + x1] += (w[k] * dx) * oy;
+            im[y1 * Wimg + x0] += (w[k] * ox) * dy;
+            im[y1 * Wimg + x1] += (w[k] * dx) * dy;
+        }
+    }
+    for (int s = 0; s < 2; ++s)
+        for (int64_t i = 0; i < np_; ++i) {
+            float c = acc[(2 * s + 1) * np_ + i];
+            if (c == 0.0f) c = 1.0f;
+            out[s * np_ + i] = acc[(2 * s) * np_ + i] / c;
+        }
+    free(acc);
+    return oob;
+}

@@ -37,6 +37,8 @@ def lib():
         L.evo_image_nearest_f32.argtypes = [vp, vp, vp, i64, ci, ci, ci, f32, f32, vp]
         L.evo_image_bilinear_f32.restype = i64
         L.evo_image_bilinear_f32.argtypes = [vp, vp, vp, i64, ci, ci, ci, f32, f32, vp]
+        L.evo_timestamp_image_f32.restype = i64
+        L.evo_timestamp_image_f32.argtypes = [vp, vp, vp, vp, i64, f32, f32, ci, ci, ci, ci, f32, f32, vp]
         L.evo_warp_flow_f32.restype = None
         L.evo_warp_flow_f32.argtypes = [vp, vp, vp, i64, vp, ci, ci, f32, vp, vp]
         L.evo_iwe_linvel.restype = i64
@@ -116,6 +118,26 @@ def image_torch_f32(xs, ys, ps, sensor_size=(180, 240), clip_out_of_range=True,
     if oob:
         raise OracleIndexError("%d events index outside the image" % oob)
     return out
+
+
+def timestamp_image_f32(xs, ys, ts, ps, sensor_size=(180, 240), clip_out_of_range=True, interpolation='bilinear',
+                        padding=True, timestamp_reverse=False):
+    """events_to_timestamp_image_torch, image.py:286-353 -> (img_pos, img_neg)."""
+    x, y, t, p = (_c(np.asarray(a).reshape(-1), np.float32) for a in (xs, ys, ts, ps))
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    if padding:
+        H, W = H + 1, W + 1
+    if interpolation is None and padding is False:
+        clipx, clipy = W, H
+    else:
+        clipx, clipy = W - 1, H - 1
+    out = np.zeros((2, H, W), np.float32)
+    oob = lib().evo_timestamp_image_f32(_p(x), _p(y), _p(t), _p(p), x.shape[0], float(t[0]), float(t[-1]),
+                                        int(bool(timestamp_reverse)), H, W, int(bool(clip_out_of_range)),
+                                        float(clipx), float(clipy), _p(out))
+    if oob:
+        raise OracleIndexError("%d events index outside the image" % oob)
+    return out[0], out[1]
 
 
 def warp_flow_f32(xs, ys, ts, flow, t0=None):

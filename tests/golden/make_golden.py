@@ -134,6 +134,24 @@ cases["np_nearest"] = ref.image.events_to_image(xi, yi, pi, sensor_size=(40, 56)
 cases["np_meanval"] = ref.image.events_to_image(xi, yi, pi, sensor_size=(40, 56), meanval=True, default=-1)
 save("image", **cases)
 
+# ---- timestamp images (image.py:219-353) ------------------------------------------------------
+cases = {}
+rng = np.random.default_rng(51)
+n = 6000
+xs = (rng.random(n) * 60 - 1).astype(np.float32)      # a few negative coordinates (wrap)
+ys = (rng.random(n) * 44).astype(np.float32)
+xs[::19] += 3                                          # and some beyond the clip threshold
+ts = (np.sort(rng.random(n)) * 0.3 + 2).astype(np.float32)
+ps = (rng.integers(0, 2, n) * 2 - 1).astype(np.float32)
+cases.update(dict(x=xs, y=ys, t=ts, p=ps))
+for tag, kw in {"default": dict(), "reverse": dict(timestamp_reverse=True), "nopad": dict(padding=False)}.items():
+    a, b = ref.image.events_to_timestamp_image_torch(T(xs), T(ys), T(ts), T(ps), sensor_size=(40, 56), **kw)
+    cases[tag + "_pos"], cases[tag + "_neg"] = a.numpy(), b.numpy()
+t64 = ts.astype(np.float64) + 1.6e9
+a, b = ref.image.events_to_timestamp_image(xs.astype(np.float64), ys.astype(np.float64), t64, ps.astype(np.float64), sensor_size=(40, 56))
+cases.update(dict(np_t=t64, np_pos=a, np_neg=b))
+save("tsimg", **cases)
+
 # ---- lower-level helpers (image.py:102-160) and the bounds mask -------------------------------
 cases = {}
 rng = np.random.default_rng(31)

@@ -150,6 +150,28 @@ def test_hot_spot_bilinear_and_signed(oracle):
         assert np.abs(out - ref)[cold].max() <= 1e-5 * np.abs(ref).max()
 
 
+def test_timestamp_images(oracle):
+    from event_utils_b200.representations.image import events_to_timestamp_image, events_to_timestamp_image_torch
+    g = golden("tsimg")
+    x, y, t, p = dev(g["x"], g["y"], g["t"], g["p"])
+    for tag, kw in {"default": dict(), "reverse": dict(timestamp_reverse=True), "nopad": dict(padding=False)}.items():
+        pos, neg = events_to_timestamp_image_torch(x, y, t, p, sensor_size=(40, 56), **kw)
+        assert pos.shape == g[tag + "_pos"].shape and pos.is_cuda
+        assert_close_to_max(pos.cpu().numpy(), g[tag + "_pos"], 1e-5, tag)
+        assert_close_to_max(neg.cpu().numpy(), g[tag + "_neg"], 1e-5, tag)
+    pos, neg = events_to_timestamp_image(g["x"].astype(np.float64), g["y"].astype(np.float64), g["np_t"], g["p"].astype(np.float64),
+                                         sensor_size=(40, 56))
+    assert pos.dtype == np.float32
+    assert_close_to_max(pos, g["np_pos"], 1e-5)
+    assert_close_to_max(neg, g["np_neg"], 1e-5)
+    # larger random case against the oracle
+    xe, ye, te, pe = make_events(17, 700000, 180, 240)
+    pos, neg = events_to_timestamp_image_torch(*dev(xe, ye, te, pe))
+    po, no = oracle.timestamp_image_f32(xe, ye, te, pe)
+    assert_close_to_max(pos.cpu().numpy(), po, 1e-5)
+    assert_close_to_max(neg.cpu().numpy(), no, 1e-5)
+
+
 def test_numpy_flavour():
     from event_utils_b200.representations.image import events_to_image
     g = golden("image")

@@ -148,6 +148,24 @@ def test_numpy_flavour_and_negpos(oracle):
     assert_close_to_max(vn.cpu().numpy(), g["np_neg"], 1e-5)
 
 
+def test_negpos_fused_large(oracle):
+    """One-pass neg/pos split against two oracle voxel builds, both kernel variants, incl. p == 0."""
+    import event_utils_b200 as eu
+    from event_utils_b200.representations.voxel_grid import events_to_neg_pos_voxel_torch
+    x, y, t, p = make_events(31, 1500003, 120, 160)
+    p[::7] = 0.0
+    rp = oracle.voxel_f32(x, y, t, (p > 0).astype(np.float32), 5, (120, 160))
+    rn = oracle.voxel_f32(x, y, t, (p <= 0).astype(np.float32), 5, (120, 160))
+    for variant in VARIANTS:
+        eu.config.variant = variant
+        vp, vn = events_to_neg_pos_voxel_torch(*dev(x, y, t, p), 5, sensor_size=(120, 160))
+        assert_close_to_max(vp.cpu().numpy(), rp, 1e-5, variant)
+        assert_close_to_max(vn.cpu().numpy(), rn, 1e-5, variant)
+    vp, vn = events_to_neg_pos_voxel_torch(*(torch.from_numpy(a) for a in (x, y, t, p)), 5, sensor_size=(120, 160))
+    assert not vp.is_cuda
+    assert_close_to_max(vn.numpy(), rn, 1e-5)
+
+
 def test_windows_helpers(oracle):
     from event_utils_b200.representations.voxel_grid import (events_to_voxel_timesync_torch, voxel_grids_fixed_n_torch)
     x, y, t, p = make_events(12, 50000, 60, 80)

@@ -83,6 +83,19 @@ def test_image_known_answers(oracle):
     assert out.shape == (5, 7) and out[0, 0] == 7500 and out[0, 6] >= 2500
 
 
+def test_timestamp_images(oracle):
+    g = golden("tsimg")
+    ev = [g[k] for k in "xytp"]
+    for tag, kw in {"default": dict(), "reverse": dict(timestamp_reverse=True), "nopad": dict(padding=False)}.items():
+        pos, neg = oracle.timestamp_image_f32(*ev, sensor_size=(40, 56), **kw)
+        assert_close_to_max(pos, g[tag + "_pos"], 2e-6, tag)
+        assert_close_to_max(neg, g[tag + "_neg"], 2e-6, tag)
+    rel = (g["np_t"] - g["np_t"][0]).astype(np.float32)
+    pos, neg = oracle.timestamp_image_f32(g["x"], g["y"], rel, g["p"], sensor_size=(40, 56))
+    assert_close_to_max(pos, g["np_pos"], 2e-6)
+    assert_close_to_max(neg, g["np_neg"], 2e-6)
+
+
 def test_flow_warp(oracle):
     g = golden("flow")
     xw, yw = oracle.warp_flow_f32(g["x"], g["y"], g["t"], g["flow"])
