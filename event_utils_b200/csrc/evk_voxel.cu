@@ -178,7 +178,7 @@ __device__ __forceinline__ void voxel_event(const VoxelArgs &A, float x, float y
 
 constexpr int kThreads = 256;
 #ifndef EVK_VOXEL_MIN_CTAS
-#define EVK_VOXEL_MIN_CTAS 8
+#define EVK_VOXEL_MIN_CTAS 5
 #endif
 
 template <int SINK, bool BIL, int LAYOUT>

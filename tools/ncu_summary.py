@@ -52,8 +52,9 @@ if __name__ == "__main__":
     summary = {}
     lines = ["# ncu --set full summaries (%s)\n" % tag]
     for rep in sys.argv[2:]:
-        for k in raw(rep):
-            name = os.path.basename(rep).replace(".ncu-rep", "")
+        for idx, k in enumerate(raw(rep)):
+            short = k["kernel"].split("(")[0].replace("void ", "").replace("evk::", "")
+            name = "%s#%d %s" % (os.path.basename(rep).replace(".ncu-rep", ""), idx, short)
             rd = to_bytes(k.get("dram__bytes_read.sum", 0), k.get("dram__bytes_read.sum.unit", "byte"))
             wr = to_bytes(k.get("dram__bytes_write.sum", 0), k.get("dram__bytes_write.sum.unit", "byte"))
             k["dram_bytes_total"] = rd + wr
