@@ -273,12 +273,12 @@ __global__ void __launch_bounds__(256) voxel_fold_kernel(const float *__restrict
 // Batched windows: CTA (w, s) scatters slice s of window w into out[w] with that window's own
 // t0 / dt (voxel_grid.py:133-134 applied per window, as voxel_grids_fixed_n_torch :53-56 does).
 __global__ void __launch_bounds__(kThreads) voxel_windows_kernel(const VoxelArgs A, const int64_t *__restrict__ offsets,
-                                                                 int n_windows, int slices)
+                                                                 int n_windows, int slices, int pairs)
 {
     unsigned oob = 0;
     const int w = blockIdx.x / slices, s = blockIdx.x - w * slices;
     if (w < n_windows) {
-        const int64_t first = offsets[w], last = offsets[w + 1];
+        const int64_t first = pairs ? offsets[2 * w] : offsets[w], last = pairs ? offsets[2 * w + 1] : offsets[w + 1];
         if (last > first) {
             VoxelArgs Aw = A;
             Aw.t0 = A.t[first];
@@ -472,7 +472,8 @@ int evk_voxel_windows_f32(const float *x, const float *y, const float *t, const 
     {
         ProfScope prof(st);
         prof_count(1);
-        voxel_windows_kernel<<<(unsigned)(n_windows * slices), kThreads, 0, st>>>(A, offsets, n_windows, (int)slices);
+        voxel_windows_kernel<<<(unsigned)(n_windows * slices), kThreads, 0, st>>>(A, offsets, n_windows, (int)slices,
+                                                                                  (flags & EVK_WINDOW_PAIRS) ? 1 : 0);
     }
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;

@@ -211,17 +211,55 @@ def events_to_voxel_timesync_torch(xs, ys, ts, ps, B, t0, t1, device=None, np_ts
                                  temporal_bilinear=temporal_bilinear)
 
 
+def _batched_windows(xs, ys, ts, ps, starts, ends, B, sensor_size):
+    """All windows [starts[w], ends[w]) in ONE launch (evk_voxel_windows_f32); None if the inputs are
+    not contiguous float32 CUDA tensors (callers then fall back to one call per window)."""
+    if not all(isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float32 and a.dim() == 1
+               and a.is_contiguous() for a in (xs, ys, ts, ps)):
+        return None
+    nw = len(starts)
+    H, W, B = int(sensor_size[0]), int(sensor_size[1]), int(B)
+    if nw == 0:
+        return []
+    L = _lib.lib()
+    dev = xs.device
+    with torch.cuda.device(dev):
+        pairs = torch.tensor(np.stack((np.asarray(starts, dtype=np.int64), np.asarray(ends, dtype=np.int64)), 1).reshape(-1),
+                             dtype=torch.int64, device=dev)
+        out = torch.empty((nw, B, H, W), dtype=torch.float32, device=dev)
+        oob = _lib.oob_counter(dev)
+        total = int(np.sum(np.asarray(ends) - np.asarray(starts)))
+        _lib.check(L.evk_voxel_windows_f32(_lib.ptr(xs), _lib.ptr(ys), _lib.ptr(ts), _lib.ptr(ps), _lib.ptr(pairs), nw, total,
+                                           B, H, W, _lib.WINDOW_PAIRS, _lib.ptr(out), _lib.ptr(oob), _lib.stream()))
+        E.raise_if_oob(oob, "voxel grid", (B, H, W))
+    return list(out.unbind(0))
+
+
 def voxel_grids_fixed_n_torch(xs, ys, ts, ps, B, n, sensor_size=(180, 240), temporal_bilinear=True):
     """List of voxel grids of n events each; drop-in for voxel_grid.py:37-57 (windows
-    range(0, len(xs)-n, n))."""
+    range(0, len(xs)-n, n)).  CUDA float32 inputs: every window in one kernel launch."""
+    starts = list(range(0, len(xs) - n, n))
+    if temporal_bilinear:
+        grids = _batched_windows(xs, ys, ts, ps, starts, [i + n for i in starts], B, sensor_size)
+        if grids is not None:
+            return grids
     return [events_to_voxel_torch(xs[i:i + n], ys[i:i + n], ts[i:i + n], ps[i:i + n], B,
                                   sensor_size=sensor_size, temporal_bilinear=temporal_bilinear)
-            for i in range(0, len(xs) - n, n)]
+            for i in starts]
 
 
 def voxel_grids_fixed_t_torch(xs, ys, ts, ps, B, t, sensor_size=(180, 240), temporal_bilinear=True):
-    """List of voxel grids of temporal width t; drop-in for voxel_grid.py:59-80."""
+    """List of voxel grids of temporal width t; drop-in for voxel_grid.py:59-80.  CUDA float32
+    inputs: every window in one kernel launch."""
     np_ts = ts.cpu().numpy()
+    t_starts = np.arange(ts[0].item(), ts[-1].item() - t, t)
+    if temporal_bilinear:
+        starts = [int(np.searchsorted(np_ts, t0)) for t0 in t_starts]
+        ends = [int(np.searchsorted(np_ts, t0 + t)) for t0 in t_starts]
+        assert(all(s < e for s, e in zip(starts, ends)))       # voxel_grid.py:108
+        grids = _batched_windows(xs, ys, ts, ps, starts, ends, B, sensor_size)
+        if grids is not None:
+            return grids
     return [events_to_voxel_timesync_torch(xs, ys, ts, ps, B, t_start, t_start + t, np_ts=np_ts,
                                            sensor_size=sensor_size, temporal_bilinear=temporal_bilinear)
-            for t_start in np.arange(ts[0].item(), ts[-1].item() - t, t)]
+            for t_start in t_starts]

@@ -45,6 +45,7 @@ extern "C" {
 #define EVK_ACCUMULATE 0x1u   /* add into `out` instead of overwriting it */
 #define EVK_BILINEAR 0x2u     /* spatial 4-tap bilinear splat instead of nearest (truncate) */
 #define EVK_CLIP 0x4u         /* events_to_image_torch(clip_out_of_range=True) semantics */
+#define EVK_WINDOW_PAIRS 0x100000u /* evk_voxel_windows_f32: offsets are (start,end) pairs, 2*n_windows entries */
 #define EVK_NEGPOS_TRUTHY 0x8u /* neg/pos split on numpy truthiness (p != 0) instead of p > 0 */
 /* kernel variant selection, bits 8..11 (0 = pick automatically) */
 #define EVK_VARIANT_SHIFT 8
@@ -115,6 +116,8 @@ int evk_voxel_aos_f32(const float *ev, int64_t n, float t0, float dt, int B, int
  * base_dataset.py:322-367): window w covers events [offsets[w], offsets[w+1]) and writes
  * out[w] ([n_windows][B][H][W]); t0/dt per window are taken from the window's first / last
  * timestamp exactly as voxel_grid.py:133-134 does.  offsets: n_windows+1 int64 on the device.
+ * With EVK_WINDOW_PAIRS offsets holds 2*n_windows entries, (start,end) per window (windows may then
+ * overlap or leave gaps, as events_to_voxel_timesync_torch's do, voxel_grid.py:105-106).
  * n_events_hint: total number of events covered (0 = unknown), used only to size the launch. */
 int evk_voxel_windows_f32(const float *x, const float *y, const float *t, const float *p,
                           const int64_t *offsets, int n_windows, int64_t n_events_hint, int B, int H,

@@ -175,6 +175,17 @@ def test_windows_helpers(oracle):
     for k, gk in enumerate(grids):
         sl = slice(12000 * k, 12000 * (k + 1))
         assert_close_to_max(gk.cpu().numpy(), oracle.voxel_f32(x[sl], y[sl], t[sl], p[sl], 5, (60, 80)), 1e-5)
+    from event_utils_b200.representations.voxel_grid import voxel_grids_fixed_t_torch
+    gt = voxel_grids_fixed_t_torch(X, Y, T, P, 4, 0.021, sensor_size=(60, 80))
+    t_starts = np.arange(t[0], t[-1] - 0.021, 0.021)
+    assert len(gt) == len(t_starts) and len(gt) >= 3
+    for k, t0 in enumerate(t_starts):
+        i0, i1 = np.searchsorted(t, t0), np.searchsorted(t, t0 + 0.021)
+        assert_close_to_max(gt[k].cpu().numpy(), oracle.voxel_f32(x[i0:i1], y[i0:i1], t[i0:i1], p[i0:i1], 4, (60, 80)), 1e-5)
+    # non-contiguous / CPU inputs take the per-window fallback and agree
+    gl = voxel_grids_fixed_n_torch(*(torch.from_numpy(a) for a in (x, y, t, p)), 5, 12000, sensor_size=(60, 80))
+    assert len(gl) == 4 and not gl[0].is_cuda
+    assert_close_to_max(gl[2].numpy(), grids[2].cpu().numpy(), 1e-5)
     v = events_to_voxel_timesync_torch(X, Y, T, P, 3, 0.02, 0.06, sensor_size=(60, 80))
     i0, i1 = np.searchsorted(t, 0.02), np.searchsorted(t, 0.06)
     assert_close_to_max(v.cpu().numpy(), oracle.voxel_f32(x[i0:i1], y[i0:i1], t[i0:i1], p[i0:i1], 3, (60, 80)), 1e-5)
