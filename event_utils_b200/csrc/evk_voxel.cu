@@ -26,6 +26,7 @@ struct VoxelArgs {
     int64_t head;  // SoA vec4 layout: scalar events before the 16-byte aligned body
     float t0, dt, bm1;
     int B, H, W, nq;
+    int auto_span;  // 1: t0 = t[0], dt = t[n-1] - t[0] read on the device (voxel_grid.py:133) -- no host sync
     int negpos;  // 0: weights = p.  1: two grids, [p>0] -> grid 0, [p<=0] -> grid 1 (voxel_grid.py:172-175).
                  // 2: numpy truthiness, [p!=0] -> grid 0, [p==0] -> grid 1 (voxel_grid.py:234-235)
     int clip;  // trilinear only
@@ -182,8 +183,16 @@ constexpr int kThreads = 256;
 #endif
 
 template <int SINK, bool BIL, int LAYOUT>
-__global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_kernel(const VoxelArgs A)
+__global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_kernel(const VoxelArgs A_in)
 {
+    VoxelArgs A = A_in;
+    if (A.auto_span && A.n > 0) {
+        // first / last timestamp straight from the (time-sorted) stream; AoS keeps t at offset 2
+        const float first = (LAYOUT == LAYOUT_AOS) ? A.x[2] : A.t[0];
+        const float last = (LAYOUT == LAYOUT_AOS) ? A.x[4 * (A.n - 1) + 2] : A.t[A.n - 1];
+        A.t0 = first;
+        A.dt = __fsub_rn(last, first);
+    }
     unsigned oob = 0;
     const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
@@ -414,6 +423,7 @@ int evk_voxel_f32(const float *x, const float *y, const float *t, const float *p
     A.B = B; A.H = H; A.W = W;
     A.clip = (flags & EVK_CLIP) ? 1 : 0;
     A.clipx = (float)(W - 1); A.clipy = (float)(H - 1);
+    A.auto_span = (flags & EVK_AUTO_SPAN) ? 1 : 0;
     A.out = out; A.oob = oob;
     // choose the load layout: 16-byte body if all four arrays share their misalignment
     const uintptr_t ax = (uintptr_t)x & 15, ay = (uintptr_t)y & 15, at = (uintptr_t)t & 15, ap = (uintptr_t)p & 15;
@@ -440,6 +450,7 @@ int evk_voxel_aos_f32(const float *ev, int64_t n, float t0, float dt, int B, int
     A.B = B; A.H = H; A.W = W;
     A.clip = (flags & EVK_CLIP) ? 1 : 0;
     A.clipx = (float)(W - 1); A.clipy = (float)(H - 1);
+    A.auto_span = (flags & EVK_AUTO_SPAN) ? 1 : 0;
     A.out = out; A.oob = oob;
     return launch_voxel(A, flags, LAYOUT_AOS, static_cast<cudaStream_t>(stream), workspace, workspace_bytes);
 }
@@ -493,6 +504,7 @@ int evk_voxel_negpos_f32(const float *x, const float *y, const float *t, const f
     A.t0 = t0; A.dt = dt; A.bm1 = (float)(B - 1);
     A.B = B; A.H = H; A.W = W;
     A.negpos = (flags & EVK_NEGPOS_TRUTHY) ? 2 : 1;
+    A.auto_span = (flags & EVK_AUTO_SPAN) ? 1 : 0;
     A.out = out_pos_neg; A.oob = oob;
     const uintptr_t ax = (uintptr_t)x & 15, ay = (uintptr_t)y & 15, at = (uintptr_t)t & 15, ap = (uintptr_t)p & 15;
     int layout = LAYOUT_SOA1;

@@ -105,12 +105,13 @@ def events_to_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240)
         return out if device.type == "cpu" else out.to(device)
 
     aos = E.aos_base(xs, ys, ts, ps) if isinstance(xs, torch.Tensor) and xs.is_cuda else None
+    ts_t = E.as_tensor(ts)
     if aos is not None:
-        first, last = aos[0, 2], aos[-1, 2]
-        fl = torch.stack((first, last)).tolist()
-        t0 = np.float32(fl[0])
-        dt = np.float32(fl[1]) - t0
-        grid = _voxel_device(None, None, None, None, float(t0), float(dt), B, H, W, aos=aos)
+        # t0 / dt are read on the device (EVK_AUTO_SPAN): no host round trip before the launch
+        grid = _voxel_device(None, None, None, None, 0.0, 1.0, B, H, W, flags=_lib.AUTO_SPAN, aos=aos)
+    elif ts_t.is_cuda and ts_t.dtype == torch.float32 and ts_t.dim() == 1:
+        grid = _voxel_device(E.coords_f32(xs, dev), E.coords_f32(ys, dev), ts_t.contiguous(), E.weights_f32(ps_t, dev),
+                             0.0, 1.0, B, H, W, flags=_lib.AUTO_SPAN)
     else:
         t, t0, dt = _times_f32(ts, dev)
         grid = _voxel_device(E.coords_f32(xs, dev), E.coords_f32(ys, dev), t, E.weights_f32(ps_t, dev),
@@ -138,10 +139,15 @@ def events_to_neg_pos_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(1
     dev = E.compute_device(xs, ys, ts, ps)
     H, W, B = int(sensor_size[0]), int(sensor_size[1]), int(B)
     with torch.cuda.device(dev):
-        t, t0, dt = _times_f32(ts, dev)
+        ts_t = E.as_tensor(ts)
+        flags = E.variant_flag()
+        if ts_t.is_cuda and ts_t.dtype == torch.float32 and ts_t.dim() == 1:
+            t, t0, dt = ts_t.contiguous(), 0.0, 1.0
+            flags |= _lib.AUTO_SPAN       # first / last timestamp read on the device
+        else:
+            t, t0, dt = _times_f32(ts, dev)
         x, y, p = E.coords_f32(xs, dev), E.coords_f32(ys, dev), E.weights_f32(ps, dev)
         out = torch.empty((2, B, H, W), dtype=torch.float32, device=dev)
-        flags = E.variant_flag()
         ws = _lib.scratch("voxel_ws", 2 * L.evk_voxel_workspace_bytes(B, H, W, flags), dev)
         oob = _lib.oob_counter(dev)
         _lib.check(L.evk_voxel_negpos_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), x.shape[0], t0, dt, B, H, W,

@@ -45,6 +45,7 @@ extern "C" {
 #define EVK_ACCUMULATE 0x1u   /* add into `out` instead of overwriting it */
 #define EVK_BILINEAR 0x2u     /* spatial 4-tap bilinear splat instead of nearest (truncate) */
 #define EVK_CLIP 0x4u         /* events_to_image_torch(clip_out_of_range=True) semantics */
+#define EVK_AUTO_SPAN 0x200000u    /* voxel: ignore the t0/dt arguments, take t[0] and t[n-1]-t[0] on the device */
 #define EVK_WINDOW_PAIRS 0x100000u /* evk_voxel_windows_f32: offsets are (start,end) pairs, 2*n_windows entries */
 #define EVK_NEGPOS_TRUTHY 0x8u /* neg/pos split on numpy truthiness (p != 0) instead of p > 0 */
 /* kernel variant selection, bits 8..11 (0 = pick automatically) */
