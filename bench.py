@@ -452,6 +452,34 @@ def secondary_metrics(L, _lib, device, peak):
                                 "iter_per_s_extrapolated_to_workload": 1.0 / (el * n / m)}
     except Exception as e:  # pragma: no cover
         out["cmax_cpu_port"] = {"error": repr(e)}
+    # the optimiser's view: variance_objective through the public API (numpy f64 in, python floats out),
+    # the way scipy's BFGS calls it (events_cmax.py:341-345); each call is a new parameter point
+    try:
+        from event_utils_b200.contrast_max.objectives import variance_objective
+        from event_utils_b200.contrast_max.warps import linvel_warp
+        from oracle import ref_port
+        m = 1_000_000
+        xs, ys, ts, ps = (a[:: n // m][:m].cpu().numpy() for a in (x, y, t, p))
+        obj, warp = variance_objective(), linvel_warp()
+        args = (xs, ys, ts, ps, warp, (180, 240), 1.0)
+        obj.evaluate_function((40.0, -20.0), *args)
+        k = 200
+        s = time.perf_counter()
+        for i in range(k):
+            prm = (40.0 + 0.01 * i, -20.0)
+            obj.evaluate_function(prm, *args)
+            obj.evaluate_gradient(prm, *args)
+        el = (time.perf_counter() - s) / k
+        out["cmax_api_1M"] = {"iter_per_s": 1.0 / el, "events": m,
+                              "what": "evaluate_function + evaluate_gradient per new parameter point through the python API "
+                                      "(device-cached events, one fused launch, result read back)"}
+        best_torch_threads(lambda: ref_port.cmax_fg_cpu((45.0, -20.0), xs[:100000], ys[:100000], ts[:100000], ps[:100000]),
+                           thread_candidates())
+        s = time.perf_counter()
+        ref_port.cmax_fg_cpu((45.0, -20.0), xs, ys, ts, ps)
+        out["cmax_api_1M"]["cpu_port_iter_per_s"] = 1.0 / (time.perf_counter() - s)
+    except Exception as e:  # pragma: no cover
+        out["cmax_api_1M"] = {"error": repr(e)}
     del x, y, t, p
     torch.cuda.empty_cache()
     # event image on a hot-spot (Zipf) stream vs a uniform one (BASELINE configs[3] shape: 1280x720)

@@ -76,7 +76,8 @@ def clear_cache():
 
 
 def _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, want_grad, use_polarity,
-                  first=0, last=None, p_scale=1.0, want_images=False, channel_mix=True):
+                  first=0, last=None, p_scale=1.0, want_images=False, channel_mix=True,
+                  objective=_lib.OBJ_VARIANCE, obj_param=0.0):
     """One fused evaluation on events [first:last) of the cached device copy.
     Returns (result[8] as numpy f64, iwe or None, d_iwe or None)."""
     L = _lib.lib()
@@ -93,7 +94,7 @@ def _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, want_grad, use_p
     with torch.cuda.device(dev):
         ws_bytes = L.evk_cmax_workspace_bytes(Hs, Ws)
         ws = _lib.scratch("cmax_ws", ws_bytes, dev)
-        result = torch.empty(8, dtype=torch.float64, device=dev)
+        result = torch.zeros(12, dtype=torch.float64, device=dev)
         iwe = torch.empty((Hs + 1, Ws + 1), dtype=torch.float32, device=dev) if want_images else None
         d_iwe = torch.empty((2, Hs + 1, Ws + 1), dtype=torch.float32, device=dev) if (want_images and want_grad) else None
         flags = (_lib.CMAX_WANT_GRAD if want_grad else 0) | (0 if use_polarity else _lib.CMAX_ABS_POLARITY) \
@@ -103,29 +104,29 @@ def _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, want_grad, use_p
         if ev.mode == "f64":
             t_ref = float(ev.t[last - 1].item()) if last != n_all else ev.t_last
             off = first * 8
-            _lib.check(L.evk_cmax_linvel_variance_f64(
+            _lib.check(L.evk_cmax_linvel_objective_f64(
                 ev.x.data_ptr() + off, ev.y.data_ptr() + off, ev.t.data_ptr() + off, ev.p.data_ptr() + off, n,
                 float(p_scale), float(params[0]), float(params[1]), t_ref, int(img_size[0]), int(img_size[1]),
-                Hs, Ws, sigma, flags, _lib.ptr(result), _lib.ptr(iwe), _lib.ptr(d_iwe), _lib.ptr(ws), ws.numel(),
-                _lib.stream()))
+                Hs, Ws, sigma, flags, int(objective), float(obj_param), _lib.ptr(result), _lib.ptr(iwe), _lib.ptr(d_iwe),
+                _lib.ptr(ws), ws.numel(), _lib.stream()))
         else:
             if last != n_all:
                 raise NotImplementedError("f32 fast mode stores t relative to the last event; "
                                           "slicing the tail (adaptive_lifespan) needs precision='f64'")
             off = first * 4
-            _lib.check(L.evk_cmax_linvel_variance_f32(
+            _lib.check(L.evk_cmax_linvel_objective_f32(
                 ev.x.data_ptr() + off, ev.y.data_ptr() + off, ev.t.data_ptr() + off, ev.p.data_ptr() + off, n,
                 float(p_scale), float(params[0]), float(params[1]), int(img_size[0]), int(img_size[1]),
-                Hs, Ws, sigma, flags, _lib.ptr(result), _lib.ptr(iwe), _lib.ptr(d_iwe), _lib.ptr(ws), ws.numel(),
-                _lib.stream()))
+                Hs, Ws, sigma, flags, int(objective), float(obj_param), _lib.ptr(result), _lib.ptr(iwe), _lib.ptr(d_iwe),
+                _lib.ptr(ws), ws.numel(), _lib.stream()))
         res = result.cpu().numpy()
         if res[4] != 0:
             raise IndexError("%d warped events index outside the IWE canvas %s" % (int(res[4]), (Hs + 1, Ws + 1)))
         return res, (iwe.cpu().numpy() if iwe is not None else None), (d_iwe.cpu().numpy() if d_iwe is not None else None)
 
 
-def _objective_of_images(iwe, d_iwe, blur_sigma, want_grad):
-    """variance objective (+ gradient) of precomputed images, on the GPU (evk_variance_objective_f32)."""
+def _objective_of_images(iwe, d_iwe, blur_sigma, want_grad, objective=_lib.OBJ_VARIANCE, obj_param=0.0):
+    """objective (+ gradient) of precomputed images, on the GPU (evk_iwe_objective_f32)."""
     L = _lib.lib()
     dev = E.compute_device()
     iwe = np.ascontiguousarray(iwe, dtype=np.float32)
@@ -133,11 +134,11 @@ def _objective_of_images(iwe, d_iwe, blur_sigma, want_grad):
         a = torch.from_numpy(iwe).to(dev)
         d = torch.from_numpy(np.ascontiguousarray(d_iwe, dtype=np.float32)).to(dev) if d_iwe is not None else None
         ws = _lib.scratch("cmax_ws", L.evk_cmax_workspace_bytes(iwe.shape[0] - 1, iwe.shape[1] - 1), dev)
-        result = torch.empty(8, dtype=torch.float64, device=dev)
+        result = torch.zeros(12, dtype=torch.float64, device=dev)
         flags = _lib.CMAX_WANT_GRAD if (want_grad and d is not None) else 0
-        _lib.check(L.evk_variance_objective_f32(_lib.ptr(a), _lib.ptr(d), iwe.shape[0], iwe.shape[1],
-                                                float(blur_sigma), flags, _lib.ptr(result), _lib.ptr(ws),
-                                                ws.numel(), _lib.stream()))
+        _lib.check(L.evk_iwe_objective_f32(_lib.ptr(a), _lib.ptr(d), iwe.shape[0], iwe.shape[1], float(blur_sigma), flags,
+                                           int(objective), float(obj_param), _lib.ptr(result), _lib.ptr(ws), ws.numel(),
+                                           _lib.stream()))
         return result.cpu().numpy()
 
 
@@ -293,3 +294,174 @@ class variance_objective(objective_function):
             return np.array([res[1], res[2]])
         _, g = self._evaluate(params, xs, ys, ts, ps, warpfunc, img_size, blur_sigma)
         return g.copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's other objective functions (objectives.py:266-596) on the same fused event pass
+# ---------------------------------------------------------------------------------------------
+class _fused_objective(objective_function):
+    """Shared machinery: one fused GPU evaluation (event pass + image-space tail) per parameter
+    point, memoised so that evaluate_function / evaluate_gradient at the same point cost one
+    launch.  Subclasses set `_kind` (an EVK_OBJ_* code) and may override `_param()`."""
+    _kind = _lib.OBJ_VARIANCE
+
+    def _param(self):
+        return 0.0
+
+    def _result(self, params, xs, ys, ts, ps, warpfunc, img_size, blur_sigma, iwe=None, d_iwe=None, want_grad=True):
+        blur_sigma = self.default_blur if blur_sigma is None else blur_sigma
+        if iwe is not None:
+            return _objective_of_images(iwe, d_iwe, blur_sigma, want_grad and d_iwe is not None, self._kind, self._param())
+        key = (tuple(float(v) for v in params), id(xs), id(ys), id(ts), id(ps), len(xs), tuple(img_size),
+               float(blur_sigma), self.use_polarity, precision, self._kind, self._param())
+        memo = getattr(self, "_memo", None)
+        if memo is not None and memo[0] == key:
+            return memo[1]
+        if getattr(warpfunc, "fused_kind", None) == "linvel":
+            res, _, _ = _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, self.has_derivative, self.use_polarity,
+                                      objective=self._kind, obj_param=self._param())
+        else:
+            img, dimg = get_iwe(params, xs, ys, ts, ps, warpfunc, img_size, use_polarity=self.use_polarity,
+                                compute_gradient=self.has_derivative)
+            res = _objective_of_images(img, dimg, blur_sigma, self.has_derivative, self._kind, self._param())
+        self._memo = (key, res)
+        return res
+
+    def evaluate_function(self, params=None, xs=None, ys=None, ts=None, ps=None,
+            warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None):
+        return float(self._result(params, xs, ys, ts, ps, warpfunc, img_size, blur_sigma, iwe=iwe, want_grad=False)[0])
+
+    def evaluate_gradient(self, params=None, xs=None, ys=None, ts=None, ps=None,
+            warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None, d_iwe=None):
+        if not self.has_derivative:
+            return None
+        if iwe is not None and d_iwe is None:
+            iwe = None
+        res = self._result(params, xs, ys, ts, ps, warpfunc, img_size, blur_sigma, iwe=iwe, d_iwe=d_iwe)
+        return np.array([res[1], res[2]])
+
+
+class rms_objective(_fused_objective):
+    """"Root mean squared" objective (objectives.py:266-306).  The reference computes
+    np.linalg.norm(iwe, 2) on the 2-D image, i.e. its SPECTRAL norm (largest singular value), so
+    f = -sigma_max(G*IWE)^2 / npix; f'_k = -2 mean(IWE * (G3d * dIWE)_k).  The event pass and the blur
+    run in the evk kernels; the singular value is one torch.linalg call on the 181x241 device image."""
+    _kind = _lib.OBJ_SOS
+
+    def __init__(self):
+        super().__init__(name="rms", use_polarity=True, has_derivative=True, default_blur=1.0)
+
+    def evaluate_function(self, params=None, xs=None, ys=None, ts=None, ps=None,
+            warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None):
+        blur_sigma = self.default_blur if blur_sigma is None else blur_sigma
+        if iwe is None:
+            iwe, _ = get_iwe(params, xs, ys, ts, ps, warpfunc, img_size, use_polarity=self.use_polarity,
+                             compute_gradient=False)
+        L = _lib.lib()
+        dev = E.compute_device()
+        with torch.cuda.device(dev):
+            a = torch.from_numpy(np.ascontiguousarray(iwe, dtype=np.float32)).to(dev)
+            g, tmp = torch.empty_like(a), torch.empty_like(a)
+            _lib.check(L.evk_gaussian_blur_f32(_lib.ptr(a), a.shape[0], a.shape[1], float(blur_sigma), _lib.ptr(g),
+                                               _lib.ptr(tmp), _lib.stream()))
+            norm = float(torch.linalg.matrix_norm(g.double(), 2))
+        return -(norm * norm) / (iwe.shape[0] * iwe.shape[1])
+
+
+class sos_objective(_fused_objective):
+    """Sum of squares objective (Stoffregen et al., CVPR'19; objectives.py:308-356): f = -mean((G*IWE)^2).
+    The reference's evaluate_gradient calls an undefined `find_lifespan` (objectives.py:345) and raises
+    NameError; the formula it would compute, -mean((G3d*dIWE)_k * 2 IWE), is what is returned here."""
+    _kind = _lib.OBJ_SOS
+
+    def __init__(self, adaptive_lifespan=False, minimum_events=10000):
+        super().__init__(name="sos", use_polarity=True, has_derivative=True, default_blur=1.0,
+                         adaptive_lifespan=adaptive_lifespan, pixel_crossings=5, minimum_events=minimum_events)
+        self.current_num_events = minimum_events
+        self.div = 1
+
+
+class soe_objective(_fused_objective):
+    """Sum of exponentials objective (objectives.py:358-399): f = -mean(exp(G*IWE)), |p| is used."""
+    _kind = _lib.OBJ_SOE
+
+    def __init__(self):
+        super().__init__(name="soe", use_polarity=False, has_derivative=True, default_blur=2.5)
+
+
+class moa_objective(_fused_objective):
+    """Max of accumulations objective (objectives.py:401-429): f = -max(G*IWE); no analytic derivative."""
+    _kind = _lib.OBJ_MOA
+
+    def __init__(self):
+        super().__init__(name="moa", use_polarity=False, has_derivative=False, default_blur=3.0)
+
+    def evaluate_function(self, params=None, xs=None, ys=None, ts=None, ps=None,
+            warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None):
+        return float(self._result(params, xs, ys, ts, ps, warpfunc, img_size, blur_sigma, iwe=iwe, want_grad=False)[0])
+
+
+class isoa_objective(_fused_objective):
+    """Inverse sum of accumulations objective (objectives.py:431-476): f = +#(G*IWE > thresh) (the
+    reference does not negate it), f'_k = -sum((G3d*dIWE)_k [G*IWE > thresh])."""
+    _kind = _lib.OBJ_ISOA
+
+    def __init__(self, thresh=0.5):
+        super().__init__(name="isoa", use_polarity=False, has_derivative=True, default_blur=1.0)
+        self.thresh = thresh
+
+    def _param(self):
+        return float(self.thresh)
+
+
+class sosa_objective(_fused_objective):
+    """Sum of suppressed accumulations objective (objectives.py:478-522): f = -sum(exp(-p G*IWE))."""
+    _kind = _lib.OBJ_SOSA
+
+    def __init__(self, p=3):
+        super().__init__(name="sosa", use_polarity=False, has_derivative=True, default_blur=2.0)
+        self.p = p
+
+    def _param(self):
+        return float(self.p)
+
+
+class r1_objective(_fused_objective):
+    """R1 objective (objectives.py:560-596): SoS and SoSA combined, with the reference's stateful
+    `last_sosa` logic kept literally; no analytic derivative."""
+    _kind = _lib.OBJ_SOSA
+
+    def __init__(self, p=3):
+        super().__init__(name="r1", use_polarity=False, has_derivative=False, default_blur=1.0)
+        self.p = p
+        self.last_sosa = 0
+
+    def _param(self):
+        return float(self.p)
+
+    def evaluate_function(self, params=None, xs=None, ys=None, ts=None, ps=None,
+            warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None):
+        res = self._result(params, xs, ys, ts, ps, warpfunc, img_size, blur_sigma, iwe=iwe, want_grad=False)
+        sos, sosa = float(res[8]), float(res[9])
+        if sosa > self.last_sosa:
+            return -sos
+        self.last_sosa = sosa
+        return -sos * sosa
+
+
+class zhu_timestamp_objective(objective_function):
+    """Squared timestamp images objective (objectives.py:524-558).  In the reference its
+    evaluate_function calls the undefined `events_to_zhu_timestamp_image` and raises NameError
+    (SURVEY Appendix B11); there is therefore no behaviour to be faithful to.  The timestamp images
+    themselves are available: representations.image.events_to_timestamp_image(_torch)."""
+    def __init__(self):
+        super().__init__(name="zhu", use_polarity=True, has_derivative=False, default_blur=2.0)
+
+    def evaluate_function(self, params=None, xs=None, ys=None, ts=None, ps=None,
+            warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None):
+        raise NotImplementedError("zhu_timestamp_objective is undefined in the reference "
+                                  "(objectives.py:545 calls a function that does not exist)")
+
+    def evaluate_gradient(self, params=None, xs=None, ys=None, ts=None, ps=None,
+            warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None, d_iwe=None):
+        return None

@@ -30,6 +30,7 @@
 //     (objectives.py:253), mixing the two gradient components by [[a,b],[b,a]]; applied to the
 //     two scalars at the end (host supplies a,b).
 #include <math.h>
+#include <string.h>
 
 #include "evk_common.cuh"
 
@@ -343,8 +344,150 @@ __global__ void cmax_final_kernel(const double *sums, const unsigned long long *
     result[7] = g1;
 }
 
+// ---- generic objective tail (the reference's other objective functions, objectives.py:266-596) ---
+// All of them are  f = reduce(phi(G))  with G = G_sigma * IWE and  g_k = -c * sum( w * (G3d * dIWE)_k )
+// for a per-pixel weight image w.  The reflect Gaussian is self-adjoint, so sum(w * G(D_k)) ==
+// sum(G(w) * D_k): ONE more blur (of w) replaces the reference's blur of the (2,H,W) stack.
+//   SOS / RMS (objectives.py:266-357)  f = -mean(G^2)          w = 2*IWE (un-blurred), c = 1/P
+//   SOE  (:358-400)                    f = -mean(exp(G))       w = exp(G),             c = 1/P
+//   MOA  (:401-430)                    f = -max(G)             no gradient
+//   ISOA (:431-477)                    f = +#(G > thresh)      w = [G > thresh],       c = 1
+//   SOSA (:478-523)                    f = -sum(exp(-p G))     w = -p exp(-p G),       c = 1
+enum { OBJ_VARIANCE = 0, OBJ_SOS = 1, OBJ_SOE = 2, OBJ_MOA = 3, OBJ_ISOA = 4, OBJ_SOSA = 5 };
+
+__device__ __forceinline__ unsigned encode_ordered(float f)
+{
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float decode_ordered(unsigned u)
+{
+    const unsigned b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+// axis-1 blur, result stored (the variance path only needs its sums and does not store it)
+__global__ void __launch_bounds__(256) cmax_blur_axis1_store_kernel(const float *__restrict__ tmp, const float *__restrict__ I,
+                                                                    int Hc, int Wc, const BlurTaps taps, int do_blur,
+                                                                    float *__restrict__ G)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= Hc * Wc) return;
+    if (!do_blur) { G[i] = I[i]; return; }
+    const int y = i / Wc, x = i - y * Wc;
+    const float *row = tmp + y * Wc;
+    double acc = (double)row[x] * taps.w[0];
+    for (int k = 1; k <= taps.r; ++k)
+        acc += ((double)row[reflect_idx(x - k, Wc)] + (double)row[reflect_idx(x + k, Wc)]) * taps.w[k];
+    G[i] = (float)acc;
+}
+
+// gsums: 0 sum(G^2)  1 sum(exp(G))  2 sum(exp(-p G))  3 #(G > thresh)  4 sum(G)  5 sum(Gw*D0)  6 sum(Gw*D1)
+__global__ void __launch_bounds__(256) cmax_obj_reduce_kernel(const float *__restrict__ G, const float *__restrict__ I, int npix,
+                                                              int kind, double param, double *gsums, unsigned *gmax,
+                                                              double *__restrict__ w)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    double g2 = 0.0, ge = 0.0, ga = 0.0, gc = 0.0, g1 = 0.0;
+    float mx = -FLT_MAX;
+    if (i < npix) {
+        const float g = G[i];
+        const double gd = (double)g;
+        g1 = gd;
+        g2 = (double)(g * g);                           // np.mean(iwe*iwe): f32 product
+        if (kind == OBJ_SOE) ge = exp(gd);              // np.exp(iwe.astype(np.double))
+        if (kind == OBJ_SOSA) ga = exp(-param * gd);    // np.exp(-p*iwe.astype(np.double))
+        if (kind == OBJ_ISOA) gc = (g > (float)param) ? 1.0 : 0.0;
+        mx = g;
+        double wi = 0.0;
+        if (kind == OBJ_SOS) wi = (double)(I[i] * 2.0f);                                  // (iwe*2.0), un-blurred IWE
+        else if (kind == OBJ_SOE) wi = ge;
+        else if (kind == OBJ_ISOA) wi = gc;
+        else if (kind == OBJ_SOSA) wi = -param * exp((double)(float)(-param * gd));       // exp((-p*iwe).astype(double)): f32 product first
+        w[i] = wi;
+    }
+    block_add(g2, gsums + 0);
+    if (kind == OBJ_SOE) block_add(ge, gsums + 1);
+    if (kind == OBJ_SOSA) block_add(ga, gsums + 2);
+    if (kind == OBJ_ISOA) block_add(gc, gsums + 3);
+    block_add(g1, gsums + 4);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(gmax, encode_ordered(mx));
+}
+
+__global__ void __launch_bounds__(256) cmax_blur_d_axis0_kernel(const double *__restrict__ w, double *__restrict__ wt, int Hc,
+                                                                int Wc, const BlurTaps taps)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= Hc * Wc) return;
+    const int y = i / Wc, x = i - y * Wc;
+    double acc = w[i] * taps.w[0];
+    for (int k = 1; k <= taps.r; ++k) acc += (w[reflect_idx(y - k, Hc) * Wc + x] + w[reflect_idx(y + k, Hc) * Wc + x]) * taps.w[k];
+    wt[i] = acc;
+}
+
+__global__ void __launch_bounds__(256) cmax_blur_d_axis1_dot_kernel(const double *__restrict__ wt, const double *__restrict__ w,
+                                                                    const float *__restrict__ D0, const float *__restrict__ D1,
+                                                                    int Hc, int Wc, const BlurTaps taps, int do_blur, double *gsums)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    double a = 0.0, b = 0.0;
+    if (i < Hc * Wc) {
+        double gw;
+        if (do_blur) {
+            const int y = i / Wc, x = i - y * Wc;
+            const double *row = wt + y * Wc;
+            gw = row[x] * taps.w[0];
+            for (int k = 1; k <= taps.r; ++k) gw += (row[reflect_idx(x - k, Wc)] + row[reflect_idx(x + k, Wc)]) * taps.w[k];
+        } else {
+            gw = w[i];
+        }
+        a = gw * (double)D0[i];
+        b = gw * (double)D1[i];
+    }
+    block_add(a, gsums + 5);
+    block_add(b, gsums + 6);
+}
+
+// result: [0]=f [1],[2]=g [3]=sum(IWE) [4]=oob events [5]=var or aux [6],[7]=un-mixed gradient
+//         [8]=mean(G^2) [9]=sum(exp(-p G)) [10]=max(G) [11]=#(G>thresh)
+__global__ void cmax_obj_final_kernel(int kind, const double *gsums, const unsigned *gmax, const double *sums,
+                                      const unsigned long long *oob, int npix, double mix_a, double mix_b, int want_grad,
+                                      double *result)
+{
+    const double P = (double)npix;
+    double f = 0.0, c = 0.0;
+    const double mx = (double)decode_ordered(*gmax);
+    if (kind == OBJ_SOS) { f = -gsums[0] / P; c = 1.0 / P; }
+    else if (kind == OBJ_SOE) { f = -gsums[1] / P; c = 1.0 / P; }
+    else if (kind == OBJ_MOA) { f = -mx; c = 0.0; }
+    else if (kind == OBJ_ISOA) { f = gsums[3]; c = 1.0; }
+    else if (kind == OBJ_SOSA) { f = -gsums[2]; c = 1.0; }
+    const double u0 = -c * gsums[5], u1 = -c * gsums[6];
+    const bool grad = want_grad && kind != OBJ_MOA;
+    result[0] = f;
+    result[1] = grad ? (mix_a * u0 + mix_b * u1) : 0.0;
+    result[2] = grad ? (mix_b * u0 + mix_a * u1) : 0.0;
+    result[3] = sums[0];
+    result[4] = (double)(*oob);
+    result[5] = gsums[4] / P;
+    result[6] = u0;
+    result[7] = u1;
+    result[8] = gsums[0] / P;
+    result[9] = gsums[2];
+    result[10] = mx;
+    result[11] = gsums[3];
+}
+
 struct CmaxWorkspace {
-    float *acc, *I, *D0, *D1, *tmp;
+    float *acc, *I, *D0, *D1, *tmp, *G;
+    double *w, *wt;             // generic objectives: per-pixel weight image and its axis-0 blur
+    double *gsums;              // 8 doubles (generic objectives)
+    unsigned *gmax;             // order-preserving encoding of max(G)
     double *sums;               // 8 doubles
     unsigned long long *oob;    // 1
 };
@@ -362,9 +505,18 @@ static size_t carve(void *base, int Hs, int Ws, CmaxWorkspace *ws)
     float *D0 = (float *)take(npix * sizeof(float));
     float *D1 = (float *)take(npix * sizeof(float));
     float *tmp = (float *)take(npix * sizeof(float));
+    float *G = (float *)take(npix * sizeof(float));
+    double *w = (double *)take(npix * sizeof(double));
+    double *wt = (double *)take(npix * sizeof(double));
+    // the four small counters below are contiguous (256-byte slots) and zeroed by one memset
+    double *gsums = (double *)take(8 * sizeof(double));
+    unsigned *gmax = (unsigned *)take(sizeof(unsigned));
     double *sums = (double *)take(8 * sizeof(double));
     unsigned long long *oob = (unsigned long long *)take(sizeof(unsigned long long));
-    if (ws) { ws->acc = acc; ws->I = I; ws->D0 = D0; ws->D1 = D1; ws->tmp = tmp; ws->sums = sums; ws->oob = oob; }
+    if (ws) {
+        ws->acc = acc; ws->I = I; ws->D0 = D0; ws->D1 = D1; ws->tmp = tmp; ws->G = G; ws->w = w; ws->wt = wt;
+        ws->gsums = gsums; ws->gmax = gmax; ws->sums = sums; ws->oob = oob;
+    }
     return off;
 }
 
@@ -393,9 +545,45 @@ static int make_taps(double sigma, BlurTaps *t)
     return EVK_OK;
 }
 
+// image-space tail shared by the event entry points and the precomputed-image entry point
+static int launch_tail(const CmaxWorkspace &ws, int Hc, int Wc, double sigma, unsigned flags, int objective, double obj_param,
+                       bool grad, double *result, cudaStream_t st)
+{
+    const int npix = Hc * Wc;
+    BlurTaps taps{};
+    double mix_a = 1.0, mix_b = 0.0;
+    const int do_blur = sigma > 0.0;
+    if (do_blur) {
+        int rc = make_taps(sigma, &taps);
+        if (rc) return rc;
+        if (!(flags & EVK_CMAX_NO_CHANNEL_MIX)) mix_coeffs(taps, &mix_a, &mix_b);
+    }
+    const int g = (npix + 255) / 256;
+    if (do_blur) { prof_count(1); cmax_blur_axis0_kernel<<<g, 256, 0, st>>>(ws.I, ws.tmp, Hc, Wc, taps); }
+    if (objective == OBJ_VARIANCE) {
+        prof_count(2);
+        cmax_blur_axis1_sums_kernel<<<g, 256, 0, st>>>(ws.tmp, ws.I, ws.D0, ws.D1, Hc, Wc, taps, do_blur, ws.sums);
+        cmax_final_kernel<<<1, 1, 0, st>>>(ws.sums, ws.oob, npix, mix_a, mix_b, grad ? 1 : 0, result);
+    } else {
+        if (objective < OBJ_SOS || objective > OBJ_SOSA) { set_error("evk_cmax: unknown objective %d", objective); return EVK_E_ARG; }
+        const bool g_needed = grad && objective != OBJ_MOA;
+        prof_count(3);
+        cmax_blur_axis1_store_kernel<<<g, 256, 0, st>>>(ws.tmp, ws.I, Hc, Wc, taps, do_blur, ws.G);
+        cmax_obj_reduce_kernel<<<g, 256, 0, st>>>(ws.G, ws.I, npix, objective, obj_param, ws.gsums, ws.gmax, ws.w);
+        if (g_needed) {
+            prof_count(do_blur ? 2 : 1);
+            if (do_blur) cmax_blur_d_axis0_kernel<<<g, 256, 0, st>>>(ws.w, ws.wt, Hc, Wc, taps);
+            cmax_blur_d_axis1_dot_kernel<<<g, 256, 0, st>>>(ws.wt, ws.w, ws.D0, ws.D1, Hc, Wc, taps, do_blur, ws.gsums);
+        }
+        cmax_obj_final_kernel<<<1, 1, 0, st>>>(objective, ws.gsums, ws.gmax, ws.sums, ws.oob, npix, mix_a, mix_b, g_needed ? 1 : 0, result);
+    }
+    EVK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
 template <int WARP>
-static int run_cmax(CmaxArgs A, double sigma, unsigned flags, double *result, float *iwe_out, float *diwe_out,
-                    void *workspace, size_t workspace_bytes, cudaStream_t st)
+static int run_cmax(CmaxArgs A, double sigma, unsigned flags, int objective, double obj_param, double *result,
+                    float *iwe_out, float *diwe_out, void *workspace, size_t workspace_bytes, cudaStream_t st)
 {
     const int Hs = A.Hc - 1, Ws = A.Wc - 1;
     if (A.n < 0 || Hs < 1 || Ws < 1 || !result || !workspace) { set_error("evk_cmax: bad arguments"); return EVK_E_ARG; }
@@ -412,30 +600,17 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, double *result, fl
     A.replicas = R;
     A.acc = ws.acc;
     A.oob = ws.oob;
-    BlurTaps taps{};
-    double mix_a = 1.0, mix_b = 0.0;
-    const int do_blur = sigma > 0.0;
-    if (do_blur) {
-        int rc = make_taps(sigma, &taps);
-        if (rc) return rc;
-        if (!(flags & EVK_CMAX_NO_CHANNEL_MIX)) mix_coeffs(taps, &mix_a, &mix_b);
-    }
     EVK_CUDA(cudaMemsetAsync(ws.acc, 0, (size_t)R * npix * kBlockFloats * sizeof(float), st));
-    EVK_CUDA(cudaMemsetAsync(ws.sums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.sums), st));  // sums + oob are adjacent
+    EVK_CUDA(cudaMemsetAsync(ws.gsums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.gsums), st));  // gsums, gmax, sums, oob are adjacent
     if (A.n > 0) {
         ProfScope prof(st);
         prof_count(1);
         if (grad) cmax_scatter_kernel<WARP, true><<<grid_for(cmax_scatter_kernel<WARP, true>, 256, A.n, 256 * 4), 256, 0, st>>>(A);
         else cmax_scatter_kernel<WARP, false><<<grid_for(cmax_scatter_kernel<WARP, false>, 256, A.n, 256 * 4), 256, 0, st>>>(A);
     }
-    prof_count(do_blur ? 4 : 3);
-    const int g = (npix + 255) / 256;
-    cmax_gather_kernel<<<g, 256, 0, st>>>(ws.acc, R, A.Hc, A.Wc, ws.I, ws.D0, ws.D1, iwe_out, diwe_out, ws.sums);
-    if (do_blur) cmax_blur_axis0_kernel<<<g, 256, 0, st>>>(ws.I, ws.tmp, A.Hc, A.Wc, taps);
-    cmax_blur_axis1_sums_kernel<<<g, 256, 0, st>>>(ws.tmp, ws.I, ws.D0, ws.D1, A.Hc, A.Wc, taps, do_blur, ws.sums);
-    cmax_final_kernel<<<1, 1, 0, st>>>(ws.sums, ws.oob, npix, mix_a, mix_b, grad ? 1 : 0, result);
-    EVK_CUDA(cudaGetLastError());
-    return EVK_OK;
+    prof_count(1);
+    cmax_gather_kernel<<<(npix + 255) / 256, 256, 0, st>>>(ws.acc, R, A.Hc, A.Wc, ws.I, ws.D0, ws.D1, iwe_out, diwe_out, ws.sums);
+    return launch_tail(ws, A.Hc, A.Wc, sigma, flags, objective, obj_param, grad, result, st);
 }
 
 // precomputed planar iwe / diwe -> the planar working images + their sums (the block accumulator is
@@ -466,36 +641,52 @@ size_t evk_cmax_workspace_bytes(int Hs, int Ws)
     return evk::carve(nullptr, Hs, Ws, nullptr);
 }
 
-int evk_cmax_linvel_variance_f64(const double *x, const double *y, const double *t, const double *p, int64_t n,
-                                 double p_scale, double vx, double vy, double t_ref, int Hm, int Wm, int Hs, int Ws,
-                                 double sigma,
-                                 unsigned flags, double *result, float *iwe_out, float *diwe_out, void *workspace,
-                                 size_t workspace_bytes, void *stream)
+int evk_cmax_linvel_objective_f64(const double *x, const double *y, const double *t, const double *p, int64_t n,
+                                  double p_scale, double vx, double vy, double t_ref, int Hm, int Wm, int Hs, int Ws,
+                                  double sigma, unsigned flags, int objective, double obj_param, double *result,
+                                  float *iwe_out, float *diwe_out, void *workspace, size_t workspace_bytes, void *stream)
 {
     using namespace evk;
-    if (n > 0 && (!x || !y || !t || !p)) { set_error("evk_cmax_linvel_variance_f64: null event array"); return EVK_E_ARG; }
+    if (n > 0 && (!x || !y || !t || !p)) { set_error("evk_cmax_linvel_objective_f64: null event array"); return EVK_E_ARG; }
     CmaxArgs A{};
     A.x = x; A.y = y; A.t = t; A.p = p; A.n = n;
     A.vx = vx; A.vy = vy; A.t_ref = t_ref; A.p_scale = p_scale;
     A.Hm = Hm; A.Wm = Wm; A.Hc = Hs + 1; A.Wc = Ws + 1;
-    return run_cmax<WARP_LINVEL_F64>(A, sigma, flags, result, iwe_out, diwe_out, workspace, workspace_bytes,
-                                     static_cast<cudaStream_t>(stream));
+    return run_cmax<WARP_LINVEL_F64>(A, sigma, flags, objective, obj_param, result, iwe_out, diwe_out, workspace,
+                                     workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
-int evk_cmax_linvel_variance_f32(const float *x, const float *y, const float *t_rel, const float *p, int64_t n,
-                                 float p_scale, float vx, float vy, int Hm, int Wm, int Hs, int Ws, double sigma,
-                                 unsigned flags,
-                                 double *result, float *iwe_out, float *diwe_out, void *workspace,
-                                 size_t workspace_bytes, void *stream)
+int evk_cmax_linvel_objective_f32(const float *x, const float *y, const float *t_rel, const float *p, int64_t n,
+                                  float p_scale, float vx, float vy, int Hm, int Wm, int Hs, int Ws, double sigma,
+                                  unsigned flags, int objective, double obj_param, double *result, float *iwe_out,
+                                  float *diwe_out, void *workspace, size_t workspace_bytes, void *stream)
 {
     using namespace evk;
-    if (n > 0 && (!x || !y || !t_rel || !p)) { set_error("evk_cmax_linvel_variance_f32: null event array"); return EVK_E_ARG; }
+    if (n > 0 && (!x || !y || !t_rel || !p)) { set_error("evk_cmax_linvel_objective_f32: null event array"); return EVK_E_ARG; }
     CmaxArgs A{};
     A.x = x; A.y = y; A.t = t_rel; A.p = p; A.n = n;
     A.vx = vx; A.vy = vy; A.t_ref = 0.0; A.p_scale = p_scale;
     A.Hm = Hm; A.Wm = Wm; A.Hc = Hs + 1; A.Wc = Ws + 1;
-    return run_cmax<WARP_LINVEL_F32>(A, sigma, flags, result, iwe_out, diwe_out, workspace, workspace_bytes,
-                                     static_cast<cudaStream_t>(stream));
+    return run_cmax<WARP_LINVEL_F32>(A, sigma, flags, objective, obj_param, result, iwe_out, diwe_out, workspace,
+                                     workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int evk_cmax_linvel_variance_f64(const double *x, const double *y, const double *t, const double *p, int64_t n,
+                                 double p_scale, double vx, double vy, double t_ref, int Hm, int Wm, int Hs, int Ws,
+                                 double sigma, unsigned flags, double *result, float *iwe_out, float *diwe_out,
+                                 void *workspace, size_t workspace_bytes, void *stream)
+{
+    return evk_cmax_linvel_objective_f64(x, y, t, p, n, p_scale, vx, vy, t_ref, Hm, Wm, Hs, Ws, sigma, flags, 0, 0.0, result,
+                                         iwe_out, diwe_out, workspace, workspace_bytes, stream);
+}
+
+int evk_cmax_linvel_variance_f32(const float *x, const float *y, const float *t_rel, const float *p, int64_t n,
+                                 float p_scale, float vx, float vy, int Hm, int Wm, int Hs, int Ws, double sigma,
+                                 unsigned flags, double *result, float *iwe_out, float *diwe_out, void *workspace,
+                                 size_t workspace_bytes, void *stream)
+{
+    return evk_cmax_linvel_objective_f32(x, y, t_rel, p, n, p_scale, vx, vy, Hm, Wm, Hs, Ws, sigma, flags, 0, 0.0, result,
+                                         iwe_out, diwe_out, workspace, workspace_bytes, stream);
 }
 
 int evk_cmax_flow_variance_f32(const float *x, const float *y, const float *t, const float *p, int64_t n,
@@ -508,36 +699,49 @@ int evk_cmax_flow_variance_f32(const float *x, const float *y, const float *t, c
     A.x = x; A.y = y; A.t = t; A.p = p; A.n = n;
     A.flow = flow; A.flow_t0 = t0; A.p_scale = 1.0;
     A.Hm = Hs; A.Wm = Ws; A.Hc = Hs + 1; A.Wc = Ws + 1;
-    return run_cmax<WARP_FLOW_F32>(A, sigma, flags, result, iwe_out, nullptr, workspace, workspace_bytes,
+    return run_cmax<WARP_FLOW_F32>(A, sigma, flags, 0, 0.0, result, iwe_out, nullptr, workspace, workspace_bytes,
                                    static_cast<cudaStream_t>(stream));
+}
+
+int evk_iwe_objective_f32(const float *iwe, const float *diwe, int Hc, int Wc, double sigma, unsigned flags, int objective,
+                          double obj_param, double *result, void *workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace evk;
+    if (!iwe || !result || !workspace || Hc < 2 || Wc < 2) { set_error("evk_iwe_objective_f32: bad arguments"); return EVK_E_ARG; }
+    if (((uintptr_t)workspace & 255) != 0) { set_error("evk_iwe_objective_f32: workspace must be 256-byte aligned"); return EVK_E_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CmaxWorkspace ws;
+    const size_t need = carve(workspace, Hc - 1, Wc - 1, &ws);
+    if (workspace_bytes < need) { set_error("evk_iwe_objective_f32: workspace of %zu bytes required", need); return EVK_E_WORKSPACE; }
+    const int npix = Hc * Wc;
+    const bool grad = (flags & EVK_CMAX_WANT_GRAD) != 0 && diwe != nullptr;
+    EVK_CUDA(cudaMemsetAsync(ws.gsums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.gsums), st));
+    prof_count(1);
+    cmax_planar_kernel<<<(npix + 255) / 256, 256, 0, st>>>(iwe, grad ? diwe : nullptr, npix, ws.I, ws.D0, ws.D1, ws.sums);
+    return launch_tail(ws, Hc, Wc, sigma, flags, objective, obj_param, grad, result, st);
 }
 
 int evk_variance_objective_f32(const float *iwe, const float *diwe, int Hc, int Wc, double sigma, unsigned flags,
                                double *result, void *workspace, size_t workspace_bytes, void *stream)
 {
+    return evk_iwe_objective_f32(iwe, diwe, Hc, Wc, sigma, flags, 0, 0.0, result, workspace, workspace_bytes, stream);
+}
+
+int evk_gaussian_blur_f32(const float *img, int H, int W, double sigma, float *out, float *tmp, void *stream)
+{
     using namespace evk;
-    if (!iwe || !result || !workspace || Hc < 2 || Wc < 2) { set_error("evk_variance_objective_f32: bad arguments"); return EVK_E_ARG; }
-    if (((uintptr_t)workspace & 255) != 0) { set_error("evk_variance_objective_f32: workspace must be 256-byte aligned"); return EVK_E_ARG; }
+    if (!img || !out || !tmp || H < 1 || W < 1) { set_error("evk_gaussian_blur_f32: bad arguments"); return EVK_E_ARG; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CmaxWorkspace ws;
-    const size_t need = carve(workspace, Hc - 1, Wc - 1, &ws);
-    if (workspace_bytes < need) { set_error("evk_variance_objective_f32: workspace of %zu bytes required", need); return EVK_E_WORKSPACE; }
-    const int npix = Hc * Wc;
-    const bool grad = (flags & EVK_CMAX_WANT_GRAD) != 0 && diwe != nullptr;
     BlurTaps taps{};
-    double mix_a = 1.0, mix_b = 0.0;
     const int do_blur = sigma > 0.0;
     if (do_blur) {
         int rc = make_taps(sigma, &taps);
         if (rc) return rc;
-        if (!(flags & EVK_CMAX_NO_CHANNEL_MIX)) mix_coeffs(taps, &mix_a, &mix_b);
     }
-    EVK_CUDA(cudaMemsetAsync(ws.sums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.sums), st));
-    const int g = (npix + 255) / 256;
-    cmax_planar_kernel<<<g, 256, 0, st>>>(iwe, grad ? diwe : nullptr, npix, ws.I, ws.D0, ws.D1, ws.sums);
-    if (do_blur) cmax_blur_axis0_kernel<<<g, 256, 0, st>>>(ws.I, ws.tmp, Hc, Wc, taps);
-    cmax_blur_axis1_sums_kernel<<<g, 256, 0, st>>>(ws.tmp, ws.I, ws.D0, ws.D1, Hc, Wc, taps, do_blur, ws.sums);
-    cmax_final_kernel<<<1, 1, 0, st>>>(ws.sums, ws.oob, npix, mix_a, mix_b, grad ? 1 : 0, result);
+    const int g = (H * W + 255) / 256;
+    prof_count(do_blur ? 2 : 1);
+    if (do_blur) cmax_blur_axis0_kernel<<<g, 256, 0, st>>>(img, tmp, H, W, taps);
+    cmax_blur_axis1_store_kernel<<<g, 256, 0, st>>>(tmp, img, H, W, taps, do_blur, out);
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

@@ -24,7 +24,6 @@ struct ImageArgs {
     int H, W;  // canvas
     int clip;
     float clipx, clipy;
-    int nqx;  // quads per row (vector variant)
     float *out;
     float *ws;
     unsigned *out_u32;
@@ -32,8 +31,6 @@ struct ImageArgs {
 };
 
 enum { ISINK_SCALAR = 0, ISINK_QUAD = 1, ISINK_WARPAGG = 2 };
-
-static inline int quads_for_cols(int W) { return W <= 1 ? 1 : (W - 1 + 2) / 3; }
 
 // Combine lanes that target the same cell: every lane learns its peers, the lowest peer lane
 // adds the group's sum.  Returns true in the lane that must issue the red, with `v` = group sum.
@@ -284,7 +281,6 @@ int evk_image_f32(const float *x, const float *y, const float *p, int64_t n, int
     A.x = x; A.y = y; A.p = p; A.n = n; A.H = Himg; A.W = Wimg;
     A.clip = (flags & EVK_CLIP) ? 1 : 0; A.clipx = clipx; A.clipy = clipy;
     A.out = out; A.oob = oob;
-    A.nqx = quads_for_cols(Wimg);
     unsigned variant = variant_of(flags);
     // AUTO: large nearest streams take the adaptive hot-spot kernel (it falls back to plain global
     // reductions by itself when the stream is not contended); bilinear keeps the vector-red form.

@@ -218,6 +218,42 @@ int evk_cmax_linvel_variance_f32(const float *x, const float *y, const float *t_
                                  float *diwe_out, void *workspace, size_t workspace_bytes,
                                  void *stream);
 
+/* The reference's other objective functions on the same fused event pass (row f3).  `objective` is
+ * one of EVK_OBJ_*; `obj_param` is the ISOA threshold / the SOSA exponent p.  result: 12 doubles --
+ * [0] f, [1..2] g, [3] sum(IWE), [4] events outside the canvas, [5] mean(G), [6..7] un-mixed gradient,
+ * [8] mean(G^2), [9] sum(exp(-p G)), [10] max(G), [11] #(G > thresh)   (G = blurred IWE).
+ *   EVK_OBJ_VARIANCE  variance_objective  objectives.py:202-264   (result as documented above)
+ *   EVK_OBJ_SOS       sos_ / rms_objective objectives.py:266-357   f = -mean(G^2), g = -mean(2 IWE * G3(dIWE))
+ *   EVK_OBJ_SOE       soe_objective       objectives.py:358-400   f = -mean(exp G), g = -mean(exp(G) G3(dIWE))
+ *   EVK_OBJ_MOA       moa_objective       objectives.py:401-430   f = -max(G), no gradient
+ *   EVK_OBJ_ISOA      isoa_objective      objectives.py:431-477   f = +#(G > thresh), g = -sum([G>thresh] G3(dIWE))
+ *   EVK_OBJ_SOSA      sosa_objective      objectives.py:478-523   f = -sum(exp(-p G)), g = -sum(-p exp(-p G) G3(dIWE)) */
+#define EVK_OBJ_VARIANCE 0
+#define EVK_OBJ_SOS 1
+#define EVK_OBJ_SOE 2
+#define EVK_OBJ_MOA 3
+#define EVK_OBJ_ISOA 4
+#define EVK_OBJ_SOSA 5
+int evk_cmax_linvel_objective_f64(const double *x, const double *y, const double *t, const double *p,
+                                  int64_t n, double p_scale, double vx, double vy, double t_ref,
+                                  int Hm, int Wm, int Hs, int Ws, double sigma, unsigned flags,
+                                  int objective, double obj_param, double *result, float *iwe_out,
+                                  float *diwe_out, void *workspace, size_t workspace_bytes,
+                                  void *stream);
+int evk_cmax_linvel_objective_f32(const float *x, const float *y, const float *t_rel, const float *p,
+                                  int64_t n, float p_scale, float vx, float vy, int Hm, int Wm,
+                                  int Hs, int Ws, double sigma, unsigned flags, int objective,
+                                  double obj_param, double *result, float *iwe_out, float *diwe_out,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+int evk_iwe_objective_f32(const float *iwe, const float *diwe, int Hc, int Wc, double sigma,
+                          unsigned flags, int objective, double obj_param, double *result,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* scipy.ndimage.gaussian_filter(img, sigma) for a 2-D f32 image (truncate=4, mode='reflect', f64 line
+ * accumulation, f32 store after each axis) -- the blur every objective applies (objectives.py:233 ...).
+ * tmp: H*W floats of scratch; out may not alias img. */
+int evk_gaussian_blur_f32(const float *img, int H, int W, double sigma, float *out, float *tmp, void *stream);
+
 /* The objective (and gradient) of a PRECOMPUTED image of warped events, i.e. the iwe= / d_iwe=
  * form of evaluate_function / evaluate_gradient (objectives.py:211-264 with iwe given; used by
  * grid_cmax, events_cmax.py:68-70).  iwe: [Hc][Wc] f32, diwe: [2][Hc][Wc] f32 or NULL. */

@@ -257,3 +257,22 @@ with contextlib.redirect_stdout(io.StringIO()):
     ga = o2.evaluate_gradient((50.0, -30.0), xs, ys, ts, ps, warp, (180, 240), 1.0)
 cases.update(dict(adapt_f=fa, adapt_g=ga, adapt_sidx=o2.s_idx))
 save("cmax", **cases)
+
+# ---- the other objective functions (objectives.py:266-596) on the lattice scene --------------------
+cases = {}
+O = ref.objectives
+objs = {"rms": O.rms_objective(), "sos": O.sos_objective(), "soe": O.soe_objective(), "moa": O.moa_objective(),
+        "isoa": O.isoa_objective(), "sosa": O.sosa_objective(), "r1": O.r1_objective()}
+xs, ys, ts, ps = scenes["lat"]
+for name, o in objs.items():
+    for prm in [(45.0, -20.0), (60.0, -35.0)]:
+        for tag, sigma in (("d", None), ("0", 0.0)):      # default blur of the objective, and no blur
+            f = o.evaluate_function(prm, xs, ys, ts, ps, warp, (180, 240), sigma)
+            try:
+                gr = o.evaluate_gradient(prm, xs, ys, ts, ps, warp, (180, 240), sigma)
+            except (NameError, TypeError):                # sos: undefined find_lifespan; moa: other signature
+                gr = None
+            gr = [np.nan, np.nan] if gr is None else list(gr)
+            cases["%s_%g_%g_%s" % (name, prm[0], prm[1], tag)] = np.array([f] + gr, dtype=np.float64)
+save("objectives", **cases)
+

@@ -160,6 +160,44 @@ def test_bfgs_survives_scipy_calling_convention():
     assert obj.evaluate_function(np.array([60.0, -35.0]), *args) < obj.evaluate_function(x0, *args)
 
 
+def test_other_objectives_against_reference_goldens():
+    """rms / sos / soe / moa / isoa / sosa / r1 (objectives.py:266-596) on the fused event pass."""
+    from event_utils_b200.contrast_max import objectives as O
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    g, c = golden("objectives"), golden("cmax")
+    ev = [c["lat" + k] for k in ("_x", "_y", "_t", "_p")]
+    warp = linvel_warp()
+    make = {"rms": O.rms_objective, "sos": O.sos_objective, "soe": O.soe_objective, "moa": O.moa_objective,
+            "isoa": O.isoa_objective, "sosa": O.sosa_objective, "r1": O.r1_objective}
+    for key in g.files:
+        name, vx, vy, tag = key.split("_")
+        ref = g[key]
+        obj = make[name]()
+        sigma = None if tag == "d" else 0.0
+        f = obj.evaluate_function((float(vx), float(vy)), *ev, warp, (180, 240), sigma)
+        if name == "isoa":
+            assert abs(f - ref[0]) <= 3, (key, f, ref[0])     # a count: pixels within 1 ulp of the threshold may flip
+        else:
+            assert abs(f - ref[0]) <= 1e-5 * abs(ref[0]), (key, f, ref[0])
+        gr = obj.evaluate_gradient((float(vx), float(vy)), *ev, warp, (180, 240), sigma)
+        if name in ("moa", "r1"):
+            assert gr is None and not obj.has_derivative
+        elif name == "sos":
+            assert gr.shape == (2,) and np.isfinite(gr).all()          # the reference raises NameError here
+            rms = g["rms_%s_%s_%s" % (vx, vy, tag)]
+            assert np.abs(gr - rms[1:]).max() <= 1e-5 * np.abs(rms[1:]).max()   # same formula as rms
+        elif name == "isoa":
+            assert np.abs(gr - ref[1:]).max() <= 2e-3 * np.abs(ref[1:]).max() + 1e-3
+        else:
+            assert np.abs(gr - ref[1:]).max() <= 1e-5 * max(np.abs(ref[1:]).max(), 1e-3), (key, gr, ref[1:])
+    with pytest.raises(NotImplementedError):
+        O.zhu_timestamp_objective().evaluate_function((1.0, 1.0), *ev, warp, (180, 240), None)
+    # the optimiser protocol works for them too (the reference's own objects lack pixel_crossings)
+    o = O.sosa_objective()
+    o.iter_update((3.0, 4.0))
+    assert o.lifespan == 1.0
+
+
 def test_flow_objective_c_abi(oracle):
     """evk_cmax_flow_variance_f32 == flow warp + bilinear IWE + variance, composed from the oracle."""
     import torch
