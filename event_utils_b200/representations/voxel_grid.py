@@ -38,7 +38,16 @@ def _voxel_device(x, y, t, p, t0, dt, B, H, W, flags=0, aos=None, out=None):
 def _times_f32(ts, dev):
     """Timestamps as f32 + the two scalars voxel_grid.py:133-134 derives from them.
     Integer timestamps are made relative first (exact), like the reference's int arithmetic."""
+    loader_arrays = isinstance(ts, np.ndarray)
     ts = E.as_tensor(ts).reshape(-1)
+    if ts.dtype == torch.float64 and loader_arrays:
+        # numpy float64 stamps, as the data loaders hold them (hdf5_dataset.py:18-23): the reference
+        # cannot take numpy at all (quirk B4), so this is our extension -- made relative to the first
+        # stamp in float64 BEFORE the cast, because absolute stamps (1.6e9 s + us) do not fit float32
+        t64 = ts.to(dev, non_blocking=True)
+        rel = (t64 - t64[0])
+        dt = np.float32(float(rel[-1].item()))
+        return rel.to(torch.float32).contiguous(), 0.0, float(dt)
     if ts.dtype == torch.float32:
         t = ts.to(dev, non_blocking=True).contiguous()
         first, last = (float(v) for v in torch.stack((ts[0], ts[-1])).tolist())
@@ -82,7 +91,7 @@ def events_to_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240)
     H, W = int(sensor_size[0]), int(sensor_size[1])
     B = int(B)
     ps_t = E.as_tensor(ps)
-    if ps_t.dtype == torch.float64:
+    if ps_t.dtype == torch.float64 and not isinstance(ps, np.ndarray):
         raise RuntimeError("Index put requires the source and destination dtypes match, "
                            "got Float for the destination and Double for the source.")
     dev = E.compute_device(xs, ys, ts, ps)

@@ -130,6 +130,27 @@ def test_host_inputs_pipeline(oracle):
     assert_close_to_max(out.numpy(), oracle.voxel_f32(xi, yi, trel, p, 5, (180, 240), t0=0.0, dt=trel[-1]), 1e-5)
 
 
+def test_data_loader_arrays(oracle):
+    """The arrays DynamicH5Dataset.get_events hands over (hdf5_dataset.py:18-23): int16 coordinates,
+    float64 absolute timestamps, float64 +-1 polarities, all numpy."""
+    from event_utils_b200.representations.voxel_grid import events_to_neg_pos_voxel_torch, events_to_voxel_torch
+    x, y, t, p = make_events(41, 200000, 180, 240)
+    xi, yi = x.astype(np.int16), y.astype(np.int16)
+    t64 = t.astype(np.float64) * 0.25 + 1.6e9        # absolute stamps: not representable in float32
+    p64 = p.astype(np.float64)
+    rel = (t64 - t64[0]).astype(np.float32)
+    ref = oracle.voxel_f32(xi, yi, rel, p, 5, (180, 240), t0=0.0, dt=rel[-1])
+    out = events_to_voxel_torch(xi, yi, t64, p64, 5, sensor_size=(180, 240))
+    assert not out.is_cuda and out.dtype == torch.float32
+    assert_close_to_max(out.numpy(), ref, 1e-5)
+    vp, vn = events_to_neg_pos_voxel_torch(xi, yi, t64, p64, 5, sensor_size=(180, 240))
+    assert_close_to_max((vp - vn).numpy(), ref, 1e-5)
+    # the single all-zero event of BaseVoxelDataset.preprocess_events (base_dataset.py:218-223): dt == 0 -> NaN
+    z = np.zeros(1)
+    out = events_to_voxel_torch(z, z, z, z, 5, sensor_size=(180, 240))
+    assert torch.isnan(out[:, 0, 0]).all() and int(torch.isnan(out).sum()) == 5
+
+
 def test_numpy_flavour_and_negpos(oracle):
     from event_utils_b200.representations.voxel_grid import (events_to_neg_pos_voxel_torch, events_to_voxel)
     g = golden("voxel_numpy")
