@@ -40,7 +40,9 @@ def coords_f32(c, dev):
     c = c.to(dev, non_blocking=True)
     if c.dtype.is_floating_point:
         c = c.long()
-    return c.clamp(-(1 << 24), 1 << 24).to(torch.float32).contiguous()
+    if c.dtype in (torch.int64, torch.int32):
+        c = c.clamp(-(1 << 24), 1 << 24)   # anything beyond is out of range for any sensor, and stays so
+    return c.to(torch.float32).contiguous()
 
 
 def weights_f32(p, dev):
