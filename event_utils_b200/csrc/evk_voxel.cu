@@ -26,6 +26,7 @@ struct VoxelArgs {
     int64_t head;  // SoA vec4 layout: scalar events before the 16-byte aligned body
     float t0, dt, bm1;
     int B, H, W, nq;
+    int hot_force;  // SINK_QUAD_HOT: 1 = cache always on, 0 = adaptive
     int auto_span;  // 1: t0 = t[0], dt = t[n-1] - t[0] read on the device (voxel_grid.py:133) -- no host sync
     int negpos;  // 0: weights = p.  1: two grids, [p>0] -> grid 0, [p<=0] -> grid 1 (voxel_grid.py:172-175).
                  // 2: numpy truthiness, [p!=0] -> grid 0, [p==0] -> grid 1 (voxel_grid.py:234-235)
@@ -36,14 +37,52 @@ struct VoxelArgs {
     unsigned long long *oob;
 };
 
-enum { SINK_SCALAR = 0, SINK_QUAD = 1 };
+enum { SINK_SCALAR = 0, SINK_QUAD = 1, SINK_QUAD_HOT = 2 };
+
+// Per-CTA write-combining cache in front of the vector reductions (SINK_QUAD_HOT): a direct-mapped
+// {quad index -> float4 partial sum} table in shared memory, same idea as evk_hot.cu.  Real sensors
+// have hot pixels (the reference ships remove_hot_pixels for them, event_util.py:166-187); every
+// event of such a pixel hits the same two grid cells and global reductions to one address serialise
+// in its L2 slice (~1.5 ns each).  Adaptive: switched on per CTA by a match.any contention probe.
+constexpr int kVoxHotLog2 = 11;
+constexpr int kVoxHotSlots = 1 << kVoxHotLog2;  // 8 KB keys + 32 KB values
+constexpr unsigned kVoxEmpty = 0xffffffffu;
+
+struct HotCtx {
+    unsigned *keys;
+    float4 *vals;
+    bool on;
+};
+
+__device__ __forceinline__ void hot_add4(const HotCtx &hc, float *ws_base, float *addr16, float4 v)
+{
+    if (hc.on) {
+        const unsigned cell = (unsigned)((addr16 - ws_base) >> 2);
+        const unsigned slot = (cell * 2654435761u) >> (32 - kVoxHotLog2);
+        unsigned k = hc.keys[slot];
+        if (k == kVoxEmpty) {
+            const unsigned old = atomicCAS(&hc.keys[slot], kVoxEmpty, cell);
+            k = (old == kVoxEmpty) ? cell : old;
+        }
+        if (k == cell) {
+            float *acc = reinterpret_cast<float *>(&hc.vals[slot]);
+            if (v.x != 0.0f) atomicAdd(acc + 0, v.x);
+            if (v.y != 0.0f) atomicAdd(acc + 1, v.y);
+            if (v.z != 0.0f) atomicAdd(acc + 2, v.z);
+            if (v.w != 0.0f) atomicAdd(acc + 3, v.w);
+            return;
+        }
+    }
+    red_add4(addr16, v);
+}
 enum { LAYOUT_SOA4 = 0, LAYOUT_SOA1 = 1, LAYOUT_AOS = 2 };
 
 static inline int quads_for_bins(int B) { return B <= 1 ? 1 : (B - 1 + 2) / 3; }
 
 // Add the temporal tap pair (value v0 at bin b0, v1 at bin b0+1) of one pixel.
 template <int SINK>
-__device__ __forceinline__ void add_bin_pair(const VoxelArgs &A, float *out, float *ws, int64_t pix, int b0, float v0, float v1)
+__device__ __forceinline__ void add_bin_pair(const VoxelArgs &A, const HotCtx &hc, float *out, float *ws, int64_t pix, int b0,
+                                             float v0, float v1)
 {
     if (SINK == SINK_SCALAR) {
         const int64_t plane = (int64_t)A.H * A.W;
@@ -64,7 +103,8 @@ __device__ __forceinline__ void add_bin_pair(const VoxelArgs &A, float *out, flo
         v.y = (s == 1) ? a : ((s == 0) ? b : 0.0f);
         v.z = (s == 2) ? a : ((s == 1) ? b : 0.0f);
         v.w = (s == 3) ? a : ((s == 2) ? b : 0.0f);
-        red_add4(ws + (pix * A.nq + q) * 4, v);
+        if (SINK == SINK_QUAD_HOT) hot_add4(hc, A.ws, ws + (pix * A.nq + q) * 4, v);
+        else red_add4(ws + (pix * A.nq + q) * 4, v);
     }
 }
 
@@ -118,7 +158,7 @@ __device__ __forceinline__ void tri_bin(const VoxelArgs &A, int b, float pw, int
 }
 
 template <int SINK, bool SPATIAL_BILINEAR>
-__device__ __forceinline__ void voxel_event(const VoxelArgs &A, float x, float y, float t, float p,
+__device__ __forceinline__ void voxel_event(const VoxelArgs &A, const HotCtx &hc, float x, float y, float t, float p,
                                             unsigned &oob)
 {
     // tau = (t - t0) / dt * (B-1), evaluated in exactly this order, no FMA (voxel_grid.py:134)
@@ -145,7 +185,7 @@ __device__ __forceinline__ void voxel_event(const VoxelArgs &A, float x, float y
         const float fl = floorf(tn);
         const float w0 = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fl)));         // bin floor(tau)
         const float w1 = __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fl + 1.0f)));  // bin floor(tau)+1
-        add_bin_pair<SINK>(A, out, ws, pix, (int)fl, __fmul_rn(p, w0), __fmul_rn(p, w1));
+        add_bin_pair<SINK>(A, hc, out, ws, pix, (int)fl, __fmul_rn(p, w0), __fmul_rn(p, w1));
     } else {
         // trilinear extension: per-bin events_to_image_torch(..., interpolation='bilinear')
         // (image.py:78-86,102-115) with the bin weight folded into the polarity.
@@ -197,6 +237,31 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
     const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
 
+    // write-combining cache (SINK_QUAD_HOT only; the arrays vanish from the other instantiations)
+    __shared__ unsigned hot_keys[SINK == SINK_QUAD_HOT ? kVoxHotSlots : 1];
+    __shared__ float4 hot_vals[SINK == SINK_QUAD_HOT ? kVoxHotSlots : 1];
+    __shared__ int hot_dups;
+    HotCtx hc{hot_keys, hot_vals, false};
+    if (SINK == SINK_QUAD_HOT) {
+        for (int s = threadIdx.x; s < kVoxHotSlots; s += kThreads) { hot_keys[s] = kVoxEmpty; hot_vals[s] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        if (threadIdx.x == 0) hot_dups = 0;
+        __syncthreads();
+        hc.on = A.hot_force != 0;
+        if (!hc.on) {
+            // contention probe: lanes whose first event shares its pixel with another lane of the warp
+            unsigned long long key = ~0ull - (threadIdx.x & 31);
+            if (tid < A.n) {
+                const float ex = (LAYOUT == LAYOUT_AOS) ? A.x[4 * tid] : A.x[tid];
+                const float ey = (LAYOUT == LAYOUT_AOS) ? A.x[4 * tid + 1] : A.y[tid];
+                int ux, uy;
+                if (trunc_checked(ex, ux) && trunc_checked(ey, uy)) key = ((unsigned long long)(unsigned)uy << 32) | (unsigned)ux;
+            }
+            if (__popc(__match_any_sync(0xffffffffu, key)) > 1) atomicAdd(&hot_dups, 1);
+            __syncthreads();
+            hc.on = hot_dups * 20 > kThreads;  // more than 5 % of the lanes collide inside their warp
+        }
+    }
+
     if (LAYOUT == LAYOUT_SOA4) {
         // 16-byte aligned body: 4 events per thread per iteration, four LDG.128 in flight
         const int64_t head = A.head;
@@ -205,17 +270,17 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
         for (int64_t g = tid; g < n4; g += stride) {
             const float4 X = ld_stream4(bx + 4 * g), Y = ld_stream4(by + 4 * g);
             const float4 T = ld_stream4(bt + 4 * g), P = ld_stream4(bp + 4 * g);
-            voxel_event<SINK, BIL>(A, X.x, Y.x, T.x, P.x, oob);
-            voxel_event<SINK, BIL>(A, X.y, Y.y, T.y, P.y, oob);
-            voxel_event<SINK, BIL>(A, X.z, Y.z, T.z, P.z, oob);
-            voxel_event<SINK, BIL>(A, X.w, Y.w, T.w, P.w, oob);
+            voxel_event<SINK, BIL>(A, hc, X.x, Y.x, T.x, P.x, oob);
+            voxel_event<SINK, BIL>(A, hc, X.y, Y.y, T.y, P.y, oob);
+            voxel_event<SINK, BIL>(A, hc, X.z, Y.z, T.z, P.z, oob);
+            voxel_event<SINK, BIL>(A, hc, X.w, Y.w, T.w, P.w, oob);
         }
         // scalar head [0, head) and tail [head + 4*n4, n)
         const int64_t tail0 = head + 4 * n4;
         const int64_t nrest = head + (A.n - tail0);
         for (int64_t i = tid; i < nrest; i += stride) {
             const int64_t j = (i < head) ? i : tail0 + (i - head);
-            voxel_event<SINK, BIL>(A, ld_stream(A.x + j), ld_stream(A.y + j), ld_stream(A.t + j), ld_stream(A.p + j), oob);
+            voxel_event<SINK, BIL>(A, hc, ld_stream(A.x + j), ld_stream(A.y + j), ld_stream(A.t + j), ld_stream(A.p + j), oob);
         }
     } else if (LAYOUT == LAYOUT_SOA1) {
         // arbitrary 4-byte alignment: coalesced scalar loads, 4 independent events in flight
@@ -228,10 +293,10 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
                 ts[k] = ld_stream(A.t + i + k * stride); ps[k] = ld_stream(A.p + i + k * stride);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) voxel_event<SINK, BIL>(A, xs[k], ys[k], ts[k], ps[k], oob);
+            for (int k = 0; k < 4; ++k) voxel_event<SINK, BIL>(A, hc, xs[k], ys[k], ts[k], ps[k], oob);
         }
         for (; i < A.n; i += stride)
-            voxel_event<SINK, BIL>(A, ld_stream(A.x + i), ld_stream(A.y + i), ld_stream(A.t + i), ld_stream(A.p + i), oob);
+            voxel_event<SINK, BIL>(A, hc, ld_stream(A.x + i), ld_stream(A.y + i), ld_stream(A.t + i), ld_stream(A.p + i), oob);
     } else {
         // AoS: one 16-byte [x,y,t,p] record per event
         int64_t i = tid;
@@ -240,12 +305,21 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
 #pragma unroll
             for (int k = 0; k < 4; ++k) e[k] = ld_stream4(A.x + 4 * (i + k * stride));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) voxel_event<SINK, BIL>(A, e[k].x, e[k].y, e[k].z, e[k].w, oob);
+            for (int k = 0; k < 4; ++k) voxel_event<SINK, BIL>(A, hc, e[k].x, e[k].y, e[k].z, e[k].w, oob);
         }
         for (; i < A.n; i += stride) {
             const float4 e = ld_stream4(A.x + 4 * i);
-            voxel_event<SINK, BIL>(A, e.x, e.y, e.z, e.w, oob);
+            voxel_event<SINK, BIL>(A, hc, e.x, e.y, e.z, e.w, oob);
         }
+    }
+    if (SINK == SINK_QUAD_HOT) {
+        __syncthreads();
+        if (hc.on)
+            for (int s = threadIdx.x; s < kVoxHotSlots; s += kThreads) {
+                const unsigned k = hot_keys[s];
+                const float4 v = hot_vals[s];
+                if (k != kVoxEmpty && (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f)) red_add4(A.ws + (size_t)k * 4, v);
+            }
     }
     flush_oob(A.oob, oob);
 }
@@ -294,7 +368,7 @@ __global__ void __launch_bounds__(kThreads) voxel_windows_kernel(const VoxelArgs
             Aw.dt = __fsub_rn(A.t[last - 1], Aw.t0);
             Aw.out = A.out + (int64_t)w * A.B * A.H * A.W;
             for (int64_t i = first + (int64_t)s * kThreads + threadIdx.x; i < last; i += (int64_t)slices * kThreads)
-                voxel_event<SINK_SCALAR, false>(Aw, A.x[i], A.y[i], A.t[i], A.p[i], oob);
+                voxel_event<SINK_SCALAR, false>(Aw, HotCtx{nullptr, nullptr, false}, A.x[i], A.y[i], A.t[i], A.p[i], oob);
         }
     }
     flush_oob(A.oob, oob);
@@ -327,8 +401,18 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
     const bool accum = (flags & EVK_ACCUMULATE) != 0;
     const int64_t npix = (int64_t)A.H * A.W;
     unsigned variant = variant_of(flags);
-    if (variant == EVK_VARIANT_AUTO)
+    // AUTO: big streams take the vector-red path with the adaptive hot-pixel cache; small ones the
+    // scalar path (no workspace, no fold).  SMEM_TILE forces the cache on, VECTOR_RED leaves it out.
+    bool hot = false;
+    if (variant == EVK_VARIANT_AUTO) {
         variant = (A.n >= (int64_t)1 << 20 && workspace != nullptr) ? EVK_VARIANT_VECTOR_RED : EVK_VARIANT_GLOBAL_RED;
+        hot = variant == EVK_VARIANT_VECTOR_RED && !bil;
+    } else if (variant == EVK_VARIANT_SMEM_TILE && !bil) {
+        variant = EVK_VARIANT_VECTOR_RED;
+        hot = true;
+        A.hot_force = 1;
+    }
+    if ((uint64_t)npix * quads_for_bins(A.B) * (A.negpos ? 2 : 1) >= 0xffffffffull) hot = false;  // 32-bit quad ids
     if (variant != EVK_VARIANT_VECTOR_RED && variant != EVK_VARIANT_GLOBAL_RED) {
         set_error("evk_voxel: variant 0x%x not available for this entry point", variant);
         return EVK_E_UNSUPPORTED;
@@ -361,7 +445,8 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
         {
             ProfScope prof(st);
             prof_count(1);
-            if (sink == SINK_QUAD) { if (bil) EVK_DISPATCH_L(SINK_QUAD, true); else EVK_DISPATCH_L(SINK_QUAD, false); }
+            if (sink == SINK_QUAD && hot) EVK_DISPATCH_L(SINK_QUAD_HOT, false);
+            else if (sink == SINK_QUAD) { if (bil) EVK_DISPATCH_L(SINK_QUAD, true); else EVK_DISPATCH_L(SINK_QUAD, false); }
             else { if (bil) EVK_DISPATCH_L(SINK_SCALAR, true); else EVK_DISPATCH_L(SINK_SCALAR, false); }
         }
 #undef EVK_DISPATCH_L

@@ -10,7 +10,7 @@ from conftest import assert_close_to_max, golden, make_events
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = ["global_red", "vector_red"]
+VARIANTS = ["global_red", "vector_red", "smem_cache", None]
 
 
 @pytest.fixture(autouse=True)
@@ -128,6 +128,36 @@ def test_host_inputs_pipeline(oracle):
     out = events_to_voxel_torch(torch.from_numpy(xi), torch.from_numpy(yi), torch.from_numpy(ti), torch.from_numpy(p), 5)
     trel = (ti - ti[0]).astype(np.float32)
     assert_close_to_max(out.numpy(), oracle.voxel_f32(xi, yi, trel, p, 5, (180, 240), t0=0.0, dt=trel[-1]), 1e-5)
+
+
+def test_hot_pixels(oracle):
+    """A stream with hot pixels (2 pixels carry 30 % of the events): every variant, incl. the adaptive
+    shared-memory cache that AUTO selects for large N, against the oracle; counts bit exact."""
+    import event_utils_b200 as eu
+    from event_utils_b200.representations.voxel_grid import events_to_neg_pos_voxel_torch, events_to_voxel_torch
+    n, H, W = 2_000_000, 260, 346
+    x, y, t, p = make_events(77, n, H, W, pol="ones")
+    rng = np.random.default_rng(78)
+    hot = rng.random(n) < 0.3
+    x[hot] = np.where(rng.random(hot.sum()) < 0.5, 17.0, 200.0)
+    y[hot] = np.where(x[hot] == 17.0, 33.0, 101.0)
+    ref = oracle.voxel_f32(x, y, t, p, 1, (H, W))          # B=1: every weight is exactly 1 -> integer counts
+    for variant in VARIANTS:
+        eu.config.variant = variant
+        out = events_to_voxel_torch(*dev(x, y, t, p), 1, sensor_size=(H, W)).cpu().numpy()
+        assert np.array_equal(out, ref), variant
+    pm = (rng.integers(0, 2, n) * 2 - 1).astype(np.float32)
+    ref5 = oracle.voxel_f32(x, y, t, pm, 5, (H, W))
+    refp = oracle.voxel_f32(x, y, t, (pm > 0).astype(np.float32), 5, (H, W))
+    # the hot cells sum ~3e5 weights of mixed sign in f32: order-dependent beyond 1e-5 there (see
+    # test_gpu_image.test_hot_spot_bilinear_and_signed); the bound is the random-walk one
+    bound = 2.0 * np.sqrt(0.15 * n) * np.finfo(np.float32).eps * np.abs(refp).max()
+    for variant in VARIANTS:
+        eu.config.variant = variant
+        out = events_to_voxel_torch(*dev(x, y, t, pm), 5, sensor_size=(H, W)).cpu().numpy()
+        assert np.abs(out - ref5).max() <= max(bound, 1e-5 * np.abs(ref5).max()), variant
+        vp, vn = events_to_neg_pos_voxel_torch(*dev(x, y, t, pm), 5, sensor_size=(H, W))
+        assert np.abs(vp.cpu().numpy() - refp).max() <= bound, variant
 
 
 def test_data_loader_arrays(oracle):

@@ -72,6 +72,19 @@ for name, v in (("global_red", _lib.VARIANT_GLOBAL_RED), ("vector_red", _lib.VAR
                                    out.data_ptr(), ws.data_ptr(), ws.numel(), oob.data_ptr(), None))
     best, avg = timeit(run)
     report("voxel " + name, best, N, 16, 4 * B * H * W)
+# the same stream with two hot pixels carrying 10 % of the events
+xh, yh = x.clone(), y.clone()
+hm = torch.rand(N, device=dev) < 0.10
+xh[hm] = torch.where(torch.rand(int(hm.sum()), device=dev) < 0.5, 17.0, 400.0)
+yh[hm] = torch.where(xh[hm] == 17.0, 33.0, 301.0)
+for name, v in (("vector_red", _lib.VARIANT_VECTOR_RED), ("smem_cache", _lib.VARIANT_SMEM_TILE), ("auto", 0)):
+    for tag, (xx, yy) in (("uniform", (x, y)), ("10% hot pixels", (xh, yh))):
+        def run(v=v, xx=xx, yy=yy):
+            _lib.check(L.evk_voxel_f32(xx.data_ptr(), yy.data_ptr(), t.data_ptr(), p.data_ptr(), N, t0, dt, B, H, W, v,
+                                       out.data_ptr(), ws.data_ptr(), ws.numel(), oob.data_ptr(), None))
+        best, avg = timeit(run)
+        report("voxel %s [%s]" % (name, tag), best, N, 16, 4 * B * H * W)
+del xh, yh, hm
 ev = torch.stack((x, y, t, p), 1).contiguous()
 for name, v in (("global_red", _lib.VARIANT_GLOBAL_RED), ("vector_red", _lib.VARIANT_VECTOR_RED)):
     def run(v=v):
