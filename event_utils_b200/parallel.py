@@ -60,3 +60,46 @@ def events_to_voxel_sharded(xs, ys, ts, ps, B, sensor_size=(180, 240), group=Non
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(grid, op=dist.ReduceOp.SUM, group=group)
     return grid
+
+
+class ShardedVoxelStream:
+    """Back-to-back sharded voxel builds (a data loader voxelising window after window): the sum
+    all-reduce of build k runs on a communication stream and overlaps the scatter kernel of build
+    k+1, which the NVLink transfer (6 MB) and its launch latency would otherwise serialise with.
+    `submit()` returns the grid buffer and the event that marks its all-reduce complete; buffers are
+    recycled round-robin (`depth` in flight)."""
+
+    def __init__(self, B, sensor_size, device, group=None, depth=2):
+        self.B, self.H, self.W = int(B), int(sensor_size[0]), int(sensor_size[1])
+        self.device, self.group = torch.device(device), group
+        self.grids = [torch.empty((self.B, self.H, self.W), dtype=torch.float32, device=self.device) for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.comm = torch.cuda.Stream(self.device)
+        self.k = 0
+        self.multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def submit(self, xs, ys, ts, ps, t0, dt):
+        from . import _lib
+        from .representations.voxel_grid import _voxel_device
+        i = self.k % len(self.grids)
+        self.k += 1
+        cur = torch.cuda.current_stream(self.device)
+        if self.k > len(self.grids):
+            cur.wait_event(self.done[i])            # the buffer's previous all-reduce must have finished
+        _voxel_device(xs, ys, ts, ps, t0, dt, self.B, self.H, self.W, out=self.grids[i])
+        if self.multi:
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            self.comm.wait_event(ready)
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(self.grids[i], op=dist.ReduceOp.SUM, group=self.group)
+                self.done[i].record(self.comm)
+        else:
+            self.done[i].record(cur)
+        return self.grids[i], self.done[i]
+
+    def drain(self):
+        """Make the current stream wait for every outstanding all-reduce."""
+        cur = torch.cuda.current_stream(self.device)
+        for ev in self.done[: min(self.k, len(self.done))]:
+            cur.wait_event(ev)
