@@ -253,6 +253,11 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner) write to
+    # file descriptor 1 directly, so point it at stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     L = _lib.lib()
@@ -419,7 +424,10 @@ def run_ours(args, rank, local_rank, world):
         }
         if extra:
             line["extra"] = extra
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
