@@ -81,3 +81,25 @@ def test_bounds_mask_known_answer():
     from event_utils_b200.util.event_util import events_bounds_mask
     m = events_bounds_mask(np.array([0, 1e-9, 240, 240.1]), np.array([5.0, 5, 5, 5]), 0, 240, 0, 180)
     assert m.tolist() == [0.0, 1.0, 1.0, 0.0]
+
+
+def test_argument_errors_are_reported_without_touching_the_gpu():
+    """Bad arguments come back as EVK_E_ARG / EVK_E_WORKSPACE with a message, before any CUDA call."""
+    from event_utils_b200 import _lib
+    L = _lib.load()
+    one = ctypes.c_void_p(16)   # a non-null, aligned, never dereferenced pointer
+    assert L.evk_voxel_f32(None, one, one, one, 10, 0.0, 1.0, 5, 4, 4, 0, one, None, 0, None, None) == -1
+    assert b"null event array" in L.evk_last_error()
+    assert L.evk_voxel_f32(one, one, one, one, -1, 0.0, 1.0, 5, 4, 4, 0, one, None, 0, None, None) == -1
+    assert L.evk_voxel_f32(one, one, one, one, 10, 0.0, 1.0, 0, 4, 4, 0, one, None, 0, None, None) == -1
+    # vector-red variant without a workspace
+    assert L.evk_voxel_f32(one, one, one, one, 10, 0.0, 1.0, 5, 4, 4, _lib.VARIANT_VECTOR_RED, one, None, 0, None, None) == -3
+    assert b"workspace" in L.evk_last_error()
+    assert L.evk_image_f32(one, one, one, 10, 1, 1, 0.0, 0.0, _lib.BILINEAR, 0.0, one, None, 0, None, None) == -1
+    assert L.evk_image_f32(one, one, None, 10, 4, 4, 0.0, 0.0, 0, 0.0, one, None, 0, None, None) == -1
+    assert L.evk_cmax_linvel_variance_f64(one, one, one, one, 10, 1.0, 0.0, 0.0, 0.0, 180, 240, 180, 240, 1.0, 0,
+                                          one, None, None, None, 0, None) == -1
+    assert L.evk_timestamp_image_f32(one, one, one, one, 10, 0.0, 1.0, 4, 4, 3.0, 3.0, 0, one, one, None, 0, None, None) == -3
+    assert L.evk_warp_flow_f32(one, one, one, 10, None, 4, 4, 0.0, one, one, None) == -1
+    assert L.evk_voxel_windows_f32(one, one, one, one, None, 3, 0, 5, 4, 4, 0, one, None, None) == -1
+    assert L.evk_voxel_negpos_f32(one, one, one, one, 10, 0.0, 1.0, 5, 4, 4, _lib.BILINEAR, one, None, 0, None, None) == -5
