@@ -93,6 +93,9 @@ def _declare(L):
     L.evk_cmax_linvel_objective_f32.restype = ci
     L.evk_cmax_linvel_objective_f32.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, ci, ci, ci, ci, f64, cu, ci, f64,
                                                 vp, vp, vp, vp, sz, vp]
+    L.evk_cmax_linvel_objective_batch_f64.restype = ci
+    L.evk_cmax_linvel_objective_batch_f64.argtypes = [vp, vp, vp, vp, i64, f64, vp, ci, f64, ci, ci, ci, ci, f64, cu, ci, f64,
+                                                      vp, vp, sz, vp]
     L.evk_iwe_objective_f32.restype = ci
     L.evk_iwe_objective_f32.argtypes = [vp, vp, ci, ci, f64, cu, ci, f64, vp, vp, sz, vp]
     L.evk_gaussian_blur_f32.restype = ci

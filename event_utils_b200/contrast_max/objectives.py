@@ -465,3 +465,43 @@ class zhu_timestamp_objective(objective_function):
     def evaluate_gradient(self, params=None, xs=None, ys=None, ts=None, ps=None,
             warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None, d_iwe=None):
         return None
+
+
+def evaluate_candidates(objective, params_list, xs, ys, ts, ps, warpfunc, img_size, blur_sigma=None, want_grad=False):
+    """Objective (and gradient) at MANY parameter points with one pass over the events per 32
+    candidates (evk_cmax_linvel_objective_batch_f64): what grid_search_initial needs
+    (events_cmax.py:300-302 evaluates 25 points per level, one full evaluation each).
+    @returns (f[K], g[K,2] or None)"""
+    params_list = [tuple(float(v) for v in prm) for prm in params_list]
+    kind = getattr(objective, "_kind", _lib.OBJ_VARIANCE)
+    prm_fn = getattr(objective, "_param", None)
+    obj_param = float(prm_fn()) if prm_fn is not None else 0.0
+    sigma = objective.default_blur if blur_sigma is None else blur_sigma
+    fused = getattr(warpfunc, "fused_kind", None) == "linvel" and precision == "f64" \
+        and not getattr(objective, "adaptive_lifespan", False) and type(objective).evaluate_function in (
+            _fused_objective.evaluate_function, variance_objective.evaluate_function)
+    if not fused:
+        f = np.array([objective.evaluate_function(prm, xs, ys, ts, ps, warpfunc, img_size, blur_sigma) for prm in params_list])
+        g = np.array([objective.evaluate_gradient(prm, xs, ys, ts, ps, warpfunc, img_size, blur_sigma)
+                      for prm in params_list]) if want_grad else None
+        return f, g
+    L = _lib.lib()
+    ev = _device_events(xs, ys, ts, ps)
+    Hs, Ws = SENSOR_SIZE
+    dev = ev.x.device
+    K = len(params_list)
+    out = np.zeros((K, 12))
+    with torch.cuda.device(dev):
+        ws = _lib.scratch("cmax_ws", L.evk_cmax_workspace_bytes(Hs, Ws), dev)
+        flags = (_lib.CMAX_WANT_GRAD if want_grad else 0) | (0 if objective.use_polarity else _lib.CMAX_ABS_POLARITY)
+        for lo in range(0, K, 32):
+            chunk = np.ascontiguousarray(np.array(params_list[lo:lo + 32], dtype=np.float64).reshape(-1, 2))
+            res = torch.zeros((chunk.shape[0], 12), dtype=torch.float64, device=dev)
+            _lib.check(L.evk_cmax_linvel_objective_batch_f64(
+                ev.x.data_ptr(), ev.y.data_ptr(), ev.t.data_ptr(), ev.p.data_ptr(), ev.n, 1.0,
+                chunk.ctypes.data, chunk.shape[0], ev.t_last, int(img_size[0]), int(img_size[1]), Hs, Ws, float(sigma), flags,
+                int(kind), obj_param, _lib.ptr(res), _lib.ptr(ws), ws.numel(), _lib.stream()))
+            out[lo:lo + chunk.shape[0]] = res.cpu().numpy()
+    if out[:, 4].any():
+        raise IndexError("warped events index outside the IWE canvas")
+    return out[:, 0].copy(), (out[:, 1:3].copy() if want_grad else None)

@@ -1,8 +1,11 @@
-"""Warp functions -- drop-in for the reference's lib/contrast_max/warps.py.
+"""Motion models for contrast maximisation -- drop-in for the reference's lib/contrast_max/warps.py
+(`warp_function` ABC :6-42, `linvel_warp` :44-61, the two empty stubs :63-83).
 
-`linvel_warp` is recognised by the objective functions in this package: events warped with it
-never leave the GPU (warp, mask, IWE, objective and gradient are one fused kernel).  Its
-`warp()` method still exists with the reference's semantics for code that calls it directly.
+An objective from `event_utils_b200.contrast_max.objectives` that is handed a `linvel_warp` never
+calls `warp()`: it recognises the model through `fused_kind` and evaluates warp, bounds mask, image
+formation, objective and gradient in one fused GPU pass over the device-resident events
+(csrc/evk_cmax.cu).  `warp()` is still provided, with the reference's semantics, for user code that
+calls it directly and for the generic (non-fused) path taken by other `warp_function` subclasses.
 """
 from abc import ABC, abstractmethod
 
@@ -10,60 +13,63 @@ import numpy as np
 
 
 class warp_function(ABC):
-    """
-    Base class of parametrised, differentiable motion models that move events to a reference
-    time (reference: warps.py:6-42).
-    """
+    """A parametrised, differentiable motion model that transports events to a reference time.
+    `name` identifies the model, `dims` is its number of degrees of freedom (used by the grid
+    search drivers, events_cmax.py:282)."""
+
+    fused_kind = None   # set by models the fused kernels implement natively
+
     def __init__(self, name, dims):
-        self.name = name
-        self.dims = dims
+        self.name, self.dims = name, dims
         super().__init__()
 
     @abstractmethod
     def warp(self, xs, ys, ts, ps, t0, params, compute_grad=False):
-        """
-        @returns xs_warped, ys_warped, xs_jacobian, ys_jacobian (jacobians (dims,N) or None)
-        """
-        pass
+        """Transport the events (xs, ys, ts, ps) to time t0 under `params`.
+        Returns (xs_warped, ys_warped, jacobian_x, jacobian_y); the Jacobians have shape
+        (dims, N) -- d x'/d params and d y'/d params per event -- or are None without
+        compute_grad."""
 
 
 class linvel_warp(warp_function):
-    """
-    Linear velocity (global optic flow) warp, reference warps.py:44-61:
-    x' = x - (t-t0)*vx, y' = y - (t-t0)*vy; d x'/d vx = d y'/d vy = -(t-t0).
-    """
-    fused_kind = "linvel"  # lets get_iwe / the objectives take the fused GPU path
+    """Global optic flow: every event moves with one image-plane velocity (vx, vy) = params,
+        x' = x - (t - t0) vx,      y' = y - (t - t0) vy,
+    so d x'/d vx = d y'/d vy = -(t - t0) and the cross terms vanish (reference warps.py:51-61)."""
+
+    fused_kind = "linvel"
 
     def __init__(self):
-        warp_function.__init__(self, 'linvel_warp', 2)
+        super().__init__('linvel_warp', 2)
 
     def warp(self, xs, ys, ts, ps, t0, params, compute_grad=False):
-        dt = ts - t0
-        x_prime = xs - dt * params[0]
-        y_prime = ys - dt * params[1]
-        jacobian_x, jacobian_y = None, None
-        if compute_grad:
-            n = len(x_prime)
-            jacobian_x = np.zeros((2, n))
-            jacobian_y = np.zeros((2, n))
-            jacobian_x[0, :] = -dt
-            jacobian_y[1, :] = -dt
-        return x_prime, y_prime, jacobian_x, jacobian_y
+        lag = ts - t0
+        moved = (xs - lag * params[0], ys - lag * params[1])
+        if not compute_grad:
+            return moved[0], moved[1], None, None
+        nothing = np.zeros_like(lag, dtype=np.float64)
+        return moved[0], moved[1], np.stack((-lag, nothing)), np.stack((nothing, -lag))
 
 
-class xyztheta_warp(warp_function):
-    """4-DoF x,y,z,rotation warp: an empty stub in the reference (warps.py:63-72), kept as one."""
+class _placeholder_warp(warp_function):
+    """The reference declares these models but leaves `warp` empty (it returns None)."""
+
+    def __init__(self, name, dims):
+        super().__init__(name, dims)
+
+    def warp(self, xs, ys, ts, ps, t0, params, compute_grad=False):
+        return None
+
+
+class xyztheta_warp(_placeholder_warp):
+    """4-DoF x, y, z, rotation model (Mitrokhin et al.); an empty stub in the reference (warps.py:63-72)."""
+
     def __init__(self):
-        warp_function.__init__(self, 'xyztheta_warp', 4)
-
-    def warp(self, xs, ys, ts, ps, t0, params, compute_grad=False):
-        pass
+        super().__init__('xyztheta_warp', 4)
 
 
-class pure_rotation_warp(warp_function):
-    """Pure rotation warp: an empty stub in the reference (warps.py:74-83), kept as one."""
+class pure_rotation_warp(_placeholder_warp):
+    """Rotation about a centre (x, y) with angular velocity theta; an empty stub in the reference
+    (warps.py:74-83), which also registers it with dims=4."""
+
     def __init__(self):
-        warp_function.__init__(self, 'pure_rotation_warp', 4)
-
-    def warp(self, xs, ys, ts, ps, t0, params, compute_grad=False):
-        pass
+        super().__init__('pure_rotation_warp', 4)

@@ -143,7 +143,8 @@ __device__ __forceinline__ Event<WARP> load_event(const CmaxArgs &A, int64_t i)
 }
 
 template <int WARP, bool GRAD>
-__device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const Event<WARP> &e, unsigned &oob)
+__device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const Event<WARP> &e, unsigned &oob, double cvx,
+                                           double cvy)
 {
     if (WARP == WARP_LINVEL_F64) {
         const double x = e.x, y = e.y, t = e.t;
@@ -151,8 +152,8 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const 
         if (A.p_scale != 1.0) p = __dmul_rn(p, A.p_scale);
         if (A.abs_polarity) p = fabs(p);
         const double d = __dsub_rn(t, A.t_ref);
-        const double xw = __dsub_rn(x, __dmul_rn(d, A.vx));  // warps.py:52-54
-        const double yw = __dsub_rn(y, __dmul_rn(d, A.vy));
+        const double xw = __dsub_rn(x, __dmul_rn(d, cvx));  // warps.py:52-54
+        const double yw = __dsub_rn(y, __dmul_rn(d, cvy));
         // event_util.py:26-27: keep iff 0 < x' <= Wm and 0 < y' <= Hm (NaN compares false -> kept)
         const bool keep = !(xw <= 0.0 || xw > (double)A.Wm) && !(yw <= 0.0 || yw > (double)A.Hm);
         if (!keep) return;  // x,y,p,j all multiplied by 0: only exact zeros are added at (0,0)..(1,1)
@@ -163,7 +164,7 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const 
         float p = e.p;
         if (A.p_scale != 1.0) p = __fmul_rn(p, (float)A.p_scale);
         if (A.abs_polarity) p = fabsf(p);
-        const float vx = (float)A.vx, vy = (float)A.vy;
+        const float vx = (float)cvx, vy = (float)cvy;
         const float xw = __fsub_rn(x, __fmul_rn(d, vx)), yw = __fsub_rn(y, __fmul_rn(d, vy));
         const bool keep = !(xw <= 0.0f || xw > (float)A.Wm) && !(yw <= 0.0f || yw > (float)A.Hm);
         if (!keep) return;
@@ -217,9 +218,36 @@ __global__ void __launch_bounds__(256) cmax_scatter_kernel(const CmaxArgs A)
 #pragma unroll
         for (int k = 0; k < kBatch; ++k) ev[k] = load_event<WARP>(A, i + k * stride);
 #pragma unroll
-        for (int k = 0; k < kBatch; ++k) cmax_event<WARP, GRAD>(A, acc, ev[k], oob);
+        for (int k = 0; k < kBatch; ++k) cmax_event<WARP, GRAD>(A, acc, ev[k], oob, A.vx, A.vy);
     }
-    for (; i < A.n; i += stride) cmax_event<WARP, GRAD>(A, acc, load_event<WARP>(A, i), oob);
+    for (; i < A.n; i += stride) cmax_event<WARP, GRAD>(A, acc, load_event<WARP>(A, i), oob, A.vx, A.vy);
+    flush_oob(A.oob, oob);
+}
+
+// K candidate parameter points in ONE pass over the events (grid_search_initial evaluates 25 points per
+// level, events_cmax.py:241-311): every event is loaded once and splatted into K accumulators.
+constexpr int kMaxCandidates = 32;
+struct Candidates {
+    int n;
+    double vx[kMaxCandidates], vy[kMaxCandidates];
+};
+
+template <int WARP, bool GRAD>
+__global__ void __launch_bounds__(256) cmax_scatter_batch_kernel(const CmaxArgs A, const Candidates C)
+{
+    unsigned oob = 0;
+    const int64_t acc_stride = (int64_t)A.Hc * A.Wc * kBlockFloats;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < A.n; i += 2 * stride) {
+        const Event<WARP> e0 = load_event<WARP>(A, i);
+        const bool has1 = i + stride < A.n;
+        const Event<WARP> e1 = has1 ? load_event<WARP>(A, i + stride) : e0;
+        for (int k = 0; k < C.n; ++k) {
+            float *acc = A.acc + k * acc_stride;
+            cmax_event<WARP, GRAD>(A, acc, e0, oob, C.vx[k], C.vy[k]);
+            if (has1) cmax_event<WARP, GRAD>(A, acc, e1, oob, C.vx[k], C.vy[k]);
+        }
+    }
     flush_oob(A.oob, oob);
 }
 
@@ -500,7 +528,7 @@ static size_t carve(void *base, int Hs, int Ws, CmaxWorkspace *ws)
     size_t off = 0;
     char *b = static_cast<char *>(base);
     auto take = [&](size_t bytes) { char *p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
-    float *acc = (float *)take(npix * kBlockFloats * sizeof(float) * kMaxReplicas);
+    float *acc = (float *)take(npix * kBlockFloats * sizeof(float) * (kMaxCandidates > kMaxReplicas ? kMaxCandidates : kMaxReplicas));
     float *I = (float *)take(npix * sizeof(float));
     float *D0 = (float *)take(npix * sizeof(float));
     float *D1 = (float *)take(npix * sizeof(float));
@@ -743,6 +771,53 @@ int evk_gaussian_blur_f32(const float *img, int H, int W, double sigma, float *o
     if (do_blur) cmax_blur_axis0_kernel<<<g, 256, 0, st>>>(img, tmp, H, W, taps);
     cmax_blur_axis1_store_kernel<<<g, 256, 0, st>>>(tmp, img, H, W, taps, do_blur, out);
     EVK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+int evk_cmax_linvel_objective_batch_f64(const double *x, const double *y, const double *t, const double *p, int64_t n,
+                                        double p_scale, const double *params_host, int n_params, double t_ref, int Hm, int Wm,
+                                        int Hs, int Ws, double sigma, unsigned flags, int objective, double obj_param,
+                                        double *results, void *workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace evk;
+    if (n < 0 || (n > 0 && (!x || !y || !t || !p)) || !params_host || n_params < 1 || n_params > kMaxCandidates || !results || !workspace) {
+        set_error("evk_cmax_linvel_objective_batch_f64: bad arguments (1 <= n_params <= %d)", kMaxCandidates);
+        return EVK_E_ARG;
+    }
+    if (((uintptr_t)workspace & 255) != 0) { set_error("evk_cmax batch: workspace must be 256-byte aligned"); return EVK_E_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CmaxWorkspace ws;
+    const size_t need = carve(workspace, Hs, Ws, &ws);
+    if (workspace_bytes < need) { set_error("evk_cmax batch: workspace of %zu bytes required", need); return EVK_E_WORKSPACE; }
+    CmaxArgs A{};
+    A.x = x; A.y = y; A.t = t; A.p = p; A.n = n;
+    A.t_ref = t_ref; A.p_scale = p_scale;
+    A.Hm = Hm; A.Wm = Wm; A.Hc = Hs + 1; A.Wc = Ws + 1;
+    A.abs_polarity = (flags & EVK_CMAX_ABS_POLARITY) ? 1 : 0;
+    A.replicas = 1; A.acc = ws.acc; A.oob = ws.oob;
+    const int npix = A.Hc * A.Wc;
+    const bool grad = (flags & EVK_CMAX_WANT_GRAD) != 0;
+    Candidates C{};
+    C.n = n_params;
+    for (int k = 0; k < n_params; ++k) { C.vx[k] = params_host[2 * k]; C.vy[k] = params_host[2 * k + 1]; }
+    EVK_CUDA(cudaMemsetAsync(ws.acc, 0, (size_t)n_params * npix * kBlockFloats * sizeof(float), st));
+    EVK_CUDA(cudaMemsetAsync(ws.oob, 0, sizeof(unsigned long long), st));
+    if (n > 0) {
+        ProfScope prof(st);
+        prof_count(1);
+        if (grad) cmax_scatter_batch_kernel<WARP_LINVEL_F64, true><<<grid_for(cmax_scatter_batch_kernel<WARP_LINVEL_F64, true>, 256, n, 256 * 2), 256, 0, st>>>(A, C);
+        else cmax_scatter_batch_kernel<WARP_LINVEL_F64, false><<<grid_for(cmax_scatter_batch_kernel<WARP_LINVEL_F64, false>, 256, n, 256 * 2), 256, 0, st>>>(A, C);
+        EVK_CUDA(cudaGetLastError());
+    }
+    for (int k = 0; k < n_params; ++k) {
+        // per-candidate image-space tail on the shared scratch images (stream-ordered)
+        EVK_CUDA(cudaMemsetAsync(ws.gsums, 0, (size_t)((char *)ws.oob - (char *)ws.gsums), st));   // keep the oob counter
+        prof_count(1);
+        cmax_gather_kernel<<<(npix + 255) / 256, 256, 0, st>>>(ws.acc + (size_t)k * npix * kBlockFloats, 1, A.Hc, A.Wc, ws.I, ws.D0,
+                                                                ws.D1, nullptr, nullptr, ws.sums);
+        int rc = launch_tail(ws, A.Hc, A.Wc, sigma, flags, objective, obj_param, grad, results + 12 * k, st);
+        if (rc) return rc;
+    }
     return EVK_OK;
 }
 

@@ -245,6 +245,15 @@ int evk_cmax_linvel_objective_f32(const float *x, const float *y, const float *t
                                   int Hs, int Ws, double sigma, unsigned flags, int objective,
                                   double obj_param, double *result, float *iwe_out, float *diwe_out,
                                   void *workspace, size_t workspace_bytes, void *stream);
+/* K parameter candidates in ONE pass over the events (grid_search_initial, events_cmax.py:241-311,
+ * evaluates num_samples^dims = 25 points per level): every event is read once and splatted into K
+ * accumulators; results: 12 doubles per candidate (layout above).  params_host: K (vx,vy) pairs in
+ * HOST memory, 1 <= K <= 32. */
+int evk_cmax_linvel_objective_batch_f64(const double *x, const double *y, const double *t, const double *p,
+                                        int64_t n, double p_scale, const double *params_host, int n_params,
+                                        double t_ref, int Hm, int Wm, int Hs, int Ws, double sigma,
+                                        unsigned flags, int objective, double obj_param, double *results,
+                                        void *workspace, size_t workspace_bytes, void *stream);
 int evk_iwe_objective_f32(const float *iwe, const float *diwe, int Hc, int Wc, double sigma,
                           unsigned flags, int objective, double obj_param, double *result,
                           void *workspace, size_t workspace_bytes, void *stream);

