@@ -417,7 +417,7 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": int(klaunch.value),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "kernel": "voxel_scatter_kernel<QUAD> (red.global.add.v4.f32)",
+                         "kernel": "voxel_scatter_kernel<QUAD_HOT> (one red.global.add.v4.f32 per event; adaptive hot-pixel cache, off for this uniform stream)",
                          "kernel_ms": k_ms, "launches_timed": int(ktimed.value),
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "step_frac": (alg_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak},
