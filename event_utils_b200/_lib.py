@@ -55,6 +55,8 @@ def _declare(L):
     L.evk_voxel_f32.argtypes = [vp, vp, vp, vp, i64, f32, f32, ci, ci, ci, cu, vp, vp, sz, vp, vp]
     L.evk_voxel_negpos_f32.restype = ci
     L.evk_voxel_negpos_f32.argtypes = [vp, vp, vp, vp, i64, f32, f32, ci, ci, ci, cu, vp, vp, sz, vp, vp]
+    L.evk_voxel_packed_f32.restype = ci
+    L.evk_voxel_packed_f32.argtypes = [vp, vp, vp, vp, i64, f64, f64, ci, ci, ci, cu, vp, vp, sz, vp, vp]
     L.evk_voxel_aos_f32.restype = ci
     L.evk_voxel_aos_f32.argtypes = [vp, i64, f32, f32, ci, ci, ci, cu, vp, vp, sz, vp, vp]
     L.evk_voxel_windows_f32.restype = ci

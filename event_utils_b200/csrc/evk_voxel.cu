@@ -22,6 +22,11 @@ namespace evk {
 
 struct VoxelArgs {
     const float *x, *y, *t, *p;  // SoA arrays (AoS: x is the interleaved base)
+    // storage layout (LAYOUT_PACKED): int16 x, int16 y, float64 t, uint8 p (0/1), 13 B/event
+    const short *px16, *py16;
+    const double *pt64;
+    const unsigned char *pp8;
+    double t_first;  // PACKED: timestamps are made relative to this in float64, then cast to float32
     int64_t n;
     int64_t head;  // SoA vec4 layout: scalar events before the 16-byte aligned body
     float t0, dt, bm1;
@@ -75,7 +80,7 @@ __device__ __forceinline__ void hot_add4(const HotCtx &hc, float *ws_base, float
     }
     red_add4(addr16, v);
 }
-enum { LAYOUT_SOA4 = 0, LAYOUT_SOA1 = 1, LAYOUT_AOS = 2 };
+enum { LAYOUT_SOA4 = 0, LAYOUT_SOA1 = 1, LAYOUT_AOS = 2, LAYOUT_PACKED = 3 };
 
 static inline int quads_for_bins(int B) { return B <= 1 ? 1 : (B - 1 + 2) / 3; }
 
@@ -228,8 +233,10 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
     VoxelArgs A = A_in;
     if (A.auto_span && A.n > 0) {
         // first / last timestamp straight from the (time-sorted) stream; AoS keeps t at offset 2
-        const float first = (LAYOUT == LAYOUT_AOS) ? A.x[2] : A.t[0];
-        const float last = (LAYOUT == LAYOUT_AOS) ? A.x[4 * (A.n - 1) + 2] : A.t[A.n - 1];
+        const float first = (LAYOUT == LAYOUT_PACKED) ? 0.0f : (LAYOUT == LAYOUT_AOS) ? A.x[2] : A.t[0];
+        const float last = (LAYOUT == LAYOUT_PACKED) ? (float)(A.pt64[A.n - 1] - A.pt64[0])
+                           : (LAYOUT == LAYOUT_AOS)  ? A.x[4 * (A.n - 1) + 2] : A.t[A.n - 1];
+        if (LAYOUT == LAYOUT_PACKED) A.t_first = A.pt64[0];
         A.t0 = first;
         A.dt = __fsub_rn(last, first);
     }
@@ -251,8 +258,8 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
             // contention probe: lanes whose first event shares its pixel with another lane of the warp
             unsigned long long key = ~0ull - (threadIdx.x & 31);
             if (tid < A.n) {
-                const float ex = (LAYOUT == LAYOUT_AOS) ? A.x[4 * tid] : A.x[tid];
-                const float ey = (LAYOUT == LAYOUT_AOS) ? A.x[4 * tid + 1] : A.y[tid];
+                const float ex = (LAYOUT == LAYOUT_PACKED) ? (float)A.px16[tid] : (LAYOUT == LAYOUT_AOS) ? A.x[4 * tid] : A.x[tid];
+                const float ey = (LAYOUT == LAYOUT_PACKED) ? (float)A.py16[tid] : (LAYOUT == LAYOUT_AOS) ? A.x[4 * tid + 1] : A.y[tid];
                 int ux, uy;
                 if (trunc_checked(ex, ux) && trunc_checked(ey, uy)) key = ((unsigned long long)(unsigned)uy << 32) | (unsigned)ux;
             }
@@ -297,6 +304,17 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
         }
         for (; i < A.n; i += stride)
             voxel_event<SINK, BIL>(A, hc, ld_stream(A.x + i), ld_stream(A.y + i), ld_stream(A.t + i), ld_stream(A.p + i), oob);
+    } else if (LAYOUT == LAYOUT_PACKED) {
+        // the on-disk layout of the reference's HDF5 / memmap formats (event_packagers.py:90-93,
+        // h5_to_memmap.py:115-117): int16 x, int16 y, float64 t, bool / uint8 p, with the loader's
+        // polarity map p*2-1 (hdf5_dataset.py:22) and the stamps made relative in float64 before the
+        // float32 cast.  13 B/event instead of 16, and no host-side casts.
+        for (int64_t i = tid; i < A.n; i += stride) {
+            const float ex = (float)__ldcs(A.px16 + i), ey = (float)__ldcs(A.py16 + i);
+            const float et = (float)(__ldcs(A.pt64 + i) - A.t_first);
+            const float ep = __ldcs(A.pp8 + i) ? 1.0f : -1.0f;
+            voxel_event<SINK, BIL>(A, hc, ex, ey, et, ep, oob);
+        }
     } else {
         // AoS: one 16-byte [x,y,t,p] record per event
         int64_t i = tid;
@@ -440,6 +458,7 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
     do {                                                       \
         if (layout == LAYOUT_SOA4) EVK_LAUNCH(S, BL, LAYOUT_SOA4); \
         else if (layout == LAYOUT_SOA1) EVK_LAUNCH(S, BL, LAYOUT_SOA1); \
+        else if (layout == LAYOUT_PACKED) EVK_LAUNCH(S, BL, LAYOUT_PACKED); \
         else EVK_LAUNCH(S, BL, LAYOUT_AOS);                    \
     } while (0)
         {
@@ -599,6 +618,25 @@ int evk_voxel_negpos_f32(const float *x, const float *y, const float *t, const f
         if (A.head > n) A.head = n;
     }
     return launch_voxel(A, flags, layout, static_cast<cudaStream_t>(stream), workspace, workspace_bytes);
+}
+
+int evk_voxel_packed_f32(const int16_t *x, const int16_t *y, const double *t, const uint8_t *p, int64_t n, double t_first,
+                         double t_last, int B, int H, int W, unsigned flags, float *out, void *workspace,
+                         size_t workspace_bytes, unsigned long long *oob, void *stream)
+{
+    using namespace evk;
+    int rc = check_common(n, B, H, W, out);
+    if (rc) return rc;
+    if (n > 0 && (!x || !y || !t || !p)) { set_error("evk_voxel_packed_f32: null event array"); return EVK_E_ARG; }
+    if (flags & EVK_BILINEAR) { set_error("evk_voxel_packed_f32: spatial bilinear is not available for the packed layout"); return EVK_E_UNSUPPORTED; }
+    VoxelArgs A{};
+    A.px16 = x; A.py16 = y; A.pt64 = t; A.pp8 = p; A.n = n;
+    A.t_first = t_first;
+    A.t0 = 0.0f; A.dt = (float)(t_last - t_first); A.bm1 = (float)(B - 1);
+    A.B = B; A.H = H; A.W = W;
+    A.auto_span = (flags & EVK_AUTO_SPAN) ? 1 : 0;
+    A.out = out; A.oob = oob;
+    return launch_voxel(A, flags, LAYOUT_PACKED, static_cast<cudaStream_t>(stream), workspace, workspace_bytes);
 }
 
 }  // extern "C"

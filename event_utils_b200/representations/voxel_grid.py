@@ -128,6 +128,39 @@ def events_to_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240)
     return grid if grid.device == device else grid.to(device)
 
 
+def events_to_voxel_packed(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240)):
+    """
+    Voxel grid straight from the reference's STORAGE layout (extension, row f4 of the scope table):
+    xs, ys int16, ts float64, ps bool / uint8 in {0,1} -- what DynamicH5Dataset / MemMapDataset read
+    from disk (hdf5_dataset.py:18-23, memmap_dataset.py) before they cast.  Polarity is mapped p*2-1
+    and the stamps are made relative in float64 on the device; numpy or torch inputs, host or CUDA.
+    Equals events_to_voxel_torch(xs.float(), ys.float(), (ts-ts[0]).float(), ps*2-1, B, ...).
+    """
+    assert(len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps))
+    if len(xs) == 0:
+        raise IndexError("index -1 is out of bounds for dimension 0 with size 0")
+    L = _lib.lib()
+    xt, yt, tt, pt = (E.as_tensor(a).reshape(-1) for a in (xs, ys, ts, ps))
+    if device is None:
+        device = xt.device
+    device = torch.device(device)
+    dev = E.compute_device(xt, yt, tt, pt)
+    H, W, B = int(sensor_size[0]), int(sensor_size[1]), int(B)
+    with torch.cuda.device(dev):
+        x = xt.to(dev, non_blocking=True).to(torch.int16).contiguous()
+        y = yt.to(dev, non_blocking=True).to(torch.int16).contiguous()
+        t = tt.to(dev, non_blocking=True).to(torch.float64).contiguous()
+        p = pt.to(dev, non_blocking=True).to(torch.uint8).contiguous()
+        out = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        flags = E.variant_flag() | _lib.AUTO_SPAN
+        ws = _lib.scratch("voxel_ws", L.evk_voxel_workspace_bytes(B, H, W, flags), dev)
+        oob = _lib.oob_counter(dev)
+        _lib.check(L.evk_voxel_packed_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), x.shape[0], 0.0, 1.0, B, H, W,
+                                          flags, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.ptr(oob), _lib.stream()))
+        E.raise_if_oob(oob, "voxel grid", (B, H, W))
+    return out if out.device == device else out.to(device)
+
+
 def events_to_neg_pos_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240), temporal_bilinear=True):
     """
     Positive and negative events in separate voxel grids; drop-in for voxel_grid.py:155-182

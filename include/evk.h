@@ -113,6 +113,15 @@ int evk_voxel_aos_f32(const float *ev, int64_t n, float t0, float dt, int B, int
                       unsigned flags, float *out, void *workspace, size_t workspace_bytes,
                       unsigned long long *oob, void *stream);
 
+/* Same, events in the reference's STORAGE layout (row f4): int16 x, int16 y, float64 t, bool/uint8 p as
+ * the HDF5 and memmap formats hold them (lib/data_formats/event_packagers.py:90-93,
+ * h5_to_memmap.py:115-117), polarity mapped p*2-1 like the loaders do (hdf5_dataset.py:22,
+ * memmap_dataset.py:24).  Timestamps are made relative to t_first in float64, then cast to float32;
+ * dt = (float)(t_last - t_first).  13 B/event instead of 16 and no host-side casts. */
+int evk_voxel_packed_f32(const int16_t *x, const int16_t *y, const double *t, const uint8_t *p, int64_t n,
+                         double t_first, double t_last, int B, int H, int W, unsigned flags, float *out,
+                         void *workspace, size_t workspace_bytes, unsigned long long *oob, void *stream);
+
 /* Batched windows (voxel_grids_fixed_n_torch, voxel_grid.py:37-57; BaseVoxelDataset windows,
  * base_dataset.py:322-367): window w covers events [offsets[w], offsets[w+1]) and writes
  * out[w] ([n_windows][B][H][W]); t0/dt per window are taken from the window's first / last

@@ -181,6 +181,28 @@ def test_data_loader_arrays(oracle):
     assert torch.isnan(out[:, 0, 0]).all() and int(torch.isnan(out).sum()) == 5
 
 
+def test_packed_storage_layout(oracle):
+    """int16 / int16 / float64 / bool arrays as stored on disk -> the same grid as the cast float32 path."""
+    import event_utils_b200 as eu
+    from event_utils_b200.representations.voxel_grid import events_to_voxel_packed
+    x, y, t, p = make_events(51, 1_300_001, 260, 346)
+    xi, yi = x.astype(np.int16), y.astype(np.int16)
+    t64 = t.astype(np.float64) * 0.2 + 1.7e9
+    pb = p > 0
+    rel = (t64 - t64[0]).astype(np.float32)
+    ref = oracle.voxel_f32(xi, yi, rel, np.where(pb, 1.0, -1.0).astype(np.float32), 5, (260, 346), t0=0.0, dt=rel[-1])
+    for variant in VARIANTS:
+        eu.config.variant = variant
+        out = events_to_voxel_packed(xi, yi, t64, pb, 5, sensor_size=(260, 346))
+        assert not out.is_cuda
+        assert_close_to_max(out.numpy(), ref, 1e-5, variant)
+    out = events_to_voxel_packed(*dev(xi, yi, t64, pb.astype(np.uint8)), 5, sensor_size=(260, 346))
+    assert out.is_cuda
+    assert_close_to_max(out.cpu().numpy(), ref, 1e-5)
+    with pytest.raises(IndexError):
+        events_to_voxel_packed(np.int16([400, 1]), np.int16([1, 1]), np.float64([0, 1]), np.uint8([1, 0]), 3, sensor_size=(260, 346))
+
+
 def test_numpy_flavour_and_negpos(oracle):
     from event_utils_b200.representations.voxel_grid import (events_to_neg_pos_voxel_torch, events_to_voxel)
     g = golden("voxel_numpy")
