@@ -387,6 +387,26 @@ def run_ours(args, rank, local_rank, world):
     assert abs(float(res.double().sum()) - expect) <= 1e-6 * n * world + 4.0
     e2e_value = n * world * e2e_steps / e2e_s / 1e6
     del hx, hy, ht, hp
+    e2e_packed = None
+    if world == 1:
+        # the same call from the reference's STORAGE layout (int16 x,y / float64 t / uint8 p, 13 B/event,
+        # event_packagers.py:90-93): what a data loader would hand over without its host-side casts
+        from event_utils_b200.representations.voxel_grid import events_to_voxel_packed
+        px = torch.empty(n, dtype=torch.int16, pin_memory=True); px.copy_(x.to(torch.int16))
+        py = torch.empty(n, dtype=torch.int16, pin_memory=True); py.copy_(y.to(torch.int16))
+        pt_ = torch.empty(n, dtype=torch.float64, pin_memory=True); pt_.copy_(t.double() + 1.6e9)
+        pp = torch.empty(n, dtype=torch.uint8, pin_memory=True); pp.copy_((p > 0).to(torch.uint8))
+        torch.cuda.synchronize()
+        for _ in range(2):
+            resp = events_to_voxel_packed(px, py, pt_, pp, B, sensor_size=(H, W))
+        sp = time.perf_counter()
+        for _ in range(e2e_steps):
+            resp = events_to_voxel_packed(px, py, pt_, pp, B, sensor_size=(H, W))
+        tp = time.perf_counter() - sp
+        assert abs(float(resp.double().sum()) - expect) <= 1e-6 * n + 4.0
+        e2e_packed = {"value": n * e2e_steps / tp / 1e6, "unit": "Mevents/s", "h2d_bytes_per_step": 13 * n,
+                      "d2h_bytes_per_step": 4 * B * H * W, "api": "events_to_voxel_packed(pinned int16/int16/float64/uint8) -> CPU tensor"}
+        del px, py, pt_, pp
 
     extra, cpu = {}, None
     if rank == 0 and world == 1:
@@ -423,6 +443,9 @@ def run_ours(args, rank, local_rank, world):
                          "step_frac": (alg_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
         }
+        if e2e_packed:
+            extra = dict(extra or {})
+            extra["e2e_storage_layout"] = e2e_packed
         if extra:
             line["extra"] = extra
         sys.stdout.flush()

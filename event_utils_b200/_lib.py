@@ -110,6 +110,8 @@ def _declare(L):
     L.evk_pipeline_create.argtypes = [c.POINTER(vp), i64]
     L.evk_pipeline_destroy.restype = None
     L.evk_pipeline_destroy.argtypes = [vp]
+    L.evk_voxel_host_packed_f32.restype = ci
+    L.evk_voxel_host_packed_f32.argtypes = [vp, vp, vp, vp, vp, i64, f64, f64, ci, ci, ci, cu, vp, c.POINTER(c.c_ulonglong)]
     L.evk_voxel_host_f32.restype = ci
     L.evk_voxel_host_f32.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, ci, ci, ci, cu, vp, c.POINTER(c.c_ulonglong)]
 

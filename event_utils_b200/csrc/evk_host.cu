@@ -34,7 +34,8 @@ int evk_pipeline_create(evk_pipeline_t **out, int64_t chunk_events)
     if (!p) { set_error("evk_pipeline_create: out of host memory"); return EVK_E_ARG; }
     p->chunk = chunk_events;
     for (int s = 0; s < 2; ++s)
-        for (int a = 0; a < 4; ++a) EVK_CUDA(cudaMalloc(&p->stage[s][a], (size_t)chunk_events * sizeof(float)));
+        for (int a = 0; a < 4; ++a)   // slot 2 (timestamps) is 8 bytes wide so that it can also stage float64 stamps
+            EVK_CUDA(cudaMalloc(&p->stage[s][a], (size_t)chunk_events * (a == 2 ? sizeof(double) : sizeof(float))));
     EVK_CUDA(cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking));
     EVK_CUDA(cudaStreamCreateWithFlags(&p->compute, cudaStreamNonBlocking));
     for (int s = 0; s < 2; ++s) {
@@ -110,6 +111,54 @@ int evk_voxel_host_f32(evk_pipeline_t *p, const float *x, const float *y, const 
         ++k;
     }
     EVK_CUDA(cudaMemcpyAsync(out_host, p->grid, grid_bytes, cudaMemcpyDefault, p->compute));  // out may be host or device
+    EVK_CUDA(cudaMemcpyAsync(p->oob_pinned, p->oob_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->compute));
+    EVK_CUDA(cudaStreamSynchronize(p->compute));
+    if (oob_host) *oob_host = *p->oob_pinned;
+    return EVK_OK;
+}
+
+// Same pipeline for the storage layout (int16 x, int16 y, float64 t, uint8 p): 13 B/event cross PCIe
+// instead of 16, and the casts happen on the device (evk_voxel_packed_f32).
+int evk_voxel_host_packed_f32(evk_pipeline_t *p, const int16_t *x, const int16_t *y, const double *t, const uint8_t *pol,
+                              int64_t n, double t_first, double t_last, int B, int H, int W, unsigned flags, float *out_host,
+                              unsigned long long *oob_host)
+{
+    using namespace evk;
+    if (!p || !out_host || n < 0 || B < 1 || H < 1 || W < 1 || (n > 0 && (!x || !y || !t || !pol))) {
+        set_error("evk_voxel_host_packed_f32: bad arguments");
+        return EVK_E_ARG;
+    }
+    const size_t grid_bytes = (size_t)B * H * W * sizeof(float);
+    if (p->grid_bytes < grid_bytes) {
+        cudaFree(p->grid);
+        p->grid = nullptr; p->grid_bytes = 0;
+        EVK_CUDA(cudaMalloc(&p->grid, grid_bytes));
+        p->grid_bytes = grid_bytes;
+    }
+    EVK_CUDA(cudaMemsetAsync(p->oob_dev, 0, sizeof(unsigned long long), p->compute));
+    EVK_CUDA(cudaMemsetAsync(p->grid, 0, grid_bytes, p->compute));
+    const unsigned cflags = (flags & ~(EVK_VARIANT_MASK | EVK_AUTO_SPAN)) | EVK_ACCUMULATE | EVK_VARIANT_GLOBAL_RED;
+    int64_t done = 0;
+    int k = 0;
+    while (done < n) {
+        const int s = k & 1;
+        const int64_t m = (n - done < p->chunk) ? (n - done) : p->chunk;
+        if (k >= 2) EVK_CUDA(cudaStreamWaitEvent(p->copy, p->consumed[s], 0));
+        EVK_CUDA(cudaMemcpyAsync(p->stage[s][0], x + done, (size_t)m * sizeof(int16_t), cudaMemcpyHostToDevice, p->copy));
+        EVK_CUDA(cudaMemcpyAsync(p->stage[s][1], y + done, (size_t)m * sizeof(int16_t), cudaMemcpyHostToDevice, p->copy));
+        EVK_CUDA(cudaMemcpyAsync(p->stage[s][2], t + done, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, p->copy));
+        EVK_CUDA(cudaMemcpyAsync(p->stage[s][3], pol + done, (size_t)m * sizeof(uint8_t), cudaMemcpyHostToDevice, p->copy));
+        EVK_CUDA(cudaEventRecord(p->copied[s], p->copy));
+        EVK_CUDA(cudaStreamWaitEvent(p->compute, p->copied[s], 0));
+        int rc = evk_voxel_packed_f32((const int16_t *)p->stage[s][0], (const int16_t *)p->stage[s][1], (const double *)p->stage[s][2],
+                                      (const uint8_t *)p->stage[s][3], m, t_first, t_last, B, H, W, cflags, p->grid, nullptr, 0,
+                                      p->oob_dev, p->compute);
+        if (rc) return rc;
+        EVK_CUDA(cudaEventRecord(p->consumed[s], p->compute));
+        done += m;
+        ++k;
+    }
+    EVK_CUDA(cudaMemcpyAsync(out_host, p->grid, grid_bytes, cudaMemcpyDefault, p->compute));
     EVK_CUDA(cudaMemcpyAsync(p->oob_pinned, p->oob_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->compute));
     EVK_CUDA(cudaStreamSynchronize(p->compute));
     if (oob_host) *oob_host = *p->oob_pinned;

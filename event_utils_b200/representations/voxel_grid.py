@@ -146,6 +146,19 @@ def events_to_voxel_packed(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240
     device = torch.device(device)
     dev = E.compute_device(xt, yt, tt, pt)
     H, W, B = int(sensor_size[0]), int(sensor_size[1]), int(B)
+    pb = pt.view(torch.uint8) if pt.dtype == torch.bool else pt
+    if (not xt.is_cuda and xt.dtype == torch.int16 and yt.dtype == torch.int16 and tt.dtype == torch.float64
+            and pb.dtype == torch.uint8 and all(a.is_contiguous() for a in (xt, yt, tt, pb))):
+        # host arrays in the storage dtypes: chunked, double-buffered H2D of the RAW 13 B/event
+        with torch.cuda.device(dev):
+            out = torch.empty((B, H, W), dtype=torch.float32, pin_memory=True)
+            bad = ctypes.c_ulonglong(0)
+            _lib.check(L.evk_voxel_host_packed_f32(_lib.pipeline(), _lib.ptr(xt), _lib.ptr(yt), _lib.ptr(tt), _lib.ptr(pb),
+                                                   xt.shape[0], float(tt[0]), float(tt[-1]), B, H, W, 0, _lib.ptr(out),
+                                                   ctypes.byref(bad)))
+        if bad.value and config.check_index_errors:
+            raise IndexError("%d events index outside the voxel grid of shape %s" % (bad.value, (B, H, W)))
+        return out if device.type == "cpu" else out.to(device)
     with torch.cuda.device(dev):
         x = xt.to(dev, non_blocking=True).to(torch.int16).contiguous()
         y = yt.to(dev, non_blocking=True).to(torch.int16).contiguous()

@@ -299,6 +299,10 @@ void evk_pipeline_destroy(evk_pipeline_t *pipe);
 int evk_voxel_host_f32(evk_pipeline_t *pipe, const float *x, const float *y, const float *t,
                        const float *p, int64_t n, float t0, float dt, int B, int H, int W,
                        unsigned flags, float *out_host, unsigned long long *oob_host);
+/* the same for host arrays in the storage layout (see evk_voxel_packed_f32): 13 B/event over PCIe */
+int evk_voxel_host_packed_f32(evk_pipeline_t *pipe, const int16_t *x, const int16_t *y, const double *t,
+                              const uint8_t *p, int64_t n, double t_first, double t_last, int B, int H,
+                              int W, unsigned flags, float *out_host, unsigned long long *oob_host);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -196,6 +196,9 @@ def test_packed_storage_layout(oracle):
         out = events_to_voxel_packed(xi, yi, t64, pb, 5, sensor_size=(260, 346))
         assert not out.is_cuda
         assert_close_to_max(out.numpy(), ref, 1e-5, variant)
+    # contiguous host tensors in the storage dtypes take the chunked H2D pipeline
+    out = events_to_voxel_packed(*(torch.from_numpy(a) for a in (xi, yi, t64, pb)), 5, sensor_size=(260, 346))
+    assert_close_to_max(out.numpy(), ref, 1e-5)
     out = events_to_voxel_packed(*dev(xi, yi, t64, pb.astype(np.uint8)), 5, sensor_size=(260, 346))
     assert out.is_cuda
     assert_close_to_max(out.cpu().numpy(), ref, 1e-5)
