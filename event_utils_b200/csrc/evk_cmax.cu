@@ -257,11 +257,12 @@ __global__ void __launch_bounds__(256) cmax_scatter_batch_kernel(const CmaxArgs 
 __device__ __forceinline__ void block_add(double v, double *dst)
 {
     __shared__ double part[8];
+    const int lt = threadIdx.y * blockDim.x + threadIdx.x;   // blocks are 256 threads, 1-D or 32x8
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();  // protect `part` against the previous call's readers
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+    if ((lt & 31) == 0) part[lt >> 5] = v;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (lt == 0) {
         double s = 0.0;
         for (int w = 0; w < 8; ++w) s += part[w];
         atomicAdd(dst, s);
@@ -511,6 +512,118 @@ __global__ void cmax_obj_final_kernel(int kind, const double *gsums, const unsig
     result[11] = gsums[3];
 }
 
+// ---- fused variance tail: gather + both blur axes + all sums + the final scalars in ONE launch ---
+// One CTA = an 8x32 tile of pixels.  It gathers the tile plus a halo of `r` pixels (reflected at the image
+// border, like scipy's mode='reflect') straight from the block accumulator into shared memory, blurs
+// vertically then horizontally with the same f64-accumulate / f32-store rounding as the separate kernels,
+// reduces the seven sums, and the last CTA to finish (ticket counter) writes the result.  Replaces four
+// launches (gather, blur axis 0, blur axis 1 + sums, final) -- at BFGS problem sizes (1e4..1e6 events) the
+// evaluation is launch-bound.
+constexpr int kTileY = 8, kTileX = 32, kFusedMaxR = 8;
+
+__device__ __forceinline__ float gather_pixel(const float *acc, int replicas, int Hc, int Wc, int y, int x, int comp)
+{
+    // comp 0: I, 1: D0, 2: D1 (see cmax_gather_kernel for the block / sign conventions)
+    const int64_t npix = (int64_t)Hc * Wc;
+    float v = 0.f;
+    for (int r = 0; r < replicas; ++r) {
+        const float *base = acc + (int64_t)r * npix * kBlockFloats;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int by = y - (k >> 1), bx = x - (k & 1);
+            if (by < 0 || bx < 0) continue;
+            const float *blk = base + ((int64_t)by * Wc + bx) * kBlockFloats;
+            if (comp == 0) v += blk[k];
+            else if (comp == 1) v += (k == 0) ? -blk[4] : (k == 1) ? blk[4] : (k == 2) ? -blk[5] : blk[5];
+            else v += (k == 0) ? -blk[6] : (k == 1) ? -blk[7] : (k == 2) ? blk[6] : blk[7];
+        }
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel(const float *__restrict__ acc, int replicas, int Hc, int Wc,
+                                                                              const BlurTaps taps, int do_blur, int want_grad,
+                                                                              double mix_a, double mix_b, float *__restrict__ iwe_out,
+                                                                              float *__restrict__ diwe_out, double *sums,
+                                                                              unsigned *ticket, const unsigned long long *oob,
+                                                                              double *result)
+{
+    __shared__ float tileI[(kTileY + 2 * kFusedMaxR) * (kTileX + 2 * kFusedMaxR)];
+    __shared__ float tileT[kTileY * (kTileX + 2 * kFusedMaxR)];
+    const int r = do_blur ? taps.r : 0;
+    const int hw = kTileX + 2 * r, hh = kTileY + 2 * r;
+    const int y0 = blockIdx.y * kTileY, x0 = blockIdx.x * kTileX;
+    const int tid = threadIdx.y * kTileX + threadIdx.x;
+    // 1. halo tile of the un-blurred IWE
+    for (int j = tid; j < hh * hw; j += kTileY * kTileX) {
+        const int ly = j / hw, lx = j - ly * hw;
+        tileI[j] = gather_pixel(acc, replicas, Hc, Wc, reflect_idx(y0 - r + ly, Hc), reflect_idx(x0 - r + lx, Wc), 0);
+    }
+    const int y = y0 + threadIdx.y, x = x0 + threadIdx.x;
+    const bool inside = y < Hc && x < Wc;
+    float vi = 0.f, d0 = 0.f, d1 = 0.f;
+    if (inside) {
+        d0 = gather_pixel(acc, replicas, Hc, Wc, y, x, 1);
+        d1 = gather_pixel(acc, replicas, Hc, Wc, y, x, 2);
+    }
+    __syncthreads();
+    if (inside) {
+        vi = tileI[(threadIdx.y + r) * hw + threadIdx.x + r];
+        const int64_t npix = (int64_t)Hc * Wc, i = (int64_t)y * Wc + x;
+        if (iwe_out) iwe_out[i] = vi;
+        if (diwe_out) { diwe_out[i] = d0; diwe_out[npix + i] = d1; }
+    }
+    double g = (double)vi;
+    if (do_blur) {
+        // 2. axis 0 (vertical), every column of the halo; rounded to f32 like scipy's intermediate array
+        for (int j = tid; j < kTileY * hw; j += kTileY * kTileX) {
+            const int ly = j / hw, lx = j - ly * hw;
+            const float *col = tileI + (ly + r) * hw + lx;
+            double a = (double)col[0] * taps.w[0];
+            for (int k = 1; k <= r; ++k) a += ((double)col[-k * hw] + (double)col[k * hw]) * taps.w[k];
+            tileT[j] = (float)a;
+        }
+        __syncthreads();
+        // 3. axis 1 (horizontal)
+        const float *row = tileT + threadIdx.y * hw + threadIdx.x + r;
+        double a = (double)row[0] * taps.w[0];
+        for (int k = 1; k <= r; ++k) a += ((double)row[-k] + (double)row[k]) * taps.w[k];
+        g = (double)(float)a;
+    }
+    if (!inside) { g = 0.0; vi = 0.f; }
+    // 4. the seven sums (same slots as the separate kernels)
+    block_add((double)vi, sums + 0);
+    block_add(g, sums + 1);
+    block_add(g * g, sums + 2);
+    block_add(g * (double)d0, sums + 3);
+    block_add(g * (double)d1, sums + 4);
+    block_add((double)d0, sums + 5);
+    block_add((double)d1, sums + 6);
+    // 5. last CTA writes the result
+    __shared__ bool last;
+    if (tid == 0) {
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (last && tid == 0) {
+        __threadfence();
+        double s[7];
+        for (int k = 0; k < 7; ++k) s[k] = atomicAdd(sums + k, 0.0);   // read through L2
+        const double P = (double)Hc * (double)Wc;
+        const double mean_g = s[1] / P, var = s[2] / P - mean_g * mean_g, mu = s[0] / P;
+        const double g0 = -2.0 * (s[3] - mu * s[5]) / P, g1 = -2.0 * (s[4] - mu * s[6]) / P;
+        result[0] = -var;
+        result[1] = want_grad ? (mix_a * g0 + mix_b * g1) : 0.0;
+        result[2] = want_grad ? (mix_b * g0 + mix_a * g1) : 0.0;
+        result[3] = s[0];
+        result[4] = (double)(*oob);
+        result[5] = var;
+        result[6] = g0;
+        result[7] = g1;
+    }
+}
+
 struct CmaxWorkspace {
     float *acc, *I, *D0, *D1, *tmp, *G;
     double *w, *wt;             // generic objectives: per-pixel weight image and its axis-0 blur
@@ -528,6 +641,12 @@ static size_t carve(void *base, int Hs, int Ws, CmaxWorkspace *ws)
     size_t off = 0;
     char *b = static_cast<char *>(base);
     auto take = [&](size_t bytes) { char *p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
+    // the small counters come first and are directly followed by the accumulator, so that ONE memset
+    // zeroes counters + the R replicas an evaluation uses
+    double *gsums = (double *)take(8 * sizeof(double));
+    unsigned *gmax = (unsigned *)take(sizeof(unsigned));
+    double *sums = (double *)take(8 * sizeof(double));
+    unsigned long long *oob = (unsigned long long *)take(sizeof(unsigned long long));
     float *acc = (float *)take(npix * kBlockFloats * sizeof(float) * (kMaxCandidates > kMaxReplicas ? kMaxCandidates : kMaxReplicas));
     float *I = (float *)take(npix * sizeof(float));
     float *D0 = (float *)take(npix * sizeof(float));
@@ -536,11 +655,6 @@ static size_t carve(void *base, int Hs, int Ws, CmaxWorkspace *ws)
     float *G = (float *)take(npix * sizeof(float));
     double *w = (double *)take(npix * sizeof(double));
     double *wt = (double *)take(npix * sizeof(double));
-    // the four small counters below are contiguous (256-byte slots) and zeroed by one memset
-    double *gsums = (double *)take(8 * sizeof(double));
-    unsigned *gmax = (unsigned *)take(sizeof(unsigned));
-    double *sums = (double *)take(8 * sizeof(double));
-    unsigned long long *oob = (unsigned long long *)take(sizeof(unsigned long long));
     if (ws) {
         ws->acc = acc; ws->I = I; ws->D0 = D0; ws->D1 = D1; ws->tmp = tmp; ws->G = G; ws->w = w; ws->wt = wt;
         ws->gsums = gsums; ws->gmax = gmax; ws->sums = sums; ws->oob = oob;
@@ -628,13 +742,30 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, int objective, dou
     A.replicas = R;
     A.acc = ws.acc;
     A.oob = ws.oob;
-    EVK_CUDA(cudaMemsetAsync(ws.acc, 0, (size_t)R * npix * kBlockFloats * sizeof(float), st));
-    EVK_CUDA(cudaMemsetAsync(ws.gsums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.gsums), st));  // gsums, gmax, sums, oob are adjacent
+    // counters (gsums, gmax, sums, oob) and the R accumulator replicas are contiguous: one memset
+    EVK_CUDA(cudaMemsetAsync(ws.gsums, 0, (size_t)((char *)ws.acc - (char *)ws.gsums) + (size_t)R * npix * kBlockFloats * sizeof(float), st));
     if (A.n > 0) {
         ProfScope prof(st);
         prof_count(1);
         if (grad) cmax_scatter_kernel<WARP, true><<<grid_for(cmax_scatter_kernel<WARP, true>, 256, A.n, 256 * 4), 256, 0, st>>>(A);
         else cmax_scatter_kernel<WARP, false><<<grid_for(cmax_scatter_kernel<WARP, false>, 256, A.n, 256 * 4), 256, 0, st>>>(A);
+    }
+    if (objective == OBJ_VARIANCE && (sigma <= 0.0 || (int)(4.0 * sigma + 0.5) <= kFusedMaxR)) {
+        // launch-bound regime matters most here: gather + blur + sums + final in one kernel
+        BlurTaps taps{};
+        double mix_a = 1.0, mix_b = 0.0;
+        const int do_blur = sigma > 0.0;
+        if (do_blur) {
+            int rc = make_taps(sigma, &taps);
+            if (rc) return rc;
+            if (!(flags & EVK_CMAX_NO_CHANNEL_MIX)) mix_coeffs(taps, &mix_a, &mix_b);
+        }
+        prof_count(1);
+        dim3 tgrid((A.Wc + kTileX - 1) / kTileX, (A.Hc + kTileY - 1) / kTileY), tblock(kTileX, kTileY);
+        cmax_fused_var_tail_kernel<<<tgrid, tblock, 0, st>>>(ws.acc, R, A.Hc, A.Wc, taps, do_blur, grad ? 1 : 0, mix_a, mix_b, iwe_out,
+                                                               diwe_out, ws.sums, ws.gmax, ws.oob, result);
+        EVK_CUDA(cudaGetLastError());
+        return EVK_OK;
     }
     prof_count(1);
     cmax_gather_kernel<<<(npix + 255) / 256, 256, 0, st>>>(ws.acc, R, A.Hc, A.Wc, ws.I, ws.D0, ws.D1, iwe_out, diwe_out, ws.sums);
