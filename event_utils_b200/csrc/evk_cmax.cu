@@ -38,6 +38,7 @@ namespace evk {
 
 constexpr int kMaxRadius = 64;
 constexpr int kMaxReplicas = 8;
+constexpr int kMaxCandidates = 32;  // parameter points per batched evaluation
 constexpr int kBlockFloats = 8;   // one 32-byte block (= one L2 sector) per pixel: {I_TL, I_TR, I_BL, I_BR, a, b, c, d}
 
 struct BlurTaps {
@@ -226,7 +227,6 @@ __global__ void __launch_bounds__(256) cmax_scatter_kernel(const CmaxArgs A)
 
 // K candidate parameter points in ONE pass over the events (grid_search_initial evaluates 25 points per
 // level, events_cmax.py:241-311): every event is loaded once and splatted into K accumulators.
-constexpr int kMaxCandidates = 32;
 struct Candidates {
     int n;
     double vx[kMaxCandidates], vy[kMaxCandidates];
@@ -550,6 +550,11 @@ __global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel(con
 {
     __shared__ float tileI[(kTileY + 2 * kFusedMaxR) * (kTileX + 2 * kFusedMaxR)];
     __shared__ float tileT[kTileY * (kTileX + 2 * kFusedMaxR)];
+    // blockIdx.z = candidate index of a batched evaluation: its own accumulator, sums, ticket and result
+    acc += (size_t)blockIdx.z * (size_t)Hc * Wc * kBlockFloats * replicas;
+    sums += 8 * blockIdx.z;
+    ticket += blockIdx.z;
+    result += 12 * blockIdx.z;
     const int r = do_blur ? taps.r : 0;
     const int hw = kTileX + 2 * r, hh = kTileY + 2 * r;
     const int y0 = blockIdx.y * kTileY, x0 = blockIdx.x * kTileX;
@@ -626,6 +631,8 @@ __global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel(con
 
 struct CmaxWorkspace {
     float *acc, *I, *D0, *D1, *tmp, *G;
+    double *bsums;              // [kMaxCandidates][8] sums of a batched evaluation
+    unsigned *btickets;         // [kMaxCandidates]
     double *w, *wt;             // generic objectives: per-pixel weight image and its axis-0 blur
     double *gsums;              // 8 doubles (generic objectives)
     unsigned *gmax;             // order-preserving encoding of max(G)
@@ -643,6 +650,8 @@ static size_t carve(void *base, int Hs, int Ws, CmaxWorkspace *ws)
     auto take = [&](size_t bytes) { char *p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
     // the small counters come first and are directly followed by the accumulator, so that ONE memset
     // zeroes counters + the R replicas an evaluation uses
+    double *bsums = (double *)take(kMaxCandidates * 8 * sizeof(double));
+    unsigned *btickets = (unsigned *)take(kMaxCandidates * sizeof(unsigned));
     double *gsums = (double *)take(8 * sizeof(double));
     unsigned *gmax = (unsigned *)take(sizeof(unsigned));
     double *sums = (double *)take(8 * sizeof(double));
@@ -657,7 +666,7 @@ static size_t carve(void *base, int Hs, int Ws, CmaxWorkspace *ws)
     double *wt = (double *)take(npix * sizeof(double));
     if (ws) {
         ws->acc = acc; ws->I = I; ws->D0 = D0; ws->D1 = D1; ws->tmp = tmp; ws->G = G; ws->w = w; ws->wt = wt;
-        ws->gsums = gsums; ws->gmax = gmax; ws->sums = sums; ws->oob = oob;
+        ws->gsums = gsums; ws->gmax = gmax; ws->sums = sums; ws->oob = oob; ws->bsums = bsums; ws->btickets = btickets;
     }
     return off;
 }
@@ -931,14 +940,31 @@ int evk_cmax_linvel_objective_batch_f64(const double *x, const double *y, const 
     Candidates C{};
     C.n = n_params;
     for (int k = 0; k < n_params; ++k) { C.vx[k] = params_host[2 * k]; C.vy[k] = params_host[2 * k + 1]; }
-    EVK_CUDA(cudaMemsetAsync(ws.acc, 0, (size_t)n_params * npix * kBlockFloats * sizeof(float), st));
-    EVK_CUDA(cudaMemsetAsync(ws.oob, 0, sizeof(unsigned long long), st));
+    // bsums, btickets, gsums, gmax, sums, oob and the accumulators are contiguous: one memset
+    EVK_CUDA(cudaMemsetAsync(ws.bsums, 0, (size_t)((char *)ws.acc - (char *)ws.bsums) + (size_t)n_params * npix * kBlockFloats * sizeof(float), st));
     if (n > 0) {
         ProfScope prof(st);
         prof_count(1);
         if (grad) cmax_scatter_batch_kernel<WARP_LINVEL_F64, true><<<grid_for(cmax_scatter_batch_kernel<WARP_LINVEL_F64, true>, 256, n, 256 * 2), 256, 0, st>>>(A, C);
         else cmax_scatter_batch_kernel<WARP_LINVEL_F64, false><<<grid_for(cmax_scatter_batch_kernel<WARP_LINVEL_F64, false>, 256, n, 256 * 2), 256, 0, st>>>(A, C);
         EVK_CUDA(cudaGetLastError());
+    }
+    if (objective == OBJ_VARIANCE && (sigma <= 0.0 || (int)(4.0 * sigma + 0.5) <= kFusedMaxR)) {
+        // all candidates' tails in ONE launch (blockIdx.z = candidate)
+        BlurTaps taps{};
+        double mix_a = 1.0, mix_b = 0.0;
+        const int do_blur = sigma > 0.0;
+        if (do_blur) {
+            int rc = make_taps(sigma, &taps);
+            if (rc) return rc;
+            if (!(flags & EVK_CMAX_NO_CHANNEL_MIX)) mix_coeffs(taps, &mix_a, &mix_b);
+        }
+        prof_count(1);
+        dim3 tgrid((A.Wc + kTileX - 1) / kTileX, (A.Hc + kTileY - 1) / kTileY, n_params), tblock(kTileX, kTileY);
+        cmax_fused_var_tail_kernel<<<tgrid, tblock, 0, st>>>(ws.acc, 1, A.Hc, A.Wc, taps, do_blur, grad ? 1 : 0, mix_a, mix_b, nullptr,
+                                                               nullptr, ws.bsums, ws.btickets, ws.oob, results);
+        EVK_CUDA(cudaGetLastError());
+        return EVK_OK;
     }
     for (int k = 0; k < n_params; ++k) {
         // per-candidate image-space tail on the shared scratch images (stream-ordered)

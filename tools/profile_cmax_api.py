@@ -45,3 +45,20 @@ for n in (15_000, 1_000_000):
     sync_each = (time.perf_counter() - t0) / K
     print("n=%8d  api %.1f us/eval | fingerprint+cache %.1f us | C call (async, back to back) %.1f us, GPU-bound %.1f us | C call + D2H sync each %.1f us"
           % (n, tot * 1e6, fp * 1e6, launch * 1e6, gpu_total * 1e6, sync_each * 1e6))
+
+# grid search: 25 candidates in one pass vs 25 separate evaluations
+from event_utils_b200.contrast_max.events_cmax import grid_search_initial
+for n in (15_000, 1_000_000):
+    xs, ys = rng.random(n) * 239, rng.random(n) * 179
+    ts, ps = np.sort(rng.random(n)) * 0.1, rng.integers(0, 2, n) * 2.0 - 1
+    obj, warp = O.variance_objective(), linvel_warp()
+    grid_search_initial(xs, ys, ts, ps, warp, obj, (180, 240))
+    t0 = time.perf_counter()
+    for _ in range(20):
+        out = grid_search_initial(xs, ys, ts, ps, warp, obj, (180, 240))
+    tb = (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ev = [obj.evaluate_function(p, xs, ys, ts, ps, warp, (180, 240), 1.0) for p in out["params"]]
+    tl = (time.perf_counter() - t0) / 20
+    print("n=%8d  grid_search_initial (25 points): batched %.0f us, one evaluation per point %.0f us" % (n, tb * 1e6, tl * 1e6))
