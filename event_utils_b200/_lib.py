@@ -106,6 +106,10 @@ def _declare(L):
     L.evk_variance_objective_f32.argtypes = [vp, vp, ci, ci, f64, cu, vp, vp, sz, vp]
     L.evk_cmax_flow_variance_f32.restype = ci
     L.evk_cmax_flow_variance_f32.argtypes = [vp, vp, vp, vp, i64, vp, f32, ci, ci, f64, cu, vp, vp, vp, sz, vp]
+    L.evk_robust_norm_workspace_bytes.restype = sz
+    L.evk_robust_norm_workspace_bytes.argtypes = []
+    L.evk_robust_norm_f32.restype = ci
+    L.evk_robust_norm_f32.argtypes = [vp, i64, i64, i64, vp, vp, vp, sz, vp]
     L.evk_pipeline_create.restype = ci
     L.evk_pipeline_create.argtypes = [c.POINTER(vp), i64]
     L.evk_pipeline_destroy.restype = None

@@ -287,6 +287,18 @@ int evk_cmax_flow_variance_f32(const float *x, const float *y, const float *t, c
                                size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * RobustNorm (row f4): clamp a tensor between two of its order statistics and rescale it.  Replaces
+ * RobustNorm.__call__ / .percentile, lib/data_loaders/data_augmentation.py:82-130 (two kthvalue sorts),
+ * the step after the voxel grid in the loaders (base_dataset.py:471).
+ *   k_low / k_top: 1-based ranks, k = 1 + round(.01 q (n-1)) computed by the caller (:100)
+ *   out = x if both statistics are 0, else (clamp(x, t_min, t_max) - t_min) / (t_max + 1e-6)
+ *   t_min_max: optional 2 floats on the device receiving the two statistics.
+ * --------------------------------------------------------------------------------------------- */
+size_t evk_robust_norm_workspace_bytes(void);
+int evk_robust_norm_f32(const float *x, int64_t n, int64_t k_low, int64_t k_top, float *out,
+                        float *t_min_max, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer pipeline: the same voxel build for events living in HOST memory (pinned memory
  * gives full PCIe bandwidth).  Events are streamed in chunks through a double-buffered device
  * staging area so the H2D copy of chunk k+1 overlaps the scatter of chunk k; the finished grid

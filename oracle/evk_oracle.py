@@ -209,3 +209,20 @@ def bounds_mask(xs, ys, x_min, x_max, y_min, y_max):
     m = np.empty_like(x)
     lib().evo_bounds_mask_f64(_p(x), _p(y), x.shape[0], x_min, x_max, y_min, y_max, _p(m))
     return m
+
+
+def robust_norm_f32(x, low_perc=0, top_perc=95):
+    """RobustNorm.__call__, data_augmentation.py:82-130 (numpy restatement: exact order statistics via
+    np.partition, f32 clamp / subtract / divide)."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    flat = a.reshape(-1)
+
+    def kth(q):
+        k = 1 + round(.01 * float(q) * (flat.size - 1))
+        return np.float32(np.partition(flat, k - 1)[k - 1])
+    t_max, t_min = kth(top_perc), kth(low_perc)
+    if t_max == 0 and t_min == 0:
+        return a.copy()
+    c = np.clip(a, t_min, t_max)
+    return ((c - c.min()) / np.float32(c.max() + np.float32(1e-6))).astype(np.float32)
+

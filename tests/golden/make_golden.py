@@ -276,3 +276,19 @@ for name, o in objs.items():
             cases["%s_%g_%g_%s" % (name, prm[0], prm[1], tag)] = np.array([f] + gr, dtype=np.float64)
 save("objectives", **cases)
 
+# ---- RobustNorm (data_augmentation.py:75-136) ----------------------------------------------------
+import importlib.util
+spec = importlib.util.spec_from_file_location("ref_data_augmentation", os.path.join(ref_loader.REF_ROOT, "lib/data_loaders/data_augmentation.py"))
+da = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(da)
+cases = {}
+rng = np.random.default_rng(61)
+v1 = torch.from_numpy(ref.voxel_grid.events_to_voxel_torch(*f32(*events(62, 30000, 60, 80)), 5, sensor_size=(60, 80)).numpy())
+v2 = torch.from_numpy(rng.standard_normal((3, 17, 23)).astype(np.float32))
+v3 = torch.zeros(2, 8, 8); v3[0, 1, 1] = 5.0          # 95th percentile and minimum are both 0 -> returned unchanged
+for tag, v, kw in (("voxel", v1, {}), ("normal", v2, dict(low_perc=10, top_perc=90)), ("sparse", v3, {})):
+    cases[tag + "_in"] = v.numpy()
+    cases[tag + "_out"] = da.RobustNorm(**kw)(v).numpy()
+    cases[tag + "_p"] = np.array([da.RobustNorm.percentile(v, q) for q in (0, 5, 50, 95, 100)])
+save("robust_norm", **cases)
+

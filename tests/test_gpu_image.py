@@ -235,3 +235,23 @@ def test_tap_helpers():
     i1, d1 = events_to_image_drv(g["drv_x"], g["drv_y"], g["drv_p"], None, None)
     assert d1 is None
     assert_close_to_max(i1, g["drv_img"], 1e-5)
+
+
+def test_robust_norm(oracle):
+    from event_utils_b200.data_loaders.data_augmentation import RobustNorm
+    g = golden("robust_norm")
+    for tag, kw in (("voxel", {}), ("normal", dict(low_perc=10, top_perc=90)), ("sparse", {})):
+        x = torch.from_numpy(g[tag + "_in"])
+        out = RobustNorm(**kw)(x.cuda())
+        assert out.is_cuda and out.shape == x.shape
+        assert_close_to_max(out.cpu().numpy(), g[tag + "_out"], 1e-6, tag)
+        assert not RobustNorm(**kw)(x).is_cuda                       # host tensor in -> host tensor out
+        got = [RobustNorm.percentile(x.cuda(), q) for q in (0, 5, 50, 95, 100)]
+        assert np.array_equal(np.float32(got), np.float32(g[tag + "_p"])), tag    # order statistics are exact
+    # a voxel-sized random tensor against the oracle, ranks straddling bin boundaries of all three passes
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((5, 480, 640)) * rng.choice([1e-3, 1.0, 300.0], size=(5, 480, 640))).astype(np.float32)
+    for kw in (dict(), dict(low_perc=1, top_perc=99.9), dict(low_perc=50, top_perc=50)):
+        out = RobustNorm(**kw)(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert_close_to_max(out, oracle.robust_norm_f32(x, **kw), 1e-6, str(kw))
+

@@ -148,3 +148,12 @@ def test_gaussian_matches_scipy(oracle):
         a = rng.standard_normal(shape).astype(np.float32)
         for sigma in (0.5, 1.0, 2.3):
             assert_close_to_max(oracle.gaussian_filter_f32(a, sigma), gaussian_filter(a, sigma), 1e-6, str(shape))
+
+
+def test_robust_norm(oracle):
+    g = golden("robust_norm")
+    for tag, kw in (("voxel", {}), ("normal", dict(low_perc=10, top_perc=90)), ("sparse", {})):
+        out = oracle.robust_norm_f32(g[tag + "_in"], **kw)
+        assert_close_to_max(out, g[tag + "_out"], 1e-7, tag)
+    assert np.array_equal(oracle.robust_norm_f32(g["sparse_in"]), g["sparse_in"])
+
