@@ -68,7 +68,6 @@ __global__ void __launch_bounds__(256) image_hot_kernel(const HotArgs A)
     V *gout = (MODE == HOT_COUNT) ? (V *)A.out_u32 : (MODE == HOT_BILINEAR && A.ws) ? (V *)A.ws : (V *)A.out;
     const int gs = (MODE == HOT_BILINEAR && A.ws) ? 4 : 1;
 
-    for (int s = threadIdx.x; s < kHotSlots; s += 256) { keys[s] = kEmpty; vals[s] = (V)0; }
     if (threadIdx.x == 0) dup_lanes = 0;
     __syncthreads();
 
@@ -88,6 +87,10 @@ __global__ void __launch_bounds__(256) image_hot_kernel(const HotArgs A)
         if (__popc(peers) > 1) atomicAdd(&dup_lanes, 1);
         __syncthreads();
         use_cache = dup_lanes * 64 > 256;  // > 4 of 256 lanes collide inside their warp (uniform streams: ~0.01)
+    }
+    if (use_cache) {   // only CTAs that will use the table pay for initialising it
+        for (int s = threadIdx.x; s < kHotSlots; s += 256) { keys[s] = kEmpty; vals[s] = (V)0; }
+        __syncthreads();
     }
 
     unsigned oob = 0;

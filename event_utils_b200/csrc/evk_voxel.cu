@@ -250,7 +250,6 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
     __shared__ int hot_dups;
     HotCtx hc{hot_keys, hot_vals, false};
     if (SINK == SINK_QUAD_HOT) {
-        for (int s = threadIdx.x; s < kVoxHotSlots; s += kThreads) { hot_keys[s] = kVoxEmpty; hot_vals[s] = make_float4(0.f, 0.f, 0.f, 0.f); }
         if (threadIdx.x == 0) hot_dups = 0;
         __syncthreads();
         hc.on = A.hot_force != 0;
@@ -266,6 +265,10 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
             if (__popc(__match_any_sync(0xffffffffu, key)) > 1) atomicAdd(&hot_dups, 1);
             __syncthreads();
             hc.on = hot_dups * 64 > kThreads;  // > 4 of 256 lanes collide inside their warp (uniform streams: ~0.03)
+        }
+        if (hc.on) {   // the table is only initialised (40 KB of stores) by CTAs that will use it
+            for (int s = threadIdx.x; s < kVoxHotSlots; s += kThreads) { hot_keys[s] = kVoxEmpty; hot_vals[s] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            __syncthreads();
         }
     }
 
