@@ -227,51 +227,10 @@ constexpr int kThreads = 256;
 #define EVK_VOXEL_MIN_CTAS 5
 #endif
 
+// The event loop of the scatter kernel for one (sink, layout) combination.
 template <int SINK, bool BIL, int LAYOUT>
-__global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_kernel(const VoxelArgs A_in)
+__device__ __forceinline__ void scatter_events(const VoxelArgs &A, const HotCtx &hc, int64_t tid, int64_t stride, unsigned &oob)
 {
-    VoxelArgs A = A_in;
-    if (A.auto_span && A.n > 0) {
-        // first / last timestamp straight from the (time-sorted) stream; AoS keeps t at offset 2
-        const float first = (LAYOUT == LAYOUT_PACKED) ? 0.0f : (LAYOUT == LAYOUT_AOS) ? A.x[2] : A.t[0];
-        const float last = (LAYOUT == LAYOUT_PACKED) ? (float)(A.pt64[A.n - 1] - A.pt64[0])
-                           : (LAYOUT == LAYOUT_AOS)  ? A.x[4 * (A.n - 1) + 2] : A.t[A.n - 1];
-        if (LAYOUT == LAYOUT_PACKED) A.t_first = A.pt64[0];
-        A.t0 = first;
-        A.dt = __fsub_rn(last, first);
-    }
-    unsigned oob = 0;
-    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-
-    // write-combining cache (SINK_QUAD_HOT only; the arrays vanish from the other instantiations)
-    __shared__ unsigned hot_keys[SINK == SINK_QUAD_HOT ? kVoxHotSlots : 1];
-    __shared__ float4 hot_vals[SINK == SINK_QUAD_HOT ? kVoxHotSlots : 1];
-    __shared__ int hot_dups;
-    HotCtx hc{hot_keys, hot_vals, false};
-    if (SINK == SINK_QUAD_HOT) {
-        if (threadIdx.x == 0) hot_dups = 0;
-        __syncthreads();
-        hc.on = A.hot_force != 0;
-        if (!hc.on) {
-            // contention probe: lanes whose first event shares its pixel with another lane of the warp
-            unsigned long long key = ~0ull - (threadIdx.x & 31);
-            if (tid < A.n) {
-                const float ex = (LAYOUT == LAYOUT_PACKED) ? (float)A.px16[tid] : (LAYOUT == LAYOUT_AOS) ? A.x[4 * tid] : A.x[tid];
-                const float ey = (LAYOUT == LAYOUT_PACKED) ? (float)A.py16[tid] : (LAYOUT == LAYOUT_AOS) ? A.x[4 * tid + 1] : A.y[tid];
-                int ux, uy;
-                if (trunc_checked(ex, ux) && trunc_checked(ey, uy)) key = ((unsigned long long)(unsigned)uy << 32) | (unsigned)ux;
-            }
-            if (__popc(__match_any_sync(0xffffffffu, key)) > 1) atomicAdd(&hot_dups, 1);
-            __syncthreads();
-            hc.on = hot_dups * 64 > kThreads;  // > 4 of 256 lanes collide inside their warp (uniform streams: ~0.03)
-        }
-        if (hc.on) {   // the table is only initialised (40 KB of stores) by CTAs that will use it
-            for (int s = threadIdx.x; s < kVoxHotSlots; s += kThreads) { hot_keys[s] = kVoxEmpty; hot_vals[s] = make_float4(0.f, 0.f, 0.f, 0.f); }
-            __syncthreads();
-        }
-    }
-
     if (LAYOUT == LAYOUT_SOA4) {
         // 16-byte aligned body: 4 events per thread per iteration, four LDG.128 in flight
         const int64_t head = A.head;
@@ -333,6 +292,57 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
             voxel_event<SINK, BIL>(A, hc, e.x, e.y, e.z, e.w, oob);
         }
     }
+}
+
+template <int SINK, bool BIL, int LAYOUT>
+__global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_kernel(const VoxelArgs A_in)
+{
+    VoxelArgs A = A_in;
+    if (A.auto_span && A.n > 0) {
+        // first / last timestamp straight from the (time-sorted) stream; AoS keeps t at offset 2
+        const float first = (LAYOUT == LAYOUT_PACKED) ? 0.0f : (LAYOUT == LAYOUT_AOS) ? A.x[2] : A.t[0];
+        const float last = (LAYOUT == LAYOUT_PACKED) ? (float)(A.pt64[A.n - 1] - A.pt64[0])
+                           : (LAYOUT == LAYOUT_AOS)  ? A.x[4 * (A.n - 1) + 2] : A.t[A.n - 1];
+        if (LAYOUT == LAYOUT_PACKED) A.t_first = A.pt64[0];
+        A.t0 = first;
+        A.dt = __fsub_rn(last, first);
+    }
+    unsigned oob = 0;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+
+    // write-combining cache (SINK_QUAD_HOT only; the arrays vanish from the other instantiations)
+    __shared__ unsigned hot_keys[SINK == SINK_QUAD_HOT ? kVoxHotSlots : 1];
+    __shared__ float4 hot_vals[SINK == SINK_QUAD_HOT ? kVoxHotSlots : 1];
+    __shared__ int hot_dups;
+    HotCtx hc{hot_keys, hot_vals, false};
+    if (SINK == SINK_QUAD_HOT) {
+        if (threadIdx.x == 0) hot_dups = 0;
+        __syncthreads();
+        hc.on = A.hot_force != 0;
+        if (!hc.on) {
+            // contention probe: lanes whose first event shares its pixel with another lane of the warp
+            unsigned long long key = ~0ull - (threadIdx.x & 31);
+            if (tid < A.n) {
+                const float ex = (LAYOUT == LAYOUT_PACKED) ? (float)A.px16[tid] : (LAYOUT == LAYOUT_AOS) ? A.x[4 * tid] : A.x[tid];
+                const float ey = (LAYOUT == LAYOUT_PACKED) ? (float)A.py16[tid] : (LAYOUT == LAYOUT_AOS) ? A.x[4 * tid + 1] : A.y[tid];
+                int ux, uy;
+                if (trunc_checked(ex, ux) && trunc_checked(ey, uy)) key = ((unsigned long long)(unsigned)uy << 32) | (unsigned)ux;
+            }
+            if (__popc(__match_any_sync(0xffffffffu, key)) > 1) atomicAdd(&hot_dups, 1);
+            __syncthreads();
+            hc.on = hot_dups * 64 > kThreads;  // > 4 of 256 lanes collide inside their warp (uniform streams: ~0.03)
+        }
+        if (hc.on) {   // the table is only initialised (40 KB of stores) by CTAs that will use it
+            for (int s = threadIdx.x; s < kVoxHotSlots; s += kThreads) { hot_keys[s] = kVoxEmpty; hot_vals[s] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            __syncthreads();
+        }
+    }
+
+    // the adaptive kernel runs the PLAIN vector-red loop when its cache is off, so an uncontended stream
+    // executes exactly the instructions of the non-adaptive kernel
+    if (SINK == SINK_QUAD_HOT && !hc.on) scatter_events<SINK_QUAD, BIL, LAYOUT>(A, hc, tid, stride, oob);
+    else scatter_events<SINK, BIL, LAYOUT>(A, hc, tid, stride, oob);
     if (SINK == SINK_QUAD_HOT) {
         __syncthreads();
         if (hc.on)
