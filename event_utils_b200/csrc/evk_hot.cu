@@ -28,6 +28,7 @@ struct HotArgs {
     unsigned *out_u32;
     unsigned long long *oob;
     int force_cache;  // 0 adaptive, 1 always on
+    int vec4;         // x, y (and p) are 16-byte aligned
 };
 
 constexpr int kHotLog2 = 12;
@@ -57,6 +58,80 @@ __device__ __forceinline__ void hot_add(unsigned *keys, V *vals, V *gout, bool u
 }
 
 enum { HOT_NEAREST = 0, HOT_BILINEAR = 1, HOT_COUNT = 2 };
+
+// one event; CACHE is a compile-time switch so that the cache-off instantiation is the plain scatter code
+template <int MODE, bool CACHE, typename V>
+__device__ __forceinline__ void hot_event(const HotArgs &A, unsigned *keys, V *vals, V *gout, int gs, float x, float y, float pin,
+                                          unsigned &oob)
+{
+    constexpr bool use_cache = CACHE;
+        if (MODE == HOT_NEAREST || MODE == HOT_COUNT) {
+            // image.py:88-95
+            const bool keep = !A.clip || (!(x >= A.clipx) && !(y >= A.clipy));
+            int ux, uy, xi, yi;
+            if (!trunc_checked(x, ux) || !trunc_checked(y, uy)) { ++oob; return; }
+            if (!keep) { ux = 0; uy = 0; }
+            if (!wrap_int_index(ux, A.W, xi) || !wrap_int_index(uy, A.H, yi)) { ++oob; return; }
+            const unsigned cell = (unsigned)yi * (unsigned)A.W + (unsigned)xi;
+            if (MODE == HOT_COUNT) {
+                hot_add<V>(keys, vals, gout, use_cache, cell, (V)1);
+            } else {
+                const float p = pin;
+                if (p != 0.0f) hot_add<V>(keys, vals, gout, use_cache, cell, (V)p);
+            }
+        } else {
+            // image.py:79-86 + 111-114
+            const float p = pin;
+            float m = 1.0f;
+            if (A.clip) m = (x >= A.clipx ? 0.0f : 1.0f) * (y >= A.clipy ? 0.0f : 1.0f);
+            const float pxf = floorf(x), pyf = floorf(y);
+            const float dx = __fsub_rn(x, pxf), dy = __fsub_rn(y, pyf);
+            int upx, upy, x0, x1, y0, y1;
+            if (!trunc_checked(__fmul_rn(pxf, m), upx) || !trunc_checked(__fmul_rn(pyf, m), upy) ||
+                !wrap_int_index(upx, A.W, x0) || !wrap_int_index(upx + 1, A.W, x1) ||
+                !wrap_int_index(upy, A.H, y0) || !wrap_int_index(upy + 1, A.H, y1)) { ++oob; return; }
+            const float w = __fmul_rn(p, m);
+            const float ox = __fsub_rn(1.0f, dx), oy = __fsub_rn(1.0f, dy);
+            const float wl = __fmul_rn(w, ox), wr = __fmul_rn(w, dx);
+            const float v00 = __fmul_rn(wl, oy), v01 = __fmul_rn(wr, oy), v10 = __fmul_rn(wl, dy), v11 = __fmul_rn(wr, dy);
+            const unsigned r0 = (unsigned)y0 * (unsigned)A.W, r1 = (unsigned)y1 * (unsigned)A.W;
+            if (!use_cache && A.ws && x1 == x0 + 1 && y1 == y0 + 1) {
+                // uncontended stream: the whole footprint as ONE vector reduction into its block
+                if (v00 != 0.0f || v01 != 0.0f || v10 != 0.0f || v11 != 0.0f)
+                    red_add4(A.ws + ((size_t)r0 + x0) * 4, make_float4(v00, v01, v10, v11));
+            } else {
+                if (v00 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x0, (V)v00, gs);
+                if (v01 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x1, (V)v01, gs);
+                if (v10 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x0, (V)v10, gs);
+                if (v11 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x1, (V)v11, gs);
+            }
+        }
+}
+
+// the event loop; VEC4: 16-byte loads (x, y, p all 16-byte aligned)
+template <int MODE, bool CACHE, bool VEC4, typename V>
+__device__ __forceinline__ void hot_loop(const HotArgs &A, unsigned *keys, V *vals, V *gout, int gs, int64_t tid, int64_t stride,
+                                         unsigned &oob)
+{
+    if (VEC4) {
+        const int64_t n4 = A.n >> 2;
+        for (int64_t g = tid; g < n4; g += stride) {
+            const float4 X = ld_stream4(A.x + 4 * g), Y = ld_stream4(A.y + 4 * g);
+            const float4 P = (MODE == HOT_COUNT) ? make_float4(1.f, 1.f, 1.f, 1.f) : ld_stream4(A.p + 4 * g);
+            hot_event<MODE, CACHE, V>(A, keys, vals, gout, gs, X.x, Y.x, P.x, oob);
+            hot_event<MODE, CACHE, V>(A, keys, vals, gout, gs, X.y, Y.y, P.y, oob);
+            hot_event<MODE, CACHE, V>(A, keys, vals, gout, gs, X.z, Y.z, P.z, oob);
+            hot_event<MODE, CACHE, V>(A, keys, vals, gout, gs, X.w, Y.w, P.w, oob);
+        }
+        for (int64_t i = (n4 << 2) + tid; i < A.n; i += stride)
+            hot_event<MODE, CACHE, V>(A, keys, vals, gout, gs, A.x[i], A.y[i], (MODE == HOT_COUNT) ? 1.0f : A.p[i], oob);
+    } else {
+        for (int64_t i = tid; i < A.n; i += stride)
+            hot_event<MODE, CACHE, V>(A, keys, vals, gout, gs, ld_stream(A.x + i), ld_stream(A.y + i),
+                                      (MODE == HOT_COUNT) ? 1.0f : ld_stream(A.p + i), oob);
+    }
+}
+
 
 template <int MODE>
 __global__ void __launch_bounds__(256) image_hot_kernel(const HotArgs A)
@@ -94,50 +169,10 @@ __global__ void __launch_bounds__(256) image_hot_kernel(const HotArgs A)
     }
 
     unsigned oob = 0;
-    for (int64_t i = tid; i < A.n; i += stride) {
-        const float x = ld_stream(A.x + i), y = ld_stream(A.y + i);
-        if (MODE == HOT_NEAREST || MODE == HOT_COUNT) {
-            // image.py:88-95
-            const bool keep = !A.clip || (!(x >= A.clipx) && !(y >= A.clipy));
-            int ux, uy, xi, yi;
-            if (!trunc_checked(x, ux) || !trunc_checked(y, uy)) { ++oob; continue; }
-            if (!keep) { ux = 0; uy = 0; }
-            if (!wrap_int_index(ux, A.W, xi) || !wrap_int_index(uy, A.H, yi)) { ++oob; continue; }
-            const unsigned cell = (unsigned)yi * (unsigned)A.W + (unsigned)xi;
-            if (MODE == HOT_COUNT) {
-                hot_add<V>(keys, vals, gout, use_cache, cell, (V)1);
-            } else {
-                const float p = ld_stream(A.p + i);
-                if (p != 0.0f) hot_add<V>(keys, vals, gout, use_cache, cell, (V)p);
-            }
-        } else {
-            // image.py:79-86 + 111-114
-            const float p = ld_stream(A.p + i);
-            float m = 1.0f;
-            if (A.clip) m = (x >= A.clipx ? 0.0f : 1.0f) * (y >= A.clipy ? 0.0f : 1.0f);
-            const float pxf = floorf(x), pyf = floorf(y);
-            const float dx = __fsub_rn(x, pxf), dy = __fsub_rn(y, pyf);
-            int upx, upy, x0, x1, y0, y1;
-            if (!trunc_checked(__fmul_rn(pxf, m), upx) || !trunc_checked(__fmul_rn(pyf, m), upy) ||
-                !wrap_int_index(upx, A.W, x0) || !wrap_int_index(upx + 1, A.W, x1) ||
-                !wrap_int_index(upy, A.H, y0) || !wrap_int_index(upy + 1, A.H, y1)) { ++oob; continue; }
-            const float w = __fmul_rn(p, m);
-            const float ox = __fsub_rn(1.0f, dx), oy = __fsub_rn(1.0f, dy);
-            const float wl = __fmul_rn(w, ox), wr = __fmul_rn(w, dx);
-            const float v00 = __fmul_rn(wl, oy), v01 = __fmul_rn(wr, oy), v10 = __fmul_rn(wl, dy), v11 = __fmul_rn(wr, dy);
-            const unsigned r0 = (unsigned)y0 * (unsigned)A.W, r1 = (unsigned)y1 * (unsigned)A.W;
-            if (!use_cache && A.ws && x1 == x0 + 1 && y1 == y0 + 1) {
-                // uncontended stream: the whole footprint as ONE vector reduction into its block
-                if (v00 != 0.0f || v01 != 0.0f || v10 != 0.0f || v11 != 0.0f)
-                    red_add4(A.ws + ((size_t)r0 + x0) * 4, make_float4(v00, v01, v10, v11));
-            } else {
-                if (v00 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x0, (V)v00, gs);
-                if (v01 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x1, (V)v01, gs);
-                if (v10 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x0, (V)v10, gs);
-                if (v11 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x1, (V)v11, gs);
-            }
-        }
-    }
+    // cache off -> the plain scatter code (vector loads when possible), cache on -> the cached code
+    if (use_cache) hot_loop<MODE, true, false, V>(A, keys, vals, gout, gs, tid, stride, oob);
+    else if (A.vec4) hot_loop<MODE, false, true, V>(A, keys, vals, gout, gs, tid, stride, oob);
+    else hot_loop<MODE, false, false, V>(A, keys, vals, gout, gs, tid, stride, oob);
     __syncthreads();
     if (use_cache) {
         for (int s = threadIdx.x; s < kHotSlots; s += 256) {
@@ -157,6 +192,7 @@ int launch_image_hot(const float *x, const float *y, const float *p, int64_t n, 
     A.x = x; A.y = y; A.p = p; A.n = n; A.H = H; A.W = W;
     A.clip = clip; A.clipx = clipx; A.clipy = clipy;
     A.out = out; A.ws = ws; A.out_u32 = out_u32; A.oob = oob; A.force_cache = force_cache;
+    A.vec4 = ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)(p ? p : x)) & 15) == 0) ? 1 : 0;
     if (n <= 0) return EVK_OK;
     ProfScope prof(st);
     prof_count(1);
