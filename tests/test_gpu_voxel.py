@@ -338,3 +338,25 @@ def test_full_size_properties(variant):
     # idempotence / determinism of the count-like grid up to fp addition order
     v2 = events_to_voxel_torch(x, y, t, p, 5, sensor_size=(480, 640))
     assert_close_to_max(v2.cpu().numpy(), v.cpu().numpy(), 1e-5)
+
+
+def test_sharded_stream_single_process(oracle):
+    """parallel.ShardedVoxelStream without a process group: buffers recycle correctly and every build
+    equals the direct call (the NCCL leg is exercised by bench.py --gpus N and the gloo test)."""
+    from event_utils_b200.parallel import ShardedVoxelStream, events_to_voxel_sharded
+    x, y, t, p = make_events(91, 300000, 90, 120)
+    X, Y, T, P = dev(x, y, t, p)
+    pipe = ShardedVoxelStream(5, (90, 120), X.device, depth=2)
+    outs = []
+    for k in range(5):
+        sl = slice(k * 50000, (k + 2) * 50000)
+        t0, dt = float(t[sl][0]), float(np.float32(t[sl][-1]) - np.float32(t[sl][0]))
+        grid, done = pipe.submit(X[sl], Y[sl], T[sl], P[sl], t0, dt)
+        done.synchronize()
+        outs.append((grid.clone(), sl, t0, dt))
+    pipe.drain()
+    for g, sl, t0, dt in outs:
+        assert_close_to_max(g.cpu().numpy(), oracle.voxel_f32(x[sl], y[sl], t[sl], p[sl], 5, (90, 120), t0=t0, dt=dt), 1e-5)
+    full = events_to_voxel_sharded(X, Y, T, P, 5, (90, 120))
+    assert_close_to_max(full.cpu().numpy(), oracle.voxel_f32(x, y, t, p, 5, (90, 120)), 1e-5)
+
