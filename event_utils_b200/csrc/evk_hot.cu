@@ -65,47 +65,47 @@ __device__ __forceinline__ void hot_event(const HotArgs &A, unsigned *keys, V *v
                                           unsigned &oob)
 {
     constexpr bool use_cache = CACHE;
-        if (MODE == HOT_NEAREST || MODE == HOT_COUNT) {
-            // image.py:88-95
-            const bool keep = !A.clip || (!(x >= A.clipx) && !(y >= A.clipy));
-            int ux, uy, xi, yi;
-            if (!trunc_checked(x, ux) || !trunc_checked(y, uy)) { ++oob; return; }
-            if (!keep) { ux = 0; uy = 0; }
-            if (!wrap_int_index(ux, A.W, xi) || !wrap_int_index(uy, A.H, yi)) { ++oob; return; }
-            const unsigned cell = (unsigned)yi * (unsigned)A.W + (unsigned)xi;
-            if (MODE == HOT_COUNT) {
-                hot_add<V>(keys, vals, gout, use_cache, cell, (V)1);
-            } else {
-                const float p = pin;
-                if (p != 0.0f) hot_add<V>(keys, vals, gout, use_cache, cell, (V)p);
-            }
+    if (MODE == HOT_NEAREST || MODE == HOT_COUNT) {
+        // image.py:88-95
+        const bool keep = !A.clip || (!(x >= A.clipx) && !(y >= A.clipy));
+        int ux, uy, xi, yi;
+        if (!trunc_checked(x, ux) || !trunc_checked(y, uy)) { ++oob; return; }
+        if (!keep) { ux = 0; uy = 0; }
+        if (!wrap_int_index(ux, A.W, xi) || !wrap_int_index(uy, A.H, yi)) { ++oob; return; }
+        const unsigned cell = (unsigned)yi * (unsigned)A.W + (unsigned)xi;
+        if (MODE == HOT_COUNT) {
+            hot_add<V>(keys, vals, gout, use_cache, cell, (V)1);
         } else {
-            // image.py:79-86 + 111-114
             const float p = pin;
-            float m = 1.0f;
-            if (A.clip) m = (x >= A.clipx ? 0.0f : 1.0f) * (y >= A.clipy ? 0.0f : 1.0f);
-            const float pxf = floorf(x), pyf = floorf(y);
-            const float dx = __fsub_rn(x, pxf), dy = __fsub_rn(y, pyf);
-            int upx, upy, x0, x1, y0, y1;
-            if (!trunc_checked(__fmul_rn(pxf, m), upx) || !trunc_checked(__fmul_rn(pyf, m), upy) ||
-                !wrap_int_index(upx, A.W, x0) || !wrap_int_index(upx + 1, A.W, x1) ||
-                !wrap_int_index(upy, A.H, y0) || !wrap_int_index(upy + 1, A.H, y1)) { ++oob; return; }
-            const float w = __fmul_rn(p, m);
-            const float ox = __fsub_rn(1.0f, dx), oy = __fsub_rn(1.0f, dy);
-            const float wl = __fmul_rn(w, ox), wr = __fmul_rn(w, dx);
-            const float v00 = __fmul_rn(wl, oy), v01 = __fmul_rn(wr, oy), v10 = __fmul_rn(wl, dy), v11 = __fmul_rn(wr, dy);
-            const unsigned r0 = (unsigned)y0 * (unsigned)A.W, r1 = (unsigned)y1 * (unsigned)A.W;
-            if (!use_cache && A.ws && x1 == x0 + 1 && y1 == y0 + 1) {
-                // uncontended stream: the whole footprint as ONE vector reduction into its block
-                if (v00 != 0.0f || v01 != 0.0f || v10 != 0.0f || v11 != 0.0f)
-                    red_add4(A.ws + ((size_t)r0 + x0) * 4, make_float4(v00, v01, v10, v11));
-            } else {
-                if (v00 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x0, (V)v00, gs);
-                if (v01 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x1, (V)v01, gs);
-                if (v10 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x0, (V)v10, gs);
-                if (v11 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x1, (V)v11, gs);
-            }
+            if (p != 0.0f) hot_add<V>(keys, vals, gout, use_cache, cell, (V)p);
         }
+    } else {
+        // image.py:79-86 + 111-114
+        const float p = pin;
+        float m = 1.0f;
+        if (A.clip) m = (x >= A.clipx ? 0.0f : 1.0f) * (y >= A.clipy ? 0.0f : 1.0f);
+        const float pxf = floorf(x), pyf = floorf(y);
+        const float dx = __fsub_rn(x, pxf), dy = __fsub_rn(y, pyf);
+        int upx, upy, x0, x1, y0, y1;
+        if (!trunc_checked(__fmul_rn(pxf, m), upx) || !trunc_checked(__fmul_rn(pyf, m), upy) ||
+            !wrap_int_index(upx, A.W, x0) || !wrap_int_index(upx + 1, A.W, x1) ||
+            !wrap_int_index(upy, A.H, y0) || !wrap_int_index(upy + 1, A.H, y1)) { ++oob; return; }
+        const float w = __fmul_rn(p, m);
+        const float ox = __fsub_rn(1.0f, dx), oy = __fsub_rn(1.0f, dy);
+        const float wl = __fmul_rn(w, ox), wr = __fmul_rn(w, dx);
+        const float v00 = __fmul_rn(wl, oy), v01 = __fmul_rn(wr, oy), v10 = __fmul_rn(wl, dy), v11 = __fmul_rn(wr, dy);
+        const unsigned r0 = (unsigned)y0 * (unsigned)A.W, r1 = (unsigned)y1 * (unsigned)A.W;
+        if (!use_cache && A.ws && x1 == x0 + 1 && y1 == y0 + 1) {
+            // uncontended stream: the whole footprint as ONE vector reduction into its block
+            if (v00 != 0.0f || v01 != 0.0f || v10 != 0.0f || v11 != 0.0f)
+                red_add4(A.ws + ((size_t)r0 + x0) * 4, make_float4(v00, v01, v10, v11));
+        } else {
+            if (v00 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x0, (V)v00, gs);
+            if (v01 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x1, (V)v01, gs);
+            if (v10 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x0, (V)v10, gs);
+            if (v11 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x1, (V)v11, gs);
+        }
+    }
 }
 
 // the event loop; VEC4: 16-byte loads (x, y, p all 16-byte aligned)

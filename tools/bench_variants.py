@@ -140,6 +140,27 @@ for dist in ("uniform", "zipf1.0", "zipf1.2"):
 del x, y, t, p
 torch.cuda.empty_cache()
 
+print("== timestamp images, flow warp, neg/pos voxel (%d events)" % N)
+xq, yq, tq, pq = uniform(N, 480, 640, 5)
+tpos = torch.empty((481, 641), device=dev); tneg = torch.empty((481, 641), device=dev)
+wst = torch.empty(L.evk_timestamp_image_workspace_bytes(481, 641), dtype=torch.uint8, device=dev)
+best, _ = timeit(lambda: _lib.check(L.evk_timestamp_image_f32(xq.data_ptr(), yq.data_ptr(), tq.data_ptr(), pq.data_ptr(), N, float(tq[0]), float(tq[-1]),
+                                                              481, 641, 640.0, 480.0, _lib.CLIP, tpos.data_ptr(), tneg.data_ptr(), wst.data_ptr(), wst.numel(),
+                                                              oob.data_ptr(), None)), iters=3, warm=1)
+report("timestamp images 480x640 (2 block REDs/event)", best, N, 16, 8 * 481 * 641)
+flow = torch.randn(2, 480, 640, device=dev) * 20
+xw, yw = torch.empty_like(xq), torch.empty_like(yq)
+best, _ = timeit(lambda: _lib.check(L.evk_warp_flow_f32(xq.data_ptr(), yq.data_ptr(), tq.data_ptr(), N, flow.data_ptr(), 480, 640, float(tq[-1]),
+                                                        xw.data_ptr(), yw.data_ptr(), None)), iters=3, warm=1)
+report("dense-flow warp 480x640 (12 B in, 8 B out per event)", best, N, 20)
+outnp = torch.empty((2, 5, 480, 640), device=dev)
+wsnp = torch.empty(2 * L.evk_voxel_workspace_bytes(5, 480, 640, 0), dtype=torch.uint8, device=dev)
+best, _ = timeit(lambda: _lib.check(L.evk_voxel_negpos_f32(xq.data_ptr(), yq.data_ptr(), tq.data_ptr(), pq.data_ptr(), N, 0.0, 1.0, 5, 480, 640,
+                                                           _lib.AUTO_SPAN, outnp.data_ptr(), wsnp.data_ptr(), wsnp.numel(), oob.data_ptr(), None)), iters=3, warm=1)
+report("neg/pos voxel 2x5x480x640, one pass", best, N, 16, 8 * 5 * 480 * 640)
+del xq, yq, tq, pq, xw, yw, flow
+torch.cuda.empty_cache()
+
 print("== cmax %d events (f64 parity mode / f32 fast mode)" % N)
 g = torch.Generator(device=dev).manual_seed(7)
 for scene in ("uniform", "lattice"):
