@@ -80,7 +80,9 @@ def _declare(L):
     L.evk_gather_bilinear_f64.restype = ci
     L.evk_gather_bilinear_f64.argtypes = [vp, vp, i64, vp, ci, ci, vp, vp, vp]
     L.evk_warp_flow_f32.restype = ci
-    L.evk_warp_flow_f32.argtypes = [vp, vp, vp, i64, vp, ci, ci, f32, vp, vp, vp]
+    L.evk_warp_flow_f32.argtypes = [vp, vp, vp, i64, vp, ci, ci, f32, vp, vp, vp, sz, vp]
+    L.evk_warp_flow_workspace_bytes.restype = sz
+    L.evk_warp_flow_workspace_bytes.argtypes = [ci, ci]
     L.evk_cmax_workspace_bytes.restype = sz
     L.evk_cmax_workspace_bytes.argtypes = [ci, ci]
     L.evk_cmax_linvel_variance_f64.restype = ci

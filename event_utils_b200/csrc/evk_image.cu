@@ -215,43 +215,98 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const ImageArgs A)
 }
 
 // ---- dense-flow warp (optic_flow.py:37-44 + ATen grid_sampler bilinear/zeros/align_corners) ---
-__device__ __forceinline__ float flow_at(const float *f, int H, int W, int yy, int xx)
+// flow [2][H][W] -> interleaved [H][W][2] = {u, v} per pixel, so that the taps of one image row are contiguous
+__global__ void __launch_bounds__(256) flow_interleave_kernel(const float *__restrict__ flow, int64_t npix, float2 *__restrict__ uv)
 {
-    return ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? __ldg(f + (int64_t)yy * W + xx) : 0.0f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) uv[i] = make_float2(flow[i], flow[npix + i]);
 }
 
+// the two taps (x0, x0+1) of row yy as {u0, v0, u1, v1}; out-of-image taps are zero (grid_sample zero padding).
+// INTERLEAVED: 16 contiguous bytes -> one LDG.128 when x0 is even, two LDG.64 otherwise; planar: four LDG.32.
+template <bool INTERLEAVED>
+__device__ __forceinline__ float4 flow_row(const float *flow, const float2 *uv, int H, int W, int yy, int x0)
+{
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)yy >= (unsigned)H) return r;
+    const bool in0 = (unsigned)x0 < (unsigned)W, in1 = (unsigned)(x0 + 1) < (unsigned)W;
+    if (INTERLEAVED) {
+        const float2 *row = uv + (int64_t)yy * W;
+        if (in0 && in1 && ((x0 & 1) == 0) && ((W & 1) == 0)) {
+            r = __ldg(reinterpret_cast<const float4 *>(row + x0));
+        } else {
+            if (in0) { const float2 a = __ldg(row + x0); r.x = a.x; r.y = a.y; }
+            if (in1) { const float2 c = __ldg(row + x0 + 1); r.z = c.x; r.w = c.y; }
+        }
+    } else {
+        const float *fu = flow + (int64_t)yy * W, *fv = fu + (int64_t)H * W;
+        if (in0) { r.x = __ldg(fu + x0); r.y = __ldg(fv + x0); }
+        if (in1) { r.z = __ldg(fu + x0 + 1); r.w = __ldg(fv + x0 + 1); }
+    }
+    return r;
+}
+
+template <bool INTERLEAVED>
+__device__ __forceinline__ void flow_one(float xe, float ye, float te, const float *flow, const float2 *uv, int H, int W, float wm1,
+                                         float hm1, float t0, float &xo, float &yo)
+{
+    // the reference normalises to [-1,1] (optic_flow.py:37-38) and grid_sample maps back
+    const float gx = __fsub_rn(__fmul_rn(__fdiv_rn(xe, wm1), 2.0f), 1.0f);
+    const float gy = __fsub_rn(__fmul_rn(__fdiv_rn(ye, hm1), 2.0f), 1.0f);
+    const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), wm1);
+    const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), hm1);
+    float u = 0.0f, v = 0.0f;
+    if (fabsf(ix) < 1.0e9f && fabsf(iy) < 1.0e9f) {
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float xs = fx + 1.0f, ys = fy + 1.0f;
+        const float nw = __fmul_rn(__fsub_rn(xs, ix), __fsub_rn(ys, iy));
+        const float ne = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(ys, iy));
+        const float sw = __fmul_rn(__fsub_rn(xs, ix), __fsub_rn(iy, fy));
+        const float se = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(iy, fy));
+        const float4 top = flow_row<INTERLEAVED>(flow, uv, H, W, y0, x0), bot = flow_row<INTERLEAVED>(flow, uv, H, W, y0 + 1, x0);
+        // accumulation order of ATen's grid_sampler: nw, ne, sw, se
+        u = __fadd_rn(u, __fmul_rn(top.x, nw)); v = __fadd_rn(v, __fmul_rn(top.y, nw));
+        u = __fadd_rn(u, __fmul_rn(top.z, ne)); v = __fadd_rn(v, __fmul_rn(top.w, ne));
+        u = __fadd_rn(u, __fmul_rn(bot.x, sw)); v = __fadd_rn(v, __fmul_rn(bot.y, sw));
+        u = __fadd_rn(u, __fmul_rn(bot.z, se)); v = __fadd_rn(v, __fmul_rn(bot.w, se));
+    }
+    const float d = __fsub_rn(te, t0);
+    xo = __fadd_rn(xe, __fmul_rn(u, d));
+    yo = __fadd_rn(ye, __fmul_rn(v, d));
+}
+
+// VEC4: every thread takes four consecutive events with 16-byte loads / stores (the host checks the
+// alignment), which also puts eight independent flow gathers in flight per thread.
+template <bool INTERLEAVED, bool VEC4>
 __global__ void __launch_bounds__(256) warp_flow_kernel(const float *__restrict__ x, const float *__restrict__ y,
                                                         const float *__restrict__ t, int64_t n,
-                                                        const float *__restrict__ flow, int H, int W, float t0,
-                                                        float *__restrict__ xw, float *__restrict__ yw)
+                                                        const float *__restrict__ flow, const float2 *__restrict__ uv, int H, int W,
+                                                        float t0, float *__restrict__ xw, float *__restrict__ yw)
 {
-    const float *fu = flow, *fv = flow + (int64_t)H * W;
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float xe = ld_stream(x + i), ye = ld_stream(y + i), te = ld_stream(t + i);
-        // the reference normalises to [-1,1] (optic_flow.py:37-38) and grid_sample maps back
-        const float gx = __fsub_rn(__fmul_rn(__fdiv_rn(xe, wm1), 2.0f), 1.0f);
-        const float gy = __fsub_rn(__fmul_rn(__fdiv_rn(ye, hm1), 2.0f), 1.0f);
-        const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), wm1);
-        const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), hm1);
-        float u = 0.0f, v = 0.0f;
-        if (fabsf(ix) < 1.0e9f && fabsf(iy) < 1.0e9f) {
-            const float fx = floorf(ix), fy = floorf(iy);
-            const int x0 = (int)fx, y0 = (int)fy;
-            const float xs = fx + 1.0f, ys = fy + 1.0f;
-            const float nw = __fmul_rn(__fsub_rn(xs, ix), __fsub_rn(ys, iy));
-            const float ne = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(ys, iy));
-            const float sw = __fmul_rn(__fsub_rn(xs, ix), __fsub_rn(iy, fy));
-            const float se = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(iy, fy));
-            u = __fadd_rn(u, __fmul_rn(flow_at(fu, H, W, y0, x0), nw));         v = __fadd_rn(v, __fmul_rn(flow_at(fv, H, W, y0, x0), nw));
-            u = __fadd_rn(u, __fmul_rn(flow_at(fu, H, W, y0, x0 + 1), ne));     v = __fadd_rn(v, __fmul_rn(flow_at(fv, H, W, y0, x0 + 1), ne));
-            u = __fadd_rn(u, __fmul_rn(flow_at(fu, H, W, y0 + 1, x0), sw));     v = __fadd_rn(v, __fmul_rn(flow_at(fv, H, W, y0 + 1, x0), sw));
-            u = __fadd_rn(u, __fmul_rn(flow_at(fu, H, W, y0 + 1, x0 + 1), se)); v = __fadd_rn(v, __fmul_rn(flow_at(fv, H, W, y0 + 1, x0 + 1), se));
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t scalar_from = 0;
+    if (VEC4) {
+        const int64_t n4 = n >> 2;
+        for (int64_t q = tid; q < n4; q += stride) {
+            const float4 xe = ld_stream4(x + 4 * q), ye = ld_stream4(y + 4 * q), te = ld_stream4(t + 4 * q);
+            float4 xo, yo;
+            flow_one<INTERLEAVED>(xe.x, ye.x, te.x, flow, uv, H, W, wm1, hm1, t0, xo.x, yo.x);
+            flow_one<INTERLEAVED>(xe.y, ye.y, te.y, flow, uv, H, W, wm1, hm1, t0, xo.y, yo.y);
+            flow_one<INTERLEAVED>(xe.z, ye.z, te.z, flow, uv, H, W, wm1, hm1, t0, xo.z, yo.z);
+            flow_one<INTERLEAVED>(xe.w, ye.w, te.w, flow, uv, H, W, wm1, hm1, t0, xo.w, yo.w);
+            __stcs(reinterpret_cast<float4 *>(xw + 4 * q), xo);
+            __stcs(reinterpret_cast<float4 *>(yw + 4 * q), yo);
         }
-        const float d = __fsub_rn(te, t0);
-        xw[i] = __fadd_rn(xe, __fmul_rn(u, d));
-        yw[i] = __fadd_rn(ye, __fmul_rn(v, d));
+        scalar_from = n4 << 2;
+    }
+    for (int64_t i = scalar_from + tid; i < n; i += stride) {
+        float xo, yo;
+        flow_one<INTERLEAVED>(ld_stream(x + i), ld_stream(y + i), ld_stream(t + i), flow, uv, H, W, wm1, hm1, t0, xo, yo);
+        xw[i] = xo;
+        yw[i] = yo;
     }
 }
 
@@ -380,14 +435,37 @@ int evk_count_u32(const float *x, const float *y, int64_t n, int Himg, int Wimg,
     return EVK_OK;
 }
 
+size_t evk_warp_flow_workspace_bytes(int H, int W)
+{
+    if (H < 1 || W < 1) return 0;
+    return (size_t)H * W * sizeof(float2);
+}
+
 int evk_warp_flow_f32(const float *x, const float *y, const float *t, int64_t n, const float *flow, int H, int W,
-                      float t0, float *xw, float *yw, void *stream)
+                      float t0, float *xw, float *yw, void *workspace, size_t workspace_bytes, void *stream)
 {
     using namespace evk;
     if (n < 0 || H < 1 || W < 1 || !flow || (n > 0 && (!x || !y || !t || !xw || !yw))) { set_error("evk_warp_flow_f32: bad arguments"); return EVK_E_ARG; }
     if (n == 0) return EVK_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t npix = (int64_t)H * W;
+    // with a workspace (and enough events to pay for the 8 B/pixel re-layout) the flow is interleaved first
+    const bool inter = workspace && workspace_bytes >= (size_t)npix * sizeof(float2) && !((uintptr_t)workspace & 15) && n >= npix / 4;
+    const bool vec = !(((uintptr_t)x | (uintptr_t)y | (uintptr_t)t | (uintptr_t)xw | (uintptr_t)yw) & 15);
+    const float2 *uv = nullptr;
+    if (inter) {
+        prof_count(1);
+        flow_interleave_kernel<<<grid_simple(npix, 256), 256, 0, st>>>(flow, npix, static_cast<float2 *>(workspace));
+        uv = static_cast<const float2 *>(workspace);
+    }
     prof_count(1);
-    warp_flow_kernel<<<grid_for(warp_flow_kernel, 256, n, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, t, n, flow, H, W, t0, xw, yw);
+#define EVK_FLOW_LAUNCH(I, V)                                                                                                  \
+    warp_flow_kernel<I, V><<<grid_for(warp_flow_kernel<I, V>, 256, n, 256 * (V ? 8 : 4)), 256, 0, st>>>(x, y, t, n, flow, uv, H, W, t0, xw, yw)
+    if (inter && vec) EVK_FLOW_LAUNCH(true, true);
+    else if (inter) EVK_FLOW_LAUNCH(true, false);
+    else if (vec) EVK_FLOW_LAUNCH(false, true);
+    else EVK_FLOW_LAUNCH(false, false);
+#undef EVK_FLOW_LAUNCH
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

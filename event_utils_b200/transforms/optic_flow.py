@@ -34,8 +34,10 @@ def warp_events_flow_torch(xt, yt, tt, pt, flow_field, t0=None,
         x, y, t = (a.reshape(-1).to(dev).to(torch.float32).contiguous() for a in (xt, yt, tt))
         f = flow[0].to(dev).to(torch.float32).contiguous()
         xw, yw = torch.empty_like(x), torch.empty_like(y)
+        ws = _lib.scratch("flow_ws", L.evk_warp_flow_workspace_bytes(f.shape[1], f.shape[2]), dev)
         _lib.check(L.evk_warp_flow_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), x.shape[0], _lib.ptr(f),
-                                       f.shape[1], f.shape[2], t0, _lib.ptr(xw), _lib.ptr(yw), _lib.stream()))
+                                       f.shape[1], f.shape[2], t0, _lib.ptr(xw), _lib.ptr(yw), _lib.ptr(ws), ws.numel(),
+                                       _lib.stream()))
     if xw.device != out_device:
         xw, yw = xw.to(out_device), yw.to(out_device)
     return xw, yw

@@ -191,9 +191,13 @@ int evk_gather_bilinear_f64(const double *x, const double *y, int64_t n, const d
  * Dense-flow warp.  Replaces warp_events_flow_torch, lib/transforms/optic_flow.py:5-46
  * (F.grid_sample bilinear, align_corners=True, zero padding, :37-44).
  * flow: [2][H][W] f32.  xw/yw: n floats.  x' = x + u(x,y)*(t-t0), y' = y + v(x,y)*(t-t0).
+ * workspace (optional, evk_warp_flow_workspace_bytes(), 16-byte aligned): lets the kernel re-lay the
+ * flow out as {u,v} pairs so that the two taps of an image row are one 16-byte load.
  * --------------------------------------------------------------------------------------------- */
+size_t evk_warp_flow_workspace_bytes(int H, int W);
 int evk_warp_flow_f32(const float *x, const float *y, const float *t, int64_t n, const float *flow,
-                      int H, int W, float t0, float *xw, float *yw, void *stream);
+                      int H, int W, float t0, float *xw, float *yw, void *workspace,
+                      size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Contrast maximisation, fused: linvel warp -> bounds mask -> bilinear IWE (+ derivative

@@ -100,6 +100,6 @@ def test_argument_errors_are_reported_without_touching_the_gpu():
     assert L.evk_cmax_linvel_variance_f64(one, one, one, one, 10, 1.0, 0.0, 0.0, 0.0, 180, 240, 180, 240, 1.0, 0,
                                           one, None, None, None, 0, None) == -1
     assert L.evk_timestamp_image_f32(one, one, one, one, 10, 0.0, 1.0, 4, 4, 3.0, 3.0, 0, one, one, None, 0, None, None) == -3
-    assert L.evk_warp_flow_f32(one, one, one, 10, None, 4, 4, 0.0, one, one, None) == -1
+    assert L.evk_warp_flow_f32(one, one, one, 10, None, 4, 4, 0.0, one, one, None, 0, None) == -1
     assert L.evk_voxel_windows_f32(one, one, one, one, None, 3, 0, 5, 4, 4, 0, one, None, None) == -1
     assert L.evk_voxel_negpos_f32(one, one, one, one, 10, 0.0, 1.0, 5, 4, 4, _lib.BILINEAR, one, None, 0, None, None) == -5

@@ -207,6 +207,18 @@ def test_flow_warp(oracle):
     xo, yo = oracle.warp_flow_f32(xe, ye, te, fl)
     assert_close_to_max(xw.cpu().numpy(), xo, 1e-5)
     assert_close_to_max(yw.cpu().numpy(), yo, 1e-5)
+    # sub-pixel and out-of-image coordinates, odd width, views that are not 16-byte aligned, few events
+    rng = np.random.default_rng(2)
+    for (H, W, n, off) in ((180, 240, 300001, 1), (181, 241, 200003, 0), (64, 34, 1000, 3), (33, 47, 90000, 2)):
+        xe = rng.uniform(-3, W + 2, n + off).astype(np.float32)
+        ye = rng.uniform(-3, H + 2, n + off).astype(np.float32)
+        te = np.sort(rng.uniform(0, 0.1, n + off)).astype(np.float32)
+        fl = (rng.standard_normal((2, H, W)) * 30).astype(np.float32)
+        xd, yd, td, fd = dev(xe, ye, te, fl)
+        xw, yw = warp_events_flow_torch(xd[off:], yd[off:], td[off:], td[off:], fd)
+        xo, yo = oracle.warp_flow_f32(xe[off:], ye[off:], te[off:], fl)
+        assert_close_to_max(xw.cpu().numpy(), xo, 1e-5)
+        assert_close_to_max(yw.cpu().numpy(), yo, 1e-5)
 
 
 def test_tap_helpers():

@@ -150,9 +150,11 @@ best, _ = timeit(lambda: _lib.check(L.evk_timestamp_image_f32(xq.data_ptr(), yq.
 report("timestamp images 480x640 (2 block REDs/event)", best, N, 16, 8 * 481 * 641)
 flow = torch.randn(2, 480, 640, device=dev) * 20
 xw, yw = torch.empty_like(xq), torch.empty_like(yq)
-best, _ = timeit(lambda: _lib.check(L.evk_warp_flow_f32(xq.data_ptr(), yq.data_ptr(), tq.data_ptr(), N, flow.data_ptr(), 480, 640, float(tq[-1]),
-                                                        xw.data_ptr(), yw.data_ptr(), None)), iters=3, warm=1)
-report("dense-flow warp 480x640 (12 B in, 8 B out per event)", best, N, 20)
+wsf = torch.empty(L.evk_warp_flow_workspace_bytes(480, 640), dtype=torch.uint8, device=dev)
+for nm, wsp, wsb in (("planar flow", None, 0), ("interleaved flow", wsf.data_ptr(), wsf.numel())):
+    best, _ = timeit(lambda: _lib.check(L.evk_warp_flow_f32(xq.data_ptr(), yq.data_ptr(), tq.data_ptr(), N, flow.data_ptr(), 480, 640, float(tq[-1]),
+                                                            xw.data_ptr(), yw.data_ptr(), wsp, wsb, None)), iters=3, warm=1)
+    report("dense-flow warp 480x640, %s" % nm, best, N, 20)
 outnp = torch.empty((2, 5, 480, 640), device=dev)
 wsnp = torch.empty(2 * L.evk_voxel_workspace_bytes(5, 480, 640, 0), dtype=torch.uint8, device=dev)
 best, _ = timeit(lambda: _lib.check(L.evk_voxel_negpos_f32(xq.data_ptr(), yq.data_ptr(), tq.data_ptr(), pq.data_ptr(), N, 0.0, 1.0, 5, 480, 640,
