@@ -423,6 +423,13 @@ def run_ours(args, rank, local_rank, world):
             torch.cuda.empty_cache()
             extra = secondary_metrics(L, _lib, device, peak)
 
+    if world > 1 and not args.no_extra:
+        del x, y, t, p
+        torch.cuda.empty_cache()
+        sharded = sharded_cmax_metric(device, world, rank)
+        if rank == 0:
+            extra = {"cmax_sharded": sharded}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Mevents/s", "n_gpus": world, "steps": args.steps,
@@ -454,6 +461,39 @@ def run_ours(args, rank, local_rank, world):
         os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_cmax_metric(device, world, rank):
+    """Contrast-maximisation (f, g) evaluations of ONE stream sharded over the ranks: per
+    evaluation each rank splats its 50 M events, one all-reduce joins the 3 x 181 x 241 partial images,
+    every rank evaluates the objective.  Timed on the device, max over ranks."""
+    from event_utils_b200.parallel import cmax_variance_sharded
+    n = N_PER_GPU
+    g = torch.Generator(device=device)
+    g.manual_seed(7000 + rank)
+    span = 0.05
+    x = torch.rand(n, generator=g, device=device) * 239.0
+    y = torch.rand(n, generator=g, device=device) * 179.0
+    t = torch.sort(torch.rand(n, generator=g, device=device) * (span / world))[0] + rank * (span / world)
+    p = (torch.randint(0, 2, (n,), generator=g, device=device) * 2 - 1).float()
+    iters = 10
+    for _ in range(2):
+        f, gr = cmax_variance_sharded((45.0, -20.0), x, y, t, p, (180, 240), 1.0, t_ref=span)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(iters):
+        f, gr = cmax_variance_sharded((45.0 + i, -20.0), x, y, t, p, (180, 240), 1.0, t_ref=span)
+    e1.record()
+    torch.cuda.synchronize()
+    el = torch.tensor([e0.elapsed_time(e1)], device=device)
+    dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    ms = float(el.item()) / iters
+    return {"ms_per_eval": ms, "evals_per_s": 1e3 / ms, "events_total": n * world, "Mevents_per_s": n * world / ms / 1e3,
+            "f": f, "g": [float(gr[0]), float(gr[1])],
+            "what": "variance objective + gradient, linvel warp, f32 fast mode, %d M events per GPU; one NCCL all-reduce of "
+                    "3x181x241 floats per evaluation; result read back to the host every evaluation" % (n // 1000000)}
 
 
 def secondary_metrics(L, _lib, device, peak):

@@ -1,5 +1,6 @@
-"""Multi-GPU voxel build: one process per GPU, events partitioned across ranks, ONE sum
-all-reduce of the (B,H,W) grid over NCCL / NVLink.
+"""Multi-GPU voxel build and contrast-maximisation evaluation: one process per GPU, events
+partitioned across ranks, ONE sum all-reduce of the (B,H,W) grid -- or of the image of warped events
+and its two derivative images -- over NCCL / NVLink.
 
 Every output of the hot path is a sum over events (index_put_(accumulate=True), reference
 image.py:95), so any partition of the events works.  The only global quantities are the two
@@ -103,3 +104,95 @@ class ShardedVoxelStream:
         cur = torch.cuda.current_stream(self.device)
         for ev in self.done[: min(self.k, len(self.done))]:
             cur.wait_event(ev)
+
+
+# ---------------------------------------------------------------------------------------------
+# contrast maximisation over a sharded stream (partial IWE + derivative images ->
+# all-reduce 523 KB -> blur / variance replicated on every rank)
+# ---------------------------------------------------------------------------------------------
+SENSOR_SIZE = (180, 240)     # the reference's fixed IWE canvas, objectives.py:191-192
+
+
+def global_last_timestamp(ts_local, group=None):
+    """Last timestamp of the WHOLE stream (the reference warps every event to ts[-1],
+    objectives.py:186) from each rank's time-sorted shard, as a Python float (f64)."""
+    last = ts_local[-1:].to(torch.float64) if ts_local.numel() else torch.full((1,), float("-inf"), dtype=torch.float64,
+                                                                               device=ts_local.device)
+    last = last.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(last, op=dist.ReduceOp.MAX, group=group)
+    return float(last.item())
+
+
+def _cmax_images_cuda(params, xs, ys, ts, ps, t_ref, img_size, want_grad, use_polarity):
+    """This rank's partial IWE and derivative images, [3][Hs+1][Ws+1] f32, and the number of its
+    events that index outside the canvas (evk_cmax_linvel_variance_f64/_f32 with image outputs)."""
+    from . import _lib
+    L = _lib.lib()
+    Hs, Ws = SENSOR_SIZE
+    dev = xs.device
+    with torch.cuda.device(dev):
+        images = torch.zeros((3, Hs + 1, Ws + 1), dtype=torch.float32, device=dev)
+        oob = torch.zeros(1, dtype=torch.int64, device=dev)
+        n = int(xs.shape[0])
+        if n == 0:
+            return images, oob
+        ws = _lib.scratch("cmax_ws", L.evk_cmax_workspace_bytes(Hs, Ws), dev)
+        result = torch.zeros(12, dtype=torch.float64, device=dev)
+        flags = (_lib.CMAX_WANT_GRAD if want_grad else 0) | (0 if use_polarity else _lib.CMAX_ABS_POLARITY)
+        diwe = images[1:] if want_grad else None
+        if ts.dtype == torch.float64:
+            x, y, t, p = (a.to(torch.float64).contiguous() for a in (xs, ys, ts, ps))
+            _lib.check(L.evk_cmax_linvel_variance_f64(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), n, 1.0,
+                                                      float(params[0]), float(params[1]), float(t_ref), int(img_size[0]),
+                                                      int(img_size[1]), Hs, Ws, 0.0, flags, _lib.ptr(result), _lib.ptr(images[0]),
+                                                      _lib.ptr(diwe), _lib.ptr(ws), ws.numel(), _lib.stream()))
+        else:
+            x, y, p = (a.to(torch.float32).contiguous() for a in (xs, ys, ps))
+            t = (ts.to(torch.float32) - float(t_ref)).contiguous()      # fast mode: t relative to the reference time
+            _lib.check(L.evk_cmax_linvel_variance_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), n, 1.0,
+                                                      float(params[0]), float(params[1]), int(img_size[0]), int(img_size[1]),
+                                                      Hs, Ws, 0.0, flags, _lib.ptr(result), _lib.ptr(images[0]), _lib.ptr(diwe),
+                                                      _lib.ptr(ws), ws.numel(), _lib.stream()))
+        oob.copy_(result[4:5])
+        return images, oob
+
+
+def _cmax_tail_cuda(images, blur_sigma, want_grad):
+    """(f, g) of the reduced images (evk_variance_objective_f32)."""
+    from . import _lib
+    L = _lib.lib()
+    dev = images.device
+    Hc, Wc = int(images.shape[1]), int(images.shape[2])
+    with torch.cuda.device(dev):
+        ws = _lib.scratch("cmax_ws", L.evk_cmax_workspace_bytes(Hc - 1, Wc - 1), dev)
+        result = torch.zeros(12, dtype=torch.float64, device=dev)
+        _lib.check(L.evk_variance_objective_f32(_lib.ptr(images[0]), _lib.ptr(images[1:]) if want_grad else None, Hc, Wc,
+                                                float(blur_sigma), _lib.CMAX_WANT_GRAD if want_grad else 0, _lib.ptr(result),
+                                                _lib.ptr(ws), ws.numel(), _lib.stream()))
+        res = result.cpu().numpy()
+    import numpy as np
+    return float(res[0]), np.array([res[1], res[2]])
+
+
+def cmax_variance_sharded(params, xs, ys, ts, ps, img_size, blur_sigma=1.0, group=None, t_ref=None,
+                          want_grad=True, use_polarity=True, compute_images=None, compute_tail=None):
+    """
+    variance_objective.evaluate_function / evaluate_gradient with linvel_warp (reference
+    objectives.py:211-264) for a stream whose events are spread over the ranks of `group`: every
+    rank splats ITS shard (tensors on its own GPU; f64 = parity mode, f32 = fast mode) into a
+    partial image of warped events and its two derivative images, ONE sum all-reduce of those
+    3 x 181 x 241 floats joins them, and every rank evaluates blur + variance (+ gradient) of the
+    full images.  Returns (f, g) -- identical on all ranks.
+    @param t_ref the stream's last timestamp if known (skips one scalar all-reduce)
+    @param compute_images, compute_tail injection points for the gloo tests (CPU oracle)
+    """
+    if t_ref is None:
+        t_ref = global_last_timestamp(ts, group)
+    images, oob = (compute_images or _cmax_images_cuda)(params, xs, ys, ts, ps, t_ref, img_size, want_grad, use_polarity)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(images, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(oob, op=dist.ReduceOp.SUM, group=group)
+    if int(oob.item()) != 0:
+        raise IndexError("%d warped events index outside the IWE canvas" % int(oob.item()))
+    return (compute_tail or _cmax_tail_cuda)(images, blur_sigma, want_grad)

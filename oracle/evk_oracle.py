@@ -155,14 +155,16 @@ def warp_flow_f32(xs, ys, ts, flow, t0=None):
 
 
 def iwe_linvel(params, xs, ys, ts, ps, img_size, compute_gradient=False, use_polarity=True,
-               sensor_size=(180, 240)):
-    """get_iwe with linvel_warp, objectives.py:184-192 -> (iwe, d_iwe or None)."""
+               sensor_size=(180, 240), t_ref=None):
+    """get_iwe with linvel_warp, objectives.py:184-192 -> (iwe, d_iwe or None).
+    t_ref: reference time of the warp; the reference uses ts[-1] (objectives.py:186), a shard of a
+    longer stream passes the stream's last timestamp."""
     x, y, t, p = (_c(a, np.float64) for a in (xs, ys, ts, ps))
     Hs, Ws = int(sensor_size[0]), int(sensor_size[1])
     iwe = np.zeros((Hs + 1, Ws + 1), np.float32)
     d = np.zeros((2, Hs + 1, Ws + 1), np.float32) if compute_gradient else None
     oob = lib().evo_iwe_linvel(_p(x), _p(y), _p(t), _p(p), x.shape[0], float(params[0]),
-                               float(params[1]), float(t[-1]), int(img_size[0]), int(img_size[1]),
+                               float(params[1]), float(t[-1] if t_ref is None else t_ref), int(img_size[0]), int(img_size[1]),
                                Hs, Ws, int(bool(use_polarity)), _p(iwe),
                                _p(d) if d is not None else None)
     if oob:

@@ -124,6 +124,42 @@ def test_vs_oracle_random(oracle, sigma):
         assert np.abs(gr - go).max() <= 1e-5 * grad_scale(iwe, d)
 
 
+def test_sharded_evaluation_matches_whole_stream(oracle):
+    """partial images of the shards summed == the image of the whole stream; the sharded
+    entry (world size 1 here, NCCL in bench.py --gpus N, gloo in test_parallel_gloo) gives f, g."""
+    import torch
+    from event_utils_b200 import parallel
+    x, y, t, p = make_events(9, 300001, 180, 240, dtype=np.float64)
+    t = t + 2.0
+    params, size = (30.0, -20.0), (180, 240)
+    fo, go = oracle.cmax_variance(params, x, y, t, p, blur_sigma=1.0)
+    iwe, d = oracle.iwe_linvel(params, x, y, t, p, size, True)
+    dev = [torch.from_numpy(a).cuda() for a in (x, y, t, p)]
+    f, g = parallel.cmax_variance_sharded(params, *dev, size, 1.0)
+    assert abs(f - fo) <= 1e-5 * abs(fo)
+    assert np.abs(g - go).max() <= 1e-5 * grad_scale(iwe, d)
+    # three uneven shards (one empty), joined by hand the way the all-reduce does
+    t_ref = parallel.global_last_timestamp(dev[2])
+    assert t_ref == float(t[-1])
+    total = torch.zeros((3, 181, 241), device="cuda")
+    for lo, hi in ((0, 100000), (100000, 100000), (100000, 300001)):
+        im, oob = parallel._cmax_images_cuda(params, *(a[lo:hi] for a in dev), t_ref, size, True, True)
+        assert int(oob) == 0
+        total += im
+    assert_close_to_max(total[0].cpu().numpy(), iwe, 1e-5)
+    assert_close_to_max(total[1:].cpu().numpy(), d, 1e-5)
+    f3, g3 = parallel._cmax_tail_cuda(total, 1.0, True)
+    assert abs(f3 - fo) <= 1e-5 * abs(fo)
+    assert np.abs(g3 - go).max() <= 1e-5 * grad_scale(iwe, d)
+    # f32 fast mode shards
+    dev32 = [a.float() for a in dev]
+    f4, g4 = parallel.cmax_variance_sharded(params, *dev32, size, 1.0, t_ref=float(dev32[2][-1]))
+    x32, y32, t32, p32 = (a.cpu().numpy().astype(np.float64) for a in dev32)
+    fo4, go4 = oracle.cmax_variance(params, x32, y32, t32, p32, blur_sigma=1.0)
+    assert abs(f4 - fo4) <= 1e-4 * abs(fo4)
+    assert np.abs(g4 - go4).max() <= 1e-3 * grad_scale(iwe, d)
+
+
 def test_f32_fast_mode(oracle):
     from event_utils_b200.contrast_max import objectives
     from event_utils_b200.contrast_max.warps import linvel_warp

@@ -65,6 +65,58 @@ def test_sharded_voxel_world2(tmp_path):
     assert spans[0][0] == 0 and spans[0][1] == spans[1][0] and spans[1][1] == 30001
 
 
+def _cmax_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from event_utils_b200.parallel import cmax_variance_sharded, global_last_timestamp, shard_bounds
+    from oracle import evk_oracle as O
+    rng = np.random.default_rng(11)
+    n = 40001
+    x = rng.uniform(0, 240, n)
+    y = rng.uniform(0, 180, n)
+    t = np.sort(rng.uniform(0, 0.05, n)) + 1.0
+    p = (rng.integers(0, 2, n) * 2 - 1).astype(np.float64)
+    params, img_size = (35.0, -22.0), (180, 240)
+    lo, hi = shard_bounds(n, world, rank)
+
+    def images(params, xs, ys, ts, ps, t_ref, img_size, want_grad, use_polarity):
+        out = torch.zeros((3, 181, 241))
+        if xs.numel():
+            iwe, d = O.iwe_linvel(params, xs.numpy(), ys.numpy(), ts.numpy(), ps.numpy(), img_size, compute_gradient=want_grad,
+                                  use_polarity=use_polarity, t_ref=t_ref)
+            out[0] = torch.from_numpy(iwe)
+            if want_grad:
+                out[1:] = torch.from_numpy(d)
+        return out, torch.zeros(1, dtype=torch.int64)
+
+    def tail(images, blur_sigma, want_grad):
+        a = images.numpy()
+        return O.variance_f(a[0], blur_sigma), (O.variance_g(a[0], a[1:], blur_sigma) if want_grad else np.zeros(2))
+
+    sh = [torch.from_numpy(a[lo:hi]) for a in (x, y, t, p)]
+    assert global_last_timestamp(sh[2]) == float(t[-1])
+    f, g = cmax_variance_sharded(params, *sh, img_size, 1.0, compute_images=images, compute_tail=tail)
+    f_ref, g_ref = O.cmax_variance(params, x, y, t, p, img_size, 1.0)
+    # an empty shard on rank 0
+    e = [torch.from_numpy(a[:0] if rank == 0 else a) for a in (x, y, t, p)]
+    f2, g2 = cmax_variance_sharded(params, *e, img_size, 1.0, compute_images=images, compute_tail=tail)
+    np.save(os.path.join(out_dir, "cmax%d.npy" % rank), np.array([f, g[0], g[1], f_ref, g_ref[0], g_ref[1], f2, g2[0], g2[1]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_cmax_world2(tmp_path):
+    world = 2
+    mp.spawn(_cmax_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rows = [np.load(tmp_path / ("cmax%d.npy" % r)) for r in range(world)]
+    assert np.array_equal(rows[0], rows[1])           # every rank returns the same numbers
+    f, g, f_ref, g_ref, f2, g2 = rows[0][0], rows[0][1:3], rows[0][3], rows[0][4:6], rows[0][6], rows[0][7:9]
+    assert abs(f - f_ref) <= 1e-5 * abs(f_ref) and abs(f2 - f_ref) <= 1e-5 * abs(f_ref)
+    scale = np.abs(g_ref).max()
+    assert np.abs(g - g_ref).max() <= 1e-4 * scale and np.abs(g2 - g_ref).max() <= 1e-4 * scale
+
+
 def test_shard_bounds_cover():
     sys.path.insert(0, ROOT)
     from event_utils_b200.parallel import shard_bounds
