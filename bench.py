@@ -421,12 +421,18 @@ def run_ours(args, rank, local_rank, world):
         if not args.no_extra:
             del x, y, t, p
             torch.cuda.empty_cache()
-            extra = secondary_metrics(L, _lib, device, peak)
+            try:
+                extra = secondary_metrics(L, _lib, device, peak)
+            except Exception as exc:   # a secondary number must never cost the headline line
+                extra = {"error": repr(exc)}
 
     if world > 1 and not args.no_extra:
         del x, y, t, p
         torch.cuda.empty_cache()
-        sharded = sharded_cmax_metric(device, world, rank)
+        try:
+            sharded = sharded_cmax_metric(device, world, rank)
+        except Exception as exc:   # a secondary number must never cost the headline line
+            sharded = {"error": repr(exc)}
         if rank == 0:
             extra = {"cmax_sharded": sharded}
 
@@ -467,6 +473,7 @@ def sharded_cmax_metric(device, world, rank):
     """Contrast-maximisation (f, g) evaluations of ONE stream sharded over the ranks: per
     evaluation each rank splats its 50 M events, one all-reduce joins the 3 x 181 x 241 partial images,
     every rank evaluates the objective.  Timed on the device, max over ranks."""
+    import torch.distributed as dist
     from event_utils_b200.parallel import cmax_variance_sharded
     n = N_PER_GPU
     g = torch.Generator(device=device)
