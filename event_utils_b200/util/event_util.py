@@ -1,5 +1,10 @@
-"""The one helper of lib/util/event_util.py that sits on the hot path."""
+"""The helpers of lib/util/event_util.py that the hot path and its drivers use."""
 import numpy as np
+
+
+def infer_resolution(xs, ys):
+    """Sensor size guessed from the largest coordinates, [max(y)+1, max(x)+1] (event_util.py:5-13)."""
+    return [np.max(ys) + 1, np.max(xs) + 1]
 
 
 def events_bounds_mask(xs, ys, x_min, x_max, y_min, y_max):

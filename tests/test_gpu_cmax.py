@@ -109,6 +109,58 @@ def test_adaptive_lifespan_and_object_protocol():
     assert jx.shape == (2, len(ev[0])) and np.all(jx[1] == 0) and np.all(jy[0] == 0)
 
 
+def _moving_points(rng, n_pts, per_pt, x_lo, x_hi, v, span=0.04):
+    """points at rest positions inside [x_lo, x_hi) x [30, 150) seen at random times, moving with velocity v"""
+    x_ref = np.repeat(rng.uniform(x_lo, x_hi, n_pts), per_pt)
+    y_ref = np.repeat(rng.uniform(30, 150, n_pts), per_pt)
+    t = rng.uniform(0, span, n_pts * per_pt)
+    return x_ref + (t - span) * v[0], y_ref + (t - span) * v[1], t
+
+
+def test_grid_search_optimisation_and_objective_surface(oracle):
+    from event_utils_b200.contrast_max import objectives as O
+    from event_utils_b200.contrast_max.events_cmax import grid_search_optimisation, sample_objective_function
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    rng = np.random.default_rng(21)
+    v_true = (60.0, -35.0)
+    x, y, t = _moving_points(rng, 300, 40, 30, 210, v_true)
+    order = np.argsort(t)
+    x, y, t = x[order], y[order], t[order]
+    t[-1] = 0.04
+    p = np.ones_like(t)
+    out = grid_search_optimisation(x, y, t, p, linvel_warp(), O.variance_objective(), (180, 240), th0=2)
+    assert np.abs(np.array(out["min_params"]) - np.array(v_true)).max() < 4.0, out["min_params"]
+    f_true = O.variance_objective().evaluate_function(v_true, x, y, t, p, linvel_warp(), (180, 240), 1.0)
+    assert out["min_func_eval"] <= 0.8 * f_true          # both negative: within 20 % of the contrast at the truth
+    # the objective surface image: every pixel against the oracle, then the normalisation
+    img = sample_objective_function(x, y, t, p, x_range=(-100, 100), y_range=(-80, 80), resolution=20)
+    assert img.shape == (8, 10)
+    raw = np.array([[-oracle.cmax_variance((c * 20 - 100, r * 20 - 80), x, y, t, p, blur_sigma=0.0, want_grad=False)[0]
+                     for c in range(10)] for r in range(8)])
+    expect = (raw - raw.min()) / (raw.max() - raw.min() + 1e-6)
+    assert np.abs(img - expect).max() <= 1e-5
+    assert np.unravel_index(np.argmax(img), img.shape) == (2, 8)      # the sample nearest (60, -35)
+
+
+def test_grid_cmax_two_motions():
+    """two halves of the sensor moving differently: every roi recovers its own velocity"""
+    from event_utils_b200.contrast_max.events_cmax import grid_cmax
+    rng = np.random.default_rng(22)
+    va, vb = (50.0, 20.0), (-40.0, -30.0)
+    xa, ya, ta = _moving_points(rng, 150, 40, 20, 100, va)
+    xb, yb, tb = _moving_points(rng, 150, 40, 140, 220, vb)
+    x, y, t = np.concatenate((xa, xb)), np.concatenate((ya, yb)), np.concatenate((ta, tb))
+    order = np.argsort(t)
+    x, y, t = x[order], y[order], t[order]
+    p = np.ones_like(t)
+    params, rois, scores = grid_cmax(x, y, t, p, roi_size=(int(np.max(y)) + 1, 120))
+    assert len(params) == len(rois) == len(scores) == 2
+    assert rois[0][1] == 0 and rois[1][1] == 120
+    assert np.abs(np.array(params[0]) - np.array(va)).max() < 5.0, params
+    assert np.abs(np.array(params[1]) - np.array(vb)).max() < 5.0, params
+    assert all(s < 0 for s in scores)
+
+
 @pytest.mark.parametrize("sigma", [1.0, 0.0, 3.0])
 def test_vs_oracle_random(oracle, sigma):
     from event_utils_b200.contrast_max.objectives import get_iwe, variance_objective

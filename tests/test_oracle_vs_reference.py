@@ -65,3 +65,15 @@ def test_cmax(ref, oracle, sigma):
         iwe, d = ref.objectives.get_iwe(params, x, y, t, p, warp, (180, 240), compute_gradient=True)
         scale = np.sqrt(np.mean((2 * (iwe - iwe.mean())) ** 2) * np.mean(d ** 2))
         assert np.abs(go - g).max() <= 1e-5 * scale
+
+
+def test_find_new_range_matches_reference(ref):
+    """the grid-search driver's interval update (events_cmax.py:160-182), host logic only"""
+    import importlib
+    ref_cmax = importlib.import_module("lib.contrast_max.events_cmax")
+    from event_utils_b200.contrast_max.events_cmax import find_new_range
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        axis = np.sort(rng.uniform(-200, 200, rng.integers(3, 9)))
+        value = rng.choice(axis) if rng.random() < 0.7 else rng.uniform(-250, 250)
+        assert np.array_equal(np.asarray(ref_cmax.find_new_range(axis, value)), np.asarray(find_new_range(axis, value)))
