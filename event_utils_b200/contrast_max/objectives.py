@@ -79,13 +79,34 @@ _result_bufs = {}
 
 
 def _result_buffers(dev):
-    """Per-device result buffers reused across evaluations: 12 doubles on the device and a pinned host
-    mirror (a fresh torch.zeros + pageable .cpu() per call costs ~25 us of a ~90 us evaluation)."""
+    """Per-device result buffer reused across evaluations: 12 doubles of PINNED HOST memory that the
+    last kernel of an evaluation writes straight over PCIe (pinned allocations are device-addressable
+    under unified addressing), so reading a result back is one stream synchronise -- no device buffer,
+    no D2H copy operation (a fresh torch.zeros + pageable .cpu() per call cost ~25 us of a ~90 us
+    evaluation, a pinned mirror + copy_ still ~10 us).  Returns (tensor, numpy view)."""
     b = _result_bufs.get(dev)
     if b is None:
-        b = (torch.zeros(12, dtype=torch.float64, device=dev), torch.zeros(12, dtype=torch.float64).pin_memory())
+        host = torch.zeros(12, dtype=torch.float64).pin_memory()
+        b = (host, host.numpy())
         _result_bufs[dev] = b
     return b
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the context manager costs
+    several microseconds per evaluation)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
 
 
 def _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, want_grad, use_polarity,
@@ -104,10 +125,10 @@ def _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, want_grad, use_p
         raise IndexError("index -1 is out of bounds for axis 0 with size 0")
     Hs, Ws = SENSOR_SIZE
     dev = ev.x.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         ws_bytes = L.evk_cmax_workspace_bytes(Hs, Ws)
         ws = _lib.scratch("cmax_ws", ws_bytes, dev)
-        result, result_host = _result_buffers(dev)
+        result, result_view = _result_buffers(dev)
         iwe = torch.empty((Hs + 1, Ws + 1), dtype=torch.float32, device=dev) if want_images else None
         d_iwe = torch.empty((2, Hs + 1, Ws + 1), dtype=torch.float32, device=dev) if (want_images and want_grad) else None
         flags = (_lib.CMAX_WANT_GRAD if want_grad else 0) | (0 if use_polarity else _lib.CMAX_ABS_POLARITY) \
@@ -132,9 +153,8 @@ def _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, want_grad, use_p
                 float(p_scale), float(params[0]), float(params[1]), int(img_size[0]), int(img_size[1]),
                 Hs, Ws, sigma, flags, int(objective), float(obj_param), _lib.ptr(result), _lib.ptr(iwe), _lib.ptr(d_iwe),
                 _lib.ptr(ws), ws.numel(), _lib.stream()))
-        result_host.copy_(result, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        res = result_host.numpy().copy()
+        res = result_view.copy()
         if res[4] != 0:
             raise IndexError("%d warped events index outside the IWE canvas %s" % (int(res[4]), (Hs + 1, Ws + 1)))
         return res, (iwe.cpu().numpy() if iwe is not None else None), (d_iwe.cpu().numpy() if d_iwe is not None else None)

@@ -52,6 +52,7 @@ struct CmaxArgs {
     double vx, vy, t_ref;  // linvel
     double p_scale;        // polarity multiplier (objectives.py:225 uses 100)
     const float *flow;     // dense flow [2][Hs][Ws]
+    const float2 *flow_uv; // the same, interleaved {u,v} per pixel (built per call in the workspace)
     float flow_t0;
     int Hm, Wm;  // bounds-mask size (img_size)
     int Hc, Wc;  // canvas = sensor + 1
@@ -117,11 +118,6 @@ __device__ __forceinline__ void splat(const CmaxArgs &A, float *acc, float xf, f
     }
 }
 
-__device__ __forceinline__ float flow_tap(const float *f, int H, int W, int yy, int xx)
-{
-    return ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? __ldg(f + (int64_t)yy * W + xx) : 0.0f;
-}
-
 // One event's four components as loaded (f64 in parity mode, f32 otherwise).
 template <int WARP> struct EvT { using type = float; };
 template <> struct EvT<WARP_LINVEL_F64> { using type = double; };
@@ -176,7 +172,6 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const 
         float p = e.p;
         if (A.abs_polarity) p = fabsf(p);
         const int H = A.Hc - 1, W = A.Wc - 1;
-        const float *fu = A.flow, *fv = A.flow + (int64_t)H * W;
         const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
         const float gx = __fsub_rn(__fmul_rn(__fdiv_rn(xe, wm1), 2.0f), 1.0f);
         const float gy = __fsub_rn(__fmul_rn(__fdiv_rn(ye, hm1), 2.0f), 1.0f);
@@ -191,10 +186,11 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const 
             const float ne = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(ys, iy));
             const float sw = __fmul_rn(__fsub_rn(xs, ix), __fsub_rn(iy, fy));
             const float se = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(iy, fy));
-            u = __fadd_rn(u, __fmul_rn(flow_tap(fu, H, W, y0, x0), nw));         v = __fadd_rn(v, __fmul_rn(flow_tap(fv, H, W, y0, x0), nw));
-            u = __fadd_rn(u, __fmul_rn(flow_tap(fu, H, W, y0, x0 + 1), ne));     v = __fadd_rn(v, __fmul_rn(flow_tap(fv, H, W, y0, x0 + 1), ne));
-            u = __fadd_rn(u, __fmul_rn(flow_tap(fu, H, W, y0 + 1, x0), sw));     v = __fadd_rn(v, __fmul_rn(flow_tap(fv, H, W, y0 + 1, x0), sw));
-            u = __fadd_rn(u, __fmul_rn(flow_tap(fu, H, W, y0 + 1, x0 + 1), se)); v = __fadd_rn(v, __fmul_rn(flow_tap(fv, H, W, y0 + 1, x0 + 1), se));
+            const float4 top = flow_row<true>(A.flow, A.flow_uv, H, W, y0, x0), bot = flow_row<true>(A.flow, A.flow_uv, H, W, y0 + 1, x0);
+            u = __fadd_rn(u, __fmul_rn(top.x, nw)); v = __fadd_rn(v, __fmul_rn(top.y, nw));
+            u = __fadd_rn(u, __fmul_rn(top.z, ne)); v = __fadd_rn(v, __fmul_rn(top.w, ne));
+            u = __fadd_rn(u, __fmul_rn(bot.x, sw)); v = __fadd_rn(v, __fmul_rn(bot.y, sw));
+            u = __fadd_rn(u, __fmul_rn(bot.z, se)); v = __fadd_rn(v, __fmul_rn(bot.w, se));
         }
         const float d = __fsub_rn(te, A.flow_t0);
         splat<false>(A, acc, __fadd_rn(xe, __fmul_rn(u, d)), __fadd_rn(ye, __fmul_rn(v, d)), p, 0.0f, true, oob);
@@ -753,6 +749,12 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, int objective, dou
     A.oob = ws.oob;
     // counters (gsums, gmax, sums, oob) and the R accumulator replicas are contiguous: one memset
     EVK_CUDA(cudaMemsetAsync(ws.gsums, 0, (size_t)((char *)ws.acc - (char *)ws.gsums) + (size_t)R * npix * kBlockFloats * sizeof(float), st));
+    if (WARP == WARP_FLOW_F32 && A.n > 0) {
+        // the generic objectives' weight image (unused by the variance tail) holds the interleaved flow
+        prof_count(1);
+        launch_flow_interleave(A.flow, (int64_t)Hs * Ws, reinterpret_cast<float2 *>(ws.w), st);
+        A.flow_uv = reinterpret_cast<const float2 *>(ws.w);
+    }
     if (A.n > 0) {
         ProfScope prof(st);
         prof_count(1);

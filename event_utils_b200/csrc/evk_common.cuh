@@ -47,6 +47,9 @@ int launch_image_hot(const float *x, const float *y, const float *p, int64_t n, 
                      float clipy, int mode, int force_cache, float *out, float *ws, unsigned *out_u32,
                      unsigned long long *oob, cudaStream_t st);
 
+// evk_image.cu: dense flow [2][H][W] -> interleaved [H][W] {u, v} pairs (see flow_row below)
+void launch_flow_interleave(const float *flow, int64_t npix, float2 *uv, cudaStream_t st);
+
 static inline unsigned variant_of(unsigned flags) { return flags & EVK_VARIANT_MASK; }
 
 // Persistent-style launch geometry: exactly ONE wave -- SM count x the number of CTAs of this
@@ -143,5 +146,30 @@ __device__ __forceinline__ void flush_oob(unsigned long long *oob, unsigned loca
 }
 
 #endif  // __CUDACC__
+
+// ---- dense-flow gather (optic_flow.py:37-44 + ATen grid_sampler bilinear/zeros/align_corners) ----
+// the two taps (x0, x0+1) of row yy as {u0, v0, u1, v1}; out-of-image taps are zero (grid_sample zero padding).
+// INTERLEAVED: 16 contiguous bytes -> one LDG.128 when x0 is even, two LDG.64 otherwise; planar: four LDG.32.
+template <bool INTERLEAVED>
+__device__ __forceinline__ float4 flow_row(const float *flow, const float2 *uv, int H, int W, int yy, int x0)
+{
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)yy >= (unsigned)H) return r;
+    const bool in0 = (unsigned)x0 < (unsigned)W, in1 = (unsigned)(x0 + 1) < (unsigned)W;
+    if (INTERLEAVED) {
+        const float2 *row = uv + (int64_t)yy * W;
+        if (in0 && in1 && ((x0 & 1) == 0) && ((W & 1) == 0)) {
+            r = __ldg(reinterpret_cast<const float4 *>(row + x0));
+        } else {
+            if (in0) { const float2 a = __ldg(row + x0); r.x = a.x; r.y = a.y; }
+            if (in1) { const float2 c = __ldg(row + x0 + 1); r.z = c.x; r.w = c.y; }
+        }
+    } else {
+        const float *fu = flow + (int64_t)yy * W, *fv = fu + (int64_t)H * W;
+        if (in0) { r.x = __ldg(fu + x0); r.y = __ldg(fv + x0); }
+        if (in1) { r.z = __ldg(fu + x0 + 1); r.w = __ldg(fv + x0 + 1); }
+    }
+    return r;
+}
 
 }  // namespace evk

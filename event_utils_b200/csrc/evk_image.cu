@@ -222,30 +222,6 @@ __global__ void __launch_bounds__(256) flow_interleave_kernel(const float *__res
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) uv[i] = make_float2(flow[i], flow[npix + i]);
 }
 
-// the two taps (x0, x0+1) of row yy as {u0, v0, u1, v1}; out-of-image taps are zero (grid_sample zero padding).
-// INTERLEAVED: 16 contiguous bytes -> one LDG.128 when x0 is even, two LDG.64 otherwise; planar: four LDG.32.
-template <bool INTERLEAVED>
-__device__ __forceinline__ float4 flow_row(const float *flow, const float2 *uv, int H, int W, int yy, int x0)
-{
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((unsigned)yy >= (unsigned)H) return r;
-    const bool in0 = (unsigned)x0 < (unsigned)W, in1 = (unsigned)(x0 + 1) < (unsigned)W;
-    if (INTERLEAVED) {
-        const float2 *row = uv + (int64_t)yy * W;
-        if (in0 && in1 && ((x0 & 1) == 0) && ((W & 1) == 0)) {
-            r = __ldg(reinterpret_cast<const float4 *>(row + x0));
-        } else {
-            if (in0) { const float2 a = __ldg(row + x0); r.x = a.x; r.y = a.y; }
-            if (in1) { const float2 c = __ldg(row + x0 + 1); r.z = c.x; r.w = c.y; }
-        }
-    } else {
-        const float *fu = flow + (int64_t)yy * W, *fv = fu + (int64_t)H * W;
-        if (in0) { r.x = __ldg(fu + x0); r.y = __ldg(fv + x0); }
-        if (in1) { r.z = __ldg(fu + x0 + 1); r.w = __ldg(fv + x0 + 1); }
-    }
-    return r;
-}
-
 template <bool INTERLEAVED>
 __device__ __forceinline__ void flow_one(float xe, float ye, float te, const float *flow, const float2 *uv, int H, int W, float wm1,
                                          float hm1, float t0, float &xo, float &yo)
@@ -308,6 +284,11 @@ __global__ void __launch_bounds__(256) warp_flow_kernel(const float *__restrict_
         xw[i] = xo;
         yw[i] = yo;
     }
+}
+
+void launch_flow_interleave(const float *flow, int64_t npix, float2 *uv, cudaStream_t st)
+{
+    flow_interleave_kernel<<<grid_simple(npix, 256), 256, 0, st>>>(flow, npix, uv);
 }
 
 }  // namespace evk
@@ -455,7 +436,7 @@ int evk_warp_flow_f32(const float *x, const float *y, const float *t, int64_t n,
     const float2 *uv = nullptr;
     if (inter) {
         prof_count(1);
-        flow_interleave_kernel<<<grid_simple(npix, 256), 256, 0, st>>>(flow, npix, static_cast<float2 *>(workspace));
+        launch_flow_interleave(flow, npix, static_cast<float2 *>(workspace), st);
         uv = static_cast<const float2 *>(workspace);
     }
     prof_count(1);

@@ -196,5 +196,14 @@ for scene in ("uniform", "lattice"):
                                                   wsc.data_ptr(), wsc.numel(), None))
     best, avg = timeit(run32, iters=3, warm=1)
     report("cmax f32 %s f+g" % scene, best, N, 16)
+    if scene == "uniform":
+        flow_c = torch.randn(2, 180, 240, device=dev) * 30
+        tf = (t64).float()
+        def runflow():
+            _lib.check(L.evk_cmax_flow_variance_f32(x32.data_ptr(), y32.data_ptr(), tf.data_ptr(), p32.data_ptr(), N, flow_c.data_ptr(), float(tf[-1]),
+                                                    180, 240, 1.0, 0, res.data_ptr(), None, wsc.data_ptr(), wsc.numel(), None))
+        best, avg = timeit(runflow, iters=3, warm=1)
+        report("cmax dense-flow warp + IWE + variance (f only)", best, N, 16)
+        del flow_c, tf
     print("   result", res.cpu().numpy())
     del x64, y64, t64, p64, x32, y32, t32, p32
