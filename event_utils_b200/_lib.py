@@ -19,6 +19,7 @@ BILINEAR = 0x2
 CLIP = 0x4
 NEGPOS_TRUTHY = 0x8
 WINDOW_PAIRS = 0x100000
+WINDOW_NEGPOS = 0x400000
 AUTO_SPAN = 0x200000
 VARIANT_AUTO = 0 << 8
 VARIANT_GLOBAL_RED = 1 << 8

@@ -176,6 +176,15 @@ __device__ __forceinline__ void voxel_event(const VoxelArgs &A, const HotCtx &hc
         const int64_t pix = (int64_t)yi * A.W + xi;
         float *out = A.out, *ws = A.ws;
         if (A.negpos) {
+            if (tn != tn) {
+                // dt == 0 (one event, or all stamps equal): the temporal weight is NaN and the reference's
+                // {0,1} polarity weight times NaN poisons the pixel in BOTH grids, every bin
+                const int64_t cells = (int64_t)A.H * A.W;
+                add_all_bins_slow<SINK>(A, out, ws, pix, tn, 1.0f);
+                add_all_bins_slow<SINK>(A, SINK == SINK_SCALAR ? out + cells * A.B : out, SINK == SINK_SCALAR ? ws : ws + cells * A.nq * 4,
+                                        pix, tn, 1.0f);
+                return;
+            }
             // fused neg/pos split: the event goes to exactly one of two grids with weight 1
             const bool pos = (A.negpos == 1) ? (p > 0.0f) : (p != 0.0f);
             const bool neg = (A.negpos == 1) ? (p <= 0.0f) : (p == 0.0f);
@@ -397,7 +406,7 @@ __global__ void __launch_bounds__(kThreads) voxel_windows_kernel(const VoxelArgs
             VoxelArgs Aw = A;
             Aw.t0 = A.t[first];
             Aw.dt = __fsub_rn(A.t[last - 1], Aw.t0);
-            Aw.out = A.out + (int64_t)w * A.B * A.H * A.W;
+            Aw.out = A.out + (int64_t)w * A.B * A.H * A.W * (A.negpos ? 2 : 1);
             for (int64_t i = first + (int64_t)s * kThreads + threadIdx.x; i < last; i += (int64_t)slices * kThreads)
                 voxel_event<SINK_SCALAR, false>(Aw, HotCtx{nullptr, nullptr, false}, A.x[i], A.y[i], A.t[i], A.p[i], oob);
         }
@@ -582,11 +591,13 @@ int evk_voxel_windows_f32(const float *x, const float *y, const float *t, const 
         return EVK_E_ARG;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grids = (flags & EVK_WINDOW_NEGPOS) ? 2 : 1;
     if (!(flags & EVK_ACCUMULATE))
-        EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)n_windows * B * H * W * sizeof(float), st));
+        EVK_CUDA(cudaMemsetAsync(out, 0, (size_t)n_windows * grids * B * H * W * sizeof(float), st));
     if (n_windows == 0) return EVK_OK;
     VoxelArgs A{};
     A.x = x; A.y = y; A.t = t; A.p = p;
+    A.negpos = grids == 2 ? ((flags & EVK_NEGPOS_TRUTHY) ? 2 : 1) : 0;
     A.bm1 = (float)(B - 1);
     A.B = B; A.H = H; A.W = W; A.nq = quads_for_bins(B);
     A.out = out; A.oob = oob;

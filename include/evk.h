@@ -47,6 +47,7 @@ extern "C" {
 #define EVK_CLIP 0x4u         /* events_to_image_torch(clip_out_of_range=True) semantics */
 #define EVK_AUTO_SPAN 0x200000u    /* voxel: ignore the t0/dt arguments, take t[0] and t[n-1]-t[0] on the device */
 #define EVK_WINDOW_PAIRS 0x100000u /* evk_voxel_windows_f32: offsets are (start,end) pairs, 2*n_windows entries */
+#define EVK_WINDOW_NEGPOS 0x400000u /* evk_voxel_windows_f32: out is [n_windows][2][B][H][W], the [p>0] / [p<=0] split per window */
 #define EVK_NEGPOS_TRUTHY 0x8u /* neg/pos split on numpy truthiness (p != 0) instead of p > 0 */
 /* kernel variant selection, bits 8..11 (0 = pick automatically) */
 #define EVK_VARIANT_SHIFT 8
@@ -128,6 +129,9 @@ int evk_voxel_packed_f32(const int16_t *x, const int16_t *y, const double *t, co
  * timestamp exactly as voxel_grid.py:133-134 does.  offsets: n_windows+1 int64 on the device.
  * With EVK_WINDOW_PAIRS offsets holds 2*n_windows entries, (start,end) per window (windows may then
  * overlap or leave gaps, as events_to_voxel_timesync_torch's do, voxel_grid.py:105-106).
+ * With EVK_WINDOW_NEGPOS out is [n_windows][2][B][H][W]: per window the two grids of
+ * events_to_neg_pos_voxel_torch (voxel_grid.py:155-182), what BaseVoxelDataset.get_voxel_grid builds
+ * with combined_voxel_channels=False (base_dataset.py:449-453).
  * n_events_hint: total number of events covered (0 = unknown), used only to size the launch. */
 int evk_voxel_windows_f32(const float *x, const float *y, const float *t, const float *p,
                           const int64_t *offsets, int n_windows, int64_t n_events_hint, int B, int H,

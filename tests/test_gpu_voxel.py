@@ -360,3 +360,41 @@ def test_sharded_stream_single_process(oracle):
     full = events_to_voxel_sharded(X, Y, T, P, 5, (90, 120))
     assert_close_to_max(full.cpu().numpy(), oracle.voxel_f32(x, y, t, p, 5, (90, 120)), 1e-5)
 
+
+
+def test_loader_window_tables_one_launch(oracle):
+    """every window of a loader table in one launch == get_voxel_grid per window (base_dataset.py:433-455),
+    combined and neg/pos channels, overlapping windows, an empty window, host and device inputs"""
+    from event_utils_b200.data_loaders import windows as Wn
+    from event_utils_b200.representations.voxel_grid import events_to_neg_pos_voxel_torch, events_to_voxel_torch
+    x, y, t, p = make_events(31, 60000, 40, 52)
+    xd, yd, td, pd = dev(x, y, t, p)
+    tables = [Wn.k_event_indices(len(x), 7000, 2000)[:-1], Wn.timeblock_indices(t, 0.013, 0.0),
+              np.array([[0, 10], [10, 10], [10, 60000], [59999, 60000]])]
+    for table in tables:
+        for combined in (True, False):
+            got = Wn.voxelize_event_windows(xd, yd, td, pd, table, 5, (40, 52), combined_voxel_channels=combined)
+            assert got.shape == (len(table), 5 if combined else 10, 40, 52)
+            for w, (i0, i1) in enumerate(table):
+                if i1 == i0:
+                    assert float(got[w].abs().sum()) == 0.0
+                    continue
+                sl = slice(int(i0), int(i1))
+                if combined:
+                    want = oracle.voxel_f32(x[sl], y[sl], t[sl], p[sl], 5, (40, 52))
+                    single = events_to_voxel_torch(xd[sl], yd[sl], td[sl], pd[sl], 5, sensor_size=(40, 52))
+                else:
+                    want = np.concatenate((oracle.voxel_f32(x[sl], y[sl], t[sl], (p[sl] > 0).astype(np.float32), 5, (40, 52)),
+                                           oracle.voxel_f32(x[sl], y[sl], t[sl], (p[sl] <= 0).astype(np.float32), 5, (40, 52))))
+                    single = torch.cat(events_to_neg_pos_voxel_torch(xd[sl], yd[sl], td[sl], pd[sl], 5, sensor_size=(40, 52)), 0)
+                if np.isnan(want).any():
+                    assert np.array_equal(np.isnan(want), np.isnan(got[w].cpu().numpy()))
+                    assert np.array_equal(np.isnan(want), np.isnan(single.cpu().numpy()))
+                    continue
+                assert_close_to_max(got[w].cpu().numpy(), want, 1e-5)
+                assert_close_to_max(got[w].cpu().numpy(), single.cpu().numpy(), 1e-5)
+    host = Wn.voxelize_event_windows(*(torch.from_numpy(a) for a in (x, y, t, p)), tables[0], 5, (40, 52))
+    assert torch.equal(host, Wn.voxelize_event_windows(xd, yd, td, pd, tables[0], 5, (40, 52))) or \
+        float((host - Wn.voxelize_event_windows(xd, yd, td, pd, tables[0], 5, (40, 52))).abs().max()) < 1e-4
+    with pytest.raises(Exception):
+        Wn.voxelize_event_windows(xd, yd, td, pd, [[0, 60001]], 5, (40, 52))

@@ -77,3 +77,40 @@ def test_find_new_range_matches_reference(ref):
         axis = np.sort(rng.uniform(-200, 200, rng.integers(3, 9)))
         value = rng.choice(axis) if rng.random() < 0.7 else rng.uniform(-250, 250)
         assert np.array_equal(np.asarray(ref_cmax.find_new_range(axis, value)), np.asarray(find_new_range(axis, value)))
+
+
+def test_window_tables_match_reference_loader(ref):
+    """k_events / t_seconds / fixed_frames / between_frames tables of BaseVoxelDataset
+    (base_dataset.py:322-417), built here vectorised"""
+    import importlib
+    bd = importlib.import_module("lib.data_loaders.base_dataset")
+    from event_utils_b200.data_loaders import windows as Wn
+    rng = np.random.default_rng(3)
+    ts = np.sort(rng.uniform(5.0, 7.5, 20000))
+    ts[100:110] = ts[100]                                   # repeated stamps
+
+    class Probe(bd.BaseVoxelDataset):                       # the table code only, no recording behind it
+        def __init__(self):
+            self.num_events, self.t0, self.tk = len(ts), ts[0], ts[-1]
+            self.duration = self.tk - self.t0
+            self.has_frames = False
+
+        def find_ts_index(self, timestamp):
+            return np.searchsorted(ts, timestamp)           # memmap_dataset.py:81-83
+
+    d = Probe()
+    for k, w in ((1000, 0), (1500, 500), (333, 33)):
+        d.set_voxel_method({"method": "k_events", "k": k, "sliding_window_w": w})
+        assert np.array_equal(np.asarray(d.event_indices), Wn.k_event_indices(len(ts), k, w))
+    for t, w in ((0.1, 0.0), (0.25, 0.05), (0.013, 0.0)):
+        d.set_voxel_method({"method": "t_seconds", "t": t, "sliding_window_t": w})
+        assert np.array_equal(np.asarray(d.event_indices), Wn.timeblock_indices(ts, t, w))
+    for nf in (1, 7, 40):
+        d.set_voxel_method({"method": "fixed_frames", "num_frames": nf})
+        assert np.array_equal(np.asarray(d.event_indices), Wn.fixed_frames_indices(ts, nf))
+    d.frame_ts = np.concatenate((np.sort(rng.uniform(5.0, 7.5, 30)), [9.0]))
+    d.num_frames = len(d.frame_ts)
+    d.set_voxel_method({"method": "between_frames"})
+    assert np.array_equal(np.asarray(d.event_indices), Wn.between_frame_indices(ts, d.frame_ts))
+    with pytest.raises(Exception):
+        Wn.check_event_indices(Wn.k_event_indices(1000, 300, 0).tolist() + [[900, 1200]], 1000)
