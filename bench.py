@@ -51,17 +51,19 @@ def measured_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def workload_config(world):
+def workload_config(world, mg_kind=None):
     return {
         "workload": ("50M uniform events -> 5x480x640 voxel grid (events_to_voxel_torch semantics), 1xB200"
                      if world == 1 else
                      "%dM events -> 5x480x640 voxel grid sharded over %d GPUs (50M-event time shard per GPU), "
-                     "one NCCL all-reduce of the grid" % (50 * world, world)),
+                     "one all-reduce of the grid per step" % (50 * world, world)),
         "events_per_gpu": N_PER_GPU, "bins": B, "height": H, "width": W,
         "layout": "SoA f32 x,y,t,p (16 B/event)",
         "seed": 2024,
         "l2_policy": "inputs (800 MB/step) larger than L2 (126 MB); no explicit flush",
-        "parallelism": ("events sharded x%d, global t0/dt agreed up front" % world) + ("; all-reduce of step k overlapped with the scatter of step k+1 (2 grid buffers)" if world > 1 else ""),
+        "parallelism": ("events sharded x%d, global t0/dt agreed up front" % world) + ((
+            "; fold + all-reduce fused in one kernel over NVLink peer memory (symmetric memory, two cross-GPU barriers), step k's reduce overlapped with the scatter of step k+1 (2 buffers)"
+            if mg_kind == "peer" else "; NCCL all-reduce of step k overlapped with the scatter of step k+1 (2 grid buffers)") if world > 1 else ""),
     }
 
 
@@ -233,7 +235,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mevents/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.gpus, "peer" if args.gpus > 1 else None),
         "cpu_baseline": {"value": value, "unit": "Mevents/s", "cores": torch.get_num_threads(), "host_cores": cores,
                          "kind": "port", "sample": sample, "cpu": cpu_model()},
         "e2e": {"value": value, "unit": "Mevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -273,8 +275,16 @@ def run_ours(args, rank, local_rank, world):
     # N > 1: double-buffered grids, the all-reduce of step k on a communication stream overlaps the
     # scatter of step k+1 (parallel.ShardedVoxelStream); every step still ends with its reduced grid.
     import event_utils_b200 as eu
-    from event_utils_b200.parallel import ShardedVoxelStream
-    pipe_mg = ShardedVoxelStream(B, (H, W), device) if world > 1 else None
+    from event_utils_b200.parallel import PeerReducedVoxel, ShardedVoxelStream
+    pipe_mg, mg_kind = None, None
+    if world > 1 and os.environ.get("EVK_BENCH_ALLREDUCE", "peer") == "peer":
+        # the product path: fold + all-reduce in one kernel over NVLink peer memory (symmetric memory)
+        try:
+            pipe_mg, mg_kind = PeerReducedVoxel(B, (H, W), device, depth=2), "peer"
+        except Exception as exc:       # no symmetric-memory support on this box: say so and take the NCCL stream
+            print("bench: PeerReducedVoxel unavailable (%r), using the NCCL stream" % (exc,), file=sys.stderr)
+    if world > 1 and pipe_mg is None:
+        pipe_mg, mg_kind = ShardedVoxelStream(B, (H, W), device), "nccl"
     eu.config.check_index_errors = False      # the bench reads the out-of-range counter once, after the timed region
 
     def step():
@@ -427,21 +437,25 @@ def run_ours(args, rank, local_rank, world):
                 extra = {"error": repr(exc)}
 
     if world > 1 and not args.no_extra:
+        try:
+            peer = peer_reduce_metric(device, x, y, t, p, t0, dt)
+        except Exception as exc:   # a secondary number must never cost the headline line
+            peer = {"error": repr(exc)}
         del x, y, t, p
         torch.cuda.empty_cache()
         try:
             sharded = sharded_cmax_metric(device, world, rank)
-        except Exception as exc:   # a secondary number must never cost the headline line
+        except Exception as exc:
             sharded = {"error": repr(exc)}
         if rank == 0:
-            extra = {"cmax_sharded": sharded}
+            extra = {"cmax_sharded": sharded, "voxel_single_call_latency": peer}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Mevents/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, mg_kind),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": 16 * n,
                     "d2h_bytes_per_step": 4 * B * H * W, "steps": e2e_steps,
@@ -471,6 +485,39 @@ def run_ours(args, rank, local_rank, world):
         os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
+
+
+def peer_reduce_metric(device, x, y, t, p, t0, dt):
+    """Latency of ONE sharded voxel build (not the pipelined stream of the headline): scatter + the fused
+    fold / all-reduce kernel over NVLink peer memory (parallel.PeerReducedVoxel) against scatter + fold + NCCL
+    all-reduce (parallel.events_to_voxel_sharded).  CUDA events, best of 10, max over ranks."""
+    import torch.distributed as dist
+    from event_utils_b200.parallel import PeerReducedVoxel, events_to_voxel_sharded
+    fused = PeerReducedVoxel(B, (H, W), device)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        best = 1e9
+        for _ in range(10):
+            dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            el = torch.tensor([a.elapsed_time(b)], device=device)
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+            best = min(best, float(el))
+        return best
+
+    ga = fused(x, y, t, p, t0, dt).clone()
+    gb = events_to_voxel_sharded(x, y, t, p, B, (H, W), t0=t0, dt=dt)
+    diff = float((ga - gb).abs().max() / gb.abs().max())
+    ms_f = timed(lambda: fused(x, y, t, p, t0, dt))
+    ms_n = timed(lambda: events_to_voxel_sharded(x, y, t, p, B, (H, W), t0=t0, dt=dt))
+    return {"fused_fold_peer_allreduce_ms": ms_f, "fold_plus_nccl_allreduce_ms": ms_n, "max_rel_diff": diff,
+            "what": "one call, %d M events per GPU; the fused kernel reads every rank's quad workspace and writes every rank's grid "
+                    "over NVLink (symmetric memory), two cross-GPU barriers" % (N_PER_GPU // 1000000)}
 
 
 def sharded_cmax_metric(device, world, rank):

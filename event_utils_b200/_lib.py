@@ -20,6 +20,7 @@ CLIP = 0x4
 NEGPOS_TRUTHY = 0x8
 WINDOW_PAIRS = 0x100000
 WINDOW_NEGPOS = 0x400000
+NO_FOLD = 0x800000
 AUTO_SPAN = 0x200000
 VARIANT_AUTO = 0 << 8
 VARIANT_GLOBAL_RED = 1 << 8
@@ -82,6 +83,8 @@ def _declare(L):
     L.evk_gather_bilinear_f64.argtypes = [vp, vp, i64, vp, ci, ci, vp, vp, vp]
     L.evk_warp_flow_f32.restype = ci
     L.evk_warp_flow_f32.argtypes = [vp, vp, vp, i64, vp, ci, ci, f32, vp, vp, vp, sz, vp]
+    L.evk_voxel_fold_allreduce_f32.restype = ci
+    L.evk_voxel_fold_allreduce_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, cu, vp]
     L.evk_warp_flow_workspace_bytes.restype = sz
     L.evk_warp_flow_workspace_bytes.argtypes = [ci, ci]
     L.evk_cmax_workspace_bytes.restype = sz

@@ -393,6 +393,46 @@ __global__ void __launch_bounds__(256) voxel_fold_kernel(const float *__restrict
     }
 }
 
+// Fused fold + all-reduce over NVLink peer memory (one process per GPU, every rank launches this
+// kernel on its own slice): rank r owns the pixels [pix_lo, pix_hi); for each of them it reads the
+// temporal quads of EVERY rank's workspace (16-byte peer loads, coalesced), sums them in rank order,
+// folds the overlapping quads into the B bins and stores the result into EVERY rank's output grid
+// (coalesced peer stores).  No intermediate partial grid, no NCCL; every cell is computed once, so all
+// ranks end up with bit-identical grids.  The caller separates it from the scatters before and the
+// readers after by a cross-GPU barrier (symmetric-memory signal pads).
+constexpr int kMaxPeers = 16;
+struct VoxelPeers {
+    const float4 *ws[kMaxPeers];
+    float *out[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(256) voxel_fold_allreduce_kernel(const VoxelPeers P, int world, int64_t pix_lo, int64_t pix_hi,
+                                                                   int64_t npix, int B, int nq)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t pix = pix_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < pix_hi; pix += stride) {
+        float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < nq; ++q) {
+            float4 cur = __ldcg(P.ws[0] + pix * nq + q);
+            for (int r = 1; r < world; ++r) {
+                const float4 o = __ldcg(P.ws[r] + pix * nq + q);
+                cur.x += o.x; cur.y += o.y; cur.z += o.z; cur.w += o.w;
+            }
+            const float vals[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int b = 3 * q + s;
+                if (b >= B) break;
+                if (s == 3 && q + 1 < nq) continue;  // emitted with slot 0 of the next quad
+                float v = vals[s];
+                if (s == 0 && q > 0) v += prev.w;
+                for (int r = 0; r < world; ++r) __stcg(P.out[r] + (int64_t)b * npix + pix, v);
+            }
+            prev = cur;
+        }
+    }
+}
+
 // Batched windows: CTA (w, s) scatters slice s of window w into out[w] with that window's own
 // t0 / dt (voxel_grid.py:133-134 applied per window, as voxel_grids_fixed_n_torch :53-56 does).
 __global__ void __launch_bounds__(kThreads) voxel_windows_kernel(const VoxelArgs A, const int64_t *__restrict__ offsets,
@@ -452,6 +492,12 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
         hot = true;
         A.hot_force = 1;
     }
+    const bool no_fold = (flags & EVK_NO_FOLD) != 0;
+    if (no_fold) {
+        // the caller folds (and reduces across GPUs) itself: the sums stay in the quad workspace
+        if (bil || A.negpos || workspace == nullptr) { set_error("evk_voxel: EVK_NO_FOLD needs a workspace and the plain (nearest, combined) grid"); return EVK_E_UNSUPPORTED; }
+        if (variant == EVK_VARIANT_GLOBAL_RED) variant = EVK_VARIANT_VECTOR_RED;
+    }
     if ((uint64_t)npix * quads_for_bins(A.B) * (A.negpos ? 2 : 1) >= 0xffffffffull) hot = false;  // 32-bit quad ids
     if (variant != EVK_VARIANT_VECTOR_RED && variant != EVK_VARIANT_GLOBAL_RED) {
         set_error("evk_voxel: variant 0x%x not available for this entry point", variant);
@@ -494,7 +540,7 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
 #undef EVK_LAUNCH
         EVK_CUDA(cudaGetLastError());
     }
-    if (sink == SINK_QUAD) {
+    if (sink == SINK_QUAD && !no_fold) {
         const int grid = grid_simple(npix, 256);
         prof_count(1);
         if (bil) {
@@ -540,7 +586,7 @@ int evk_voxel_f32(const float *x, const float *y, const float *t, const float *p
                   size_t workspace_bytes, unsigned long long *oob, void *stream)
 {
     using namespace evk;
-    int rc = check_common(n, B, H, W, out);
+    int rc = check_common(n, B, H, W, (flags & EVK_NO_FOLD) ? static_cast<const void *>(&rc) : out);
     if (rc) return rc;
     if (n > 0 && (!x || !y || !t || !p)) { set_error("evk_voxel_f32: null event array"); return EVK_E_ARG; }
     VoxelArgs A{};
@@ -615,6 +661,35 @@ int evk_voxel_windows_f32(const float *x, const float *y, const float *t, const 
                                                                                   (flags & EVK_WINDOW_PAIRS) ? 1 : 0);
     }
     EVK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+int evk_voxel_fold_allreduce_f32(const void *const *peer_workspaces, float *const *peer_outs, int world, int rank, int B, int H,
+                                 int W, unsigned flags, void *stream)
+{
+    using namespace evk;
+    (void)flags;
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || B < 1 || H < 1 || W < 1 || !peer_workspaces || !peer_outs) {
+        set_error("evk_voxel_fold_allreduce_f32: bad arguments (world=%d rank=%d, at most %d peers)", world, rank, kMaxPeers);
+        return EVK_E_ARG;
+    }
+    VoxelPeers P{};
+    for (int r = 0; r < world; ++r) {
+        if (!peer_workspaces[r] || !peer_outs[r] || ((uintptr_t)peer_workspaces[r] & 15)) {
+            set_error("evk_voxel_fold_allreduce_f32: peer %d: null or misaligned pointer", r);
+            return EVK_E_ARG;
+        }
+        P.ws[r] = static_cast<const float4 *>(peer_workspaces[r]);
+        P.out[r] = peer_outs[r];
+    }
+    const int64_t npix = (int64_t)H * W;
+    const int64_t lo = npix * rank / world, hi = npix * (rank + 1) / world;
+    if (hi > lo) {
+        prof_count(1);
+        voxel_fold_allreduce_kernel<<<grid_simple(hi - lo, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(P, world, lo, hi, npix, B,
+                                                                                                            quads_for_bins(B));
+        EVK_CUDA(cudaGetLastError());
+    }
     return EVK_OK;
 }
 

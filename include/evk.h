@@ -47,6 +47,7 @@ extern "C" {
 #define EVK_CLIP 0x4u         /* events_to_image_torch(clip_out_of_range=True) semantics */
 #define EVK_AUTO_SPAN 0x200000u    /* voxel: ignore the t0/dt arguments, take t[0] and t[n-1]-t[0] on the device */
 #define EVK_WINDOW_PAIRS 0x100000u /* evk_voxel_windows_f32: offsets are (start,end) pairs, 2*n_windows entries */
+#define EVK_NO_FOLD 0x800000u /* evk_voxel_f32: leave the sums in the quad workspace (out may be NULL); evk_voxel_fold_allreduce_f32 finishes */
 #define EVK_WINDOW_NEGPOS 0x400000u /* evk_voxel_windows_f32: out is [n_windows][2][B][H][W], the [p>0] / [p<=0] split per window */
 #define EVK_NEGPOS_TRUTHY 0x8u /* neg/pos split on numpy truthiness (p != 0) instead of p > 0 */
 /* kernel variant selection, bits 8..11 (0 = pick automatically) */
@@ -122,6 +123,16 @@ int evk_voxel_aos_f32(const float *ev, int64_t n, float t0, float dt, int B, int
 int evk_voxel_packed_f32(const int16_t *x, const int16_t *y, const double *t, const uint8_t *p, int64_t n,
                          double t_first, double t_last, int B, int H, int W, unsigned flags, float *out,
                          void *workspace, size_t workspace_bytes, unsigned long long *oob, void *stream);
+
+/* Multi-GPU finish of a sharded voxel build (no reference counterpart: the reference is single-process;
+ * SURVEY 8e): after every rank has run evk_voxel_f32(..., EVK_NO_FOLD) on its shard into a workspace that
+ * its peers can address (CUDA IPC / symmetric memory over NVLink), and a cross-GPU barrier, each rank calls
+ * this once: it reduces ITS slice of the pixels over all ranks' workspaces, folds the temporal quads into
+ * the B bins and writes the result into every rank's [B][H][W] grid -- fold and all-reduce in one kernel
+ * over peer memory.  A second cross-GPU barrier must follow before the grids are read or the workspaces
+ * reused.  peer_workspaces / peer_outs: HOST arrays of `world` device pointers, index = rank. */
+int evk_voxel_fold_allreduce_f32(const void *const *peer_workspaces, float *const *peer_outs, int world,
+                                 int rank, int B, int H, int W, unsigned flags, void *stream);
 
 /* Batched windows (voxel_grids_fixed_n_torch, voxel_grid.py:37-57; BaseVoxelDataset windows,
  * base_dataset.py:322-367): window w covers events [offsets[w], offsets[w+1]) and writes

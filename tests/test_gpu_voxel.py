@@ -398,3 +398,81 @@ def test_loader_window_tables_one_launch(oracle):
         float((host - Wn.voxelize_event_windows(xd, yd, td, pd, tables[0], 5, (40, 52))).abs().max()) < 1e-4
     with pytest.raises(Exception):
         Wn.voxelize_event_windows(xd, yd, td, pd, [[0, 60001]], 5, (40, 52))
+
+
+def test_fold_allreduce_kernel_on_one_device(oracle):
+    """evk_voxel_fold_allreduce_f32 with the peers emulated on one GPU: world 1 == the ordinary fold; world 3 (three shards, three workspaces, three grids, one call per emulated rank) == the whole
+    stream, and all grids are bit-identical."""
+    from event_utils_b200 import _lib
+    L = _lib.lib()
+    B, H, W = 5, 37, 53
+    x, y, t, p = make_events(41, 200000, H, W)
+    xd, yd, td, pd = dev(x, y, t, p)
+    t0, dt = float(t[0]), float(np.float32(t[-1]) - np.float32(t[0]))
+    oob = torch.zeros(1, dtype=torch.int64, device="cuda")
+    wsb = L.evk_voxel_workspace_bytes(B, H, W, 0)
+
+    def scatter(lo, hi, ws):
+        _lib.check(L.evk_voxel_f32(xd[lo:hi].data_ptr(), yd[lo:hi].data_ptr(), td[lo:hi].data_ptr(), pd[lo:hi].data_ptr(), hi - lo, t0, dt,
+                                   B, H, W, _lib.NO_FOLD, None, ws.data_ptr(), ws.numel(), oob.data_ptr(), None))
+
+    ref = torch.empty((B, H, W), device="cuda")
+    wsr = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    _lib.check(L.evk_voxel_f32(xd.data_ptr(), yd.data_ptr(), td.data_ptr(), pd.data_ptr(), len(x), t0, dt, B, H, W, _lib.VARIANT_VECTOR_RED,
+                               ref.data_ptr(), wsr.data_ptr(), wsr.numel(), oob.data_ptr(), None))
+    for bounds in ([(0, 200000)], [(0, 70000), (70000, 70000), (70000, 200000)]):
+        world = len(bounds)
+        wss = [torch.empty(wsb, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        outs = [torch.full((B, H, W), float("nan"), device="cuda") for _ in range(world)]
+        for (lo, hi), ws in zip(bounds, wss):
+            scatter(lo, hi, ws)
+        pw = (ctypes.c_void_p * world)(*[w.data_ptr() for w in wss])
+        po = (ctypes.c_void_p * world)(*[o.data_ptr() for o in outs])
+        for r in range(world):
+            _lib.check(L.evk_voxel_fold_allreduce_f32(pw, po, world, r, B, H, W, 0, None))
+        torch.cuda.synchronize()
+        for o in outs[1:]:
+            assert torch.equal(o, outs[0])
+        assert_close_to_max(outs[0].cpu().numpy(), ref.cpu().numpy(), 2e-6)   # two runs of float atomics: order differs
+        assert_close_to_max(outs[0].cpu().numpy(), oracle.voxel_f32(x, y, t, p, B, (H, W)), 1e-5)
+    assert int(oob) == 0
+    assert L.evk_voxel_fold_allreduce_f32(pw, po, 17, 0, B, H, W, 0, None) == -1
+    assert L.evk_voxel_f32(xd.data_ptr(), yd.data_ptr(), td.data_ptr(), pd.data_ptr(), len(x), t0, dt, B, H, W, _lib.NO_FOLD,
+                           None, None, 0, oob.data_ptr(), None) != 0          # NO_FOLD needs the workspace
+
+
+def _peer_worker(rank, world, port, out_dir):
+    import os
+    import sys
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from event_utils_b200.parallel import PeerReducedVoxel, events_to_voxel_sharded, shard_bounds
+    B, H, W = 5, 60, 80
+    x, y, t, p = make_events(43, 300001, H, W)
+    lo, hi = shard_bounds(len(x), world, rank)
+    sh = [torch.from_numpy(a[lo:hi]).cuda() for a in (x, y, t, p)]
+    t0, dt = float(t[0]), float(np.float32(t[-1]) - np.float32(t[0]))
+    fused = PeerReducedVoxel(B, (H, W), torch.device("cuda", rank))
+    for _ in range(3):                                    # the buffers are reused call after call
+        grid = fused(*sh, t0, dt).clone()
+    nccl = events_to_voxel_sharded(*sh, B, (H, W), t0=t0, dt=dt)
+    np.save(os.path.join(out_dir, "peer%d.npy" % rank), np.stack((grid.cpu().numpy(), nccl.cpu().numpy())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_peer_reduced_voxel_two_gpus(oracle, tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_peer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "peer0.npy"), np.load(tmp_path / "peer1.npy")
+    assert np.array_equal(a[0], b[0])                     # bit-identical on both ranks
+    x, y, t, p = make_events(43, 300001, 60, 80)
+    want = oracle.voxel_f32(x, y, t, p, 5, (60, 80))
+    assert_close_to_max(a[0], want, 1e-5)
+    assert_close_to_max(a[1], want, 1e-5)
