@@ -406,17 +406,33 @@ struct VoxelPeers {
     float *out[kMaxPeers];
 };
 
-__global__ void __launch_bounds__(256) voxel_fold_allreduce_kernel(const VoxelPeers P, int world, int64_t pix_lo, int64_t pix_hi,
-                                                                   int64_t npix, int B, int nq)
+// WORLD > 0: compile-time peer count (the peer loads of a pixel are all issued before the first add);
+// WORLD == 0: run-time count.  NQ likewise (2 quads = the 5-bin grid of the data loaders).
+template <int WORLD, int NQ>
+__global__ void __launch_bounds__(256) voxel_fold_allreduce_kernel(const VoxelPeers P, int world_rt, int64_t pix_lo, int64_t pix_hi,
+                                                                   int64_t npix, int B, int nq_rt)
 {
+    const int world = WORLD ? WORLD : world_rt;
+    const int nq = NQ ? NQ : nq_rt;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t pix = pix_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < pix_hi; pix += stride) {
         float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
         for (int q = 0; q < nq; ++q) {
-            float4 cur = __ldcg(P.ws[0] + pix * nq + q);
-            for (int r = 1; r < world; ++r) {
-                const float4 o = __ldcg(P.ws[r] + pix * nq + q);
-                cur.x += o.x; cur.y += o.y; cur.z += o.z; cur.w += o.w;
+            float4 part[WORLD ? WORLD : 1];
+            float4 cur;
+            if (WORLD) {
+#pragma unroll
+                for (int r = 0; r < WORLD; ++r) part[r] = __ldcg(P.ws[r] + pix * nq + q);
+                cur = part[0];
+#pragma unroll
+                for (int r = 1; r < WORLD; ++r) { cur.x += part[r].x; cur.y += part[r].y; cur.z += part[r].z; cur.w += part[r].w; }
+            } else {
+                cur = __ldcg(P.ws[0] + pix * nq + q);
+                for (int r = 1; r < world; ++r) {
+                    const float4 o = __ldcg(P.ws[r] + pix * nq + q);
+                    cur.x += o.x; cur.y += o.y; cur.z += o.z; cur.w += o.w;
+                }
             }
             const float vals[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
@@ -426,6 +442,7 @@ __global__ void __launch_bounds__(256) voxel_fold_allreduce_kernel(const VoxelPe
                 if (s == 3 && q + 1 < nq) continue;  // emitted with slot 0 of the next quad
                 float v = vals[s];
                 if (s == 0 && q > 0) v += prev.w;
+#pragma unroll
                 for (int r = 0; r < world; ++r) __stcg(P.out[r] + (int64_t)b * npix + pix, v);
             }
             prev = cur;
@@ -686,8 +703,16 @@ int evk_voxel_fold_allreduce_f32(const void *const *peer_workspaces, float *cons
     const int64_t lo = npix * rank / world, hi = npix * (rank + 1) / world;
     if (hi > lo) {
         prof_count(1);
-        voxel_fold_allreduce_kernel<<<grid_simple(hi - lo, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(P, world, lo, hi, npix, B,
-                                                                                                            quads_for_bins(B));
+        const int nq = quads_for_bins(B);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        // 128-thread CTAs: the slice is small (npix / world pixels), spread it over the SMs
+        const int grid = grid_simple(hi - lo, 128);
+#define EVK_FAR(WN, QN) voxel_fold_allreduce_kernel<WN, QN><<<grid, 128, 0, st>>>(P, world, lo, hi, npix, B, nq)
+        if (nq == 2 && world == 2) EVK_FAR(2, 2);
+        else if (nq == 2 && world == 4) EVK_FAR(4, 2);
+        else if (nq == 2 && world == 8) EVK_FAR(8, 2);
+        else EVK_FAR(0, 0);
+#undef EVK_FAR
         EVK_CUDA(cudaGetLastError());
     }
     return EVK_OK;

@@ -420,7 +420,8 @@ def test_fold_allreduce_kernel_on_one_device(oracle):
     wsr = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     _lib.check(L.evk_voxel_f32(xd.data_ptr(), yd.data_ptr(), td.data_ptr(), pd.data_ptr(), len(x), t0, dt, B, H, W, _lib.VARIANT_VECTOR_RED,
                                ref.data_ptr(), wsr.data_ptr(), wsr.numel(), oob.data_ptr(), None))
-    for bounds in ([(0, 200000)], [(0, 70000), (70000, 70000), (70000, 200000)]):
+    even = lambda w: [(200000 * r // w, 200000 * (r + 1) // w) for r in range(w)]   # noqa: E731  (2, 4, 8: unrolled kernels)
+    for bounds in ([(0, 200000)], [(0, 70000), (70000, 70000), (70000, 200000)], even(2), even(4), even(8)):
         world = len(bounds)
         wss = [torch.empty(wsb, dtype=torch.uint8, device="cuda") for _ in range(world)]
         outs = [torch.full((B, H, W), float("nan"), device="cuda") for _ in range(world)]
