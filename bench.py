@@ -160,10 +160,14 @@ def best_torch_threads(fn, candidates):
     best, best_t = candidates[0], float("inf")
     for c in candidates:
         torch.set_num_threads(c)
-        fn()
-        s = time.perf_counter()
-        fn()
-        el = time.perf_counter() - s
+        fn()                                   # warm-up at this thread count
+        el = float("inf")
+        for _ in range(2):
+            s = time.perf_counter()
+            fn()
+            el = min(el, time.perf_counter() - s)
+            if el > 3.0 * best_t:              # hopeless candidate: do not spend a second run on it
+                break
         if el < best_t:
             best, best_t = c, el
     torch.set_num_threads(best)
@@ -172,7 +176,7 @@ def best_torch_threads(fn, candidates):
 
 def thread_candidates():
     cores = os.cpu_count() or 1
-    return sorted(set(c for c in (1, 4, 8, 16, 32, cores) if c <= cores))
+    return sorted(set(c for c in (1, 4, 8, 16, 32, 64, cores) if c <= cores))
 
 
 def time_cpu_port(n, repeats):
@@ -180,9 +184,8 @@ def time_cpu_port(n, repeats):
     cores = os.cpu_count() or 1
     x, y, t, p = cpu_sample_events(n)
     xt, yt, tt, pt = (torch.from_numpy(a) for a in (x, y, t, p))
-    m = min(n, 500_000)
-    threads = best_torch_threads(lambda: ref_port.voxel_torch_cpu(xt[:m], yt[:m], tt[:m], pt[:m], B, (H, W)),
-                                 thread_candidates())
+    # calibrate on the full sample: the best thread count at 0.5 M events is not the best at 5 M
+    threads = best_torch_threads(lambda: ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W)), thread_candidates())
     best_t = float("inf")
     for _ in range(repeats):
         s = time.perf_counter()
@@ -219,8 +222,7 @@ def run_reference(args, rank, world):
     n = CPU_SAMPLE
     x, y, t, p = cpu_sample_events(n)
     xt, yt, tt, pt = (torch.from_numpy(a) for a in (x, y, t, p))
-    m = min(n, 500_000)
-    best_torch_threads(lambda: ref_port.voxel_torch_cpu(xt[:m], yt[:m], tt[:m], pt[:m], B, (H, W)), thread_candidates())
+    best_torch_threads(lambda: ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W)), thread_candidates())
     for _ in range(args.warmup):
         ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W))
     s = time.perf_counter()
