@@ -485,20 +485,49 @@ class r1_objective(_fused_objective):
 
 
 class zhu_timestamp_objective(objective_function):
-    """Squared timestamp images objective (objectives.py:524-558).  In the reference its
-    evaluate_function calls the undefined `events_to_zhu_timestamp_image` and raises NameError
-    (SURVEY Appendix B11); there is therefore no behaviour to be faithful to.  The timestamp images
-    themselves are available: representations.image.events_to_timestamp_image(_torch)."""
+    """Squared timestamp images objective (Zhu et al., CVPR'19; objectives.py:524-558):
+        f = -( sum((G * T+)^2) + sum((G * T-)^2) )
+    with T+ / T- the average-timestamp images of the warped positive / negative events.  The reference's
+    evaluate_function calls `events_to_zhu_timestamp_image`, a name that does not exist anywhere in it
+    (NameError); the function it evidently means is `events_to_timestamp_image`
+    (image.py:219-284, same argument order, same (pos, neg) return), which is what is used here with its
+    defaults -- so this class does what the reference's code says once that one name is resolved.  Warp
+    and bounds mask stay on the host as written there (:540-543: x, y, t AND p are multiplied by the mask);
+    timestamp images, blur and the two sums run on the GPU."""
     def __init__(self):
         super().__init__(name="zhu", use_polarity=True, has_derivative=False, default_blur=2.0)
 
     def evaluate_function(self, params=None, xs=None, ys=None, ts=None, ps=None,
             warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None):
-        raise NotImplementedError("zhu_timestamp_objective is undefined in the reference "
-                                  "(objectives.py:545 calls a function that does not exist)")
+        from ..representations.image import _timestamp_images
+        if iwe is not None:
+            raise NameError("name 'posimg' is not defined")      # the reference's iwe= branch never defines its images
+        xs, ys, ts, ps = (np.asarray(a, dtype=np.float64) for a in (xs, ys, ts, ps))
+        xw, yw, _, _ = warpfunc.warp(xs, ys, ts, ps, ts[-1], params, compute_grad=False)
+        mask = events_bounds_mask(xw, yw, 0, img_size[1], 0, img_size[0])
+        xw, yw, tm, pm = xw * mask, yw * mask, ts * mask, ps * mask
+        blur_sigma = self.default_blur if blur_sigma is None else blur_sigma
+        L = _lib.lib()
+        dev = E.compute_device()
+        with torch.cuda.device(dev):
+            # events_to_timestamp_image (image.py:241-261): stamps relative to the first, in f64, then f32
+            rel = tm - tm[0]
+            x, y, p = (torch.from_numpy(np.ascontiguousarray(a)).to(dev).float() for a in (xw, yw, pm))
+            t = torch.from_numpy(rel).to(dev).float()
+            pos, neg = _timestamp_images(x, y, t, p, 0.0, float(np.float32(rel[-1])), SENSOR_SIZE, True, 'bilinear', True, False)
+            total = 0.0
+            for img in (pos, neg):
+                if blur_sigma > 0:
+                    g, tmp = torch.empty_like(img), torch.empty_like(img)
+                    _lib.check(L.evk_gaussian_blur_f32(_lib.ptr(img), img.shape[0], img.shape[1], float(blur_sigma), _lib.ptr(g),
+                                                       _lib.ptr(tmp), _lib.stream()))
+                    img = g
+                total += float((img * img).sum())                  # np.sum of an f32 image: f32 pairwise sum
+        return -total
 
     def evaluate_gradient(self, params=None, xs=None, ys=None, ts=None, ps=None,
             warpfunc=None, img_size=None, blur_sigma=None, showimg=False, iwe=None, d_iwe=None):
+        """No derivative known (objectives.py:553-558)."""
         return None
 
 

@@ -276,6 +276,24 @@ for name, o in objs.items():
             cases["%s_%g_%g_%s" % (name, prm[0], prm[1], tag)] = np.array([f] + gr, dtype=np.float64)
 save("objectives", **cases)
 
+# ---- zhu_timestamp_objective (objectives.py:524-558) ------------------------------------------------
+# As shipped it raises NameError: it calls `events_to_zhu_timestamp_image`, which exists nowhere in the
+# reference.  The golden is the reference's own code with that one name bound to the function it evidently
+# means, events_to_timestamp_image (image.py:219-284), through an adapter that drops the two keyword
+# arguments that function does not take.
+def _zhu_images(xs, ys, ts, ps, compute_gradient=False, showimg=False):
+    return ref.image.events_to_timestamp_image(xs, ys, ts, ps)
+
+
+O.events_to_zhu_timestamp_image = _zhu_images
+cases = {}
+xs, ys, ts, ps = scenes["lat"]
+for prm in [(45.0, -20.0), (60.0, -35.0), (0.0, 0.0)]:
+    for tag, sigma in (("d", None), ("0", 0.0), ("1", 1.0)):
+        cases["zhu_%g_%g_%s" % (prm[0], prm[1], tag)] = np.array(
+            O.zhu_timestamp_objective().evaluate_function(prm, xs, ys, ts, ps, warp, (180, 240), sigma), dtype=np.float64)
+save("zhu", **cases)
+
 # ---- RobustNorm (data_augmentation.py:75-136) ----------------------------------------------------
 import importlib.util
 spec = importlib.util.spec_from_file_location("ref_data_augmentation", os.path.join(ref_loader.REF_ROOT, "lib/data_loaders/data_augmentation.py"))

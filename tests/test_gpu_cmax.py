@@ -278,8 +278,15 @@ def test_other_objectives_against_reference_goldens():
             assert np.abs(gr - ref[1:]).max() <= 2e-3 * np.abs(ref[1:]).max() + 1e-3
         else:
             assert np.abs(gr - ref[1:]).max() <= 1e-5 * max(np.abs(ref[1:]).max(), 1e-3), (key, gr, ref[1:])
-    with pytest.raises(NotImplementedError):
-        O.zhu_timestamp_objective().evaluate_function((1.0, 1.0), *ev, warp, (180, 240), None)
+    # zhu: golden = the reference's code with its one undefined name bound to events_to_timestamp_image
+    z = golden("zhu")
+    for key in z.files:
+        _, vx, vy, tag = key.split("_")
+        sigma = {"d": None, "0": 0.0, "1": 1.0}[tag]
+        zo = O.zhu_timestamp_objective()
+        f = zo.evaluate_function((float(vx), float(vy)), *ev, warp, (180, 240), sigma)
+        assert abs(f - float(z[key])) <= 1e-5 * abs(float(z[key])), (key, f, float(z[key]))
+        assert zo.evaluate_gradient((float(vx), float(vy)), *ev, warp, (180, 240), sigma) is None and not zo.has_derivative
     # the optimiser protocol works for them too (the reference's own objects lack pixel_crossings)
     o = O.sosa_objective()
     o.iter_update((3.0, 4.0))

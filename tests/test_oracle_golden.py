@@ -157,3 +157,22 @@ def test_robust_norm(oracle):
         assert_close_to_max(out, g[tag + "_out"], 1e-7, tag)
     assert np.array_equal(oracle.robust_norm_f32(g["sparse_in"]), g["sparse_in"])
 
+
+
+def test_zhu_objective_composition(oracle):
+    """warp -> bounds mask -> timestamp images -> blur -> sum of squares (objectives.py:536-550) restated
+    from the oracle's pieces against the golden of the reference's code"""
+    c, z = golden("cmax"), golden("zhu")
+    xs, ys, ts, ps = (c["lat" + k] for k in ("_x", "_y", "_t", "_p"))
+    for key in z.files:
+        _, vx, vy, tag = key.split("_")
+        sigma = {"d": 2.0, "0": 0.0, "1": 1.0}[tag]
+        lag = ts - ts[-1]
+        xw, yw = xs - lag * float(vx), ys - lag * float(vy)
+        m = oracle.bounds_mask(xw, yw, 0, 240, 0, 180)
+        tm = ts * m
+        pos, neg = oracle.timestamp_image_f32(xw * m, yw * m, tm - tm[0], ps * m)
+        if sigma > 0:
+            pos, neg = oracle.gaussian_filter_f32(pos, sigma), oracle.gaussian_filter_f32(neg, sigma)
+        f = -(np.sum(pos * pos) + np.sum(neg * neg))
+        assert abs(f - float(z[key])) <= 1e-5 * abs(float(z[key])), (key, f, float(z[key]))
