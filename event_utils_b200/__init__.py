@@ -9,7 +9,10 @@ Module map (reference module -> this package):
     lib/transforms/optic_flow.py      -> event_utils_b200.transforms.optic_flow
     lib/contrast_max/warps.py         -> event_utils_b200.contrast_max.warps
     lib/contrast_max/objectives.py    -> event_utils_b200.contrast_max.objectives
+    lib/contrast_max/events_cmax.py   -> event_utils_b200.contrast_max.events_cmax (drivers)
     lib/util/event_util.py (mask)     -> event_utils_b200.util.event_util
+    lib/data_loaders (window tables, RobustNorm) -> event_utils_b200.data_loaders.{windows,data_augmentation}
+    multi-GPU (no reference counterpart)         -> event_utils_b200.parallel
 """
 from . import config  # noqa: F401
 
