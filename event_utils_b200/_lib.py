@@ -174,9 +174,17 @@ def ptr(t):
 _scratch = {}
 
 
+def _stream_key(key, device):
+    """Scratch is reused call after call, which is only safe in stream order: one buffer per
+    (purpose, device, stream), so that callers working on several streams or threads do not share one."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    return (key, idx, torch.cuda.current_stream(idx).cuda_stream)
+
+
 def scratch(key, nbytes, device):
-    """A cached 256-byte aligned device scratch buffer (uint8) of at least nbytes."""
-    k = (key, device.index if device.index is not None else torch.cuda.current_device())
+    """A cached 256-byte aligned device scratch buffer (uint8) of at least nbytes, private to the
+    current stream of `device`."""
+    k = _stream_key(key, device)
     buf = _scratch.get(k)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
@@ -185,7 +193,7 @@ def scratch(key, nbytes, device):
 
 
 def oob_counter(device):
-    k = ("oob", device.index if device.index is not None else torch.cuda.current_device())
+    k = _stream_key("oob", device)
     buf = _scratch.get(k)
     if buf is None:
         buf = torch.zeros(1, dtype=torch.int64, device=device)
@@ -199,11 +207,14 @@ _pipelines = {}
 
 
 def pipeline(chunk_events=4 << 20):
-    dev = torch.cuda.current_device()
-    p = _pipelines.get(dev)
+    """The host-input pipeline (staging buffers + two streams, csrc/evk_host.cu) of the calling THREAD on
+    the current device: a pipeline serves one call at a time, and ctypes releases the GIL during it."""
+    import threading
+    k = (torch.cuda.current_device(), threading.get_ident())
+    p = _pipelines.get(k)
     if p is None:
         h = ctypes.c_void_p()
         check(lib().evk_pipeline_create(ctypes.byref(h), chunk_events))
         p = h
-        _pipelines[dev] = p
+        _pipelines[k] = p
     return p

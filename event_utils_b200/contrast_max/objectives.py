@@ -84,11 +84,12 @@ def _result_buffers(dev):
     under unified addressing), so reading a result back is one stream synchronise -- no device buffer,
     no D2H copy operation (a fresh torch.zeros + pageable .cpu() per call cost ~25 us of a ~90 us
     evaluation, a pinned mirror + copy_ still ~10 us).  Returns (tensor, numpy view)."""
-    b = _result_bufs.get(dev)
+    k = (dev, torch.cuda.current_stream(dev).cuda_stream)        # one buffer per stream: reuse is only safe in stream order
+    b = _result_bufs.get(k)
     if b is None:
         host = torch.zeros(12, dtype=torch.float64).pin_memory()
         b = (host, host.numpy())
-        _result_bufs[dev] = b
+        _result_bufs[k] = b
     return b
 
 

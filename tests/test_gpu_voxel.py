@@ -477,3 +477,36 @@ def test_peer_reduced_voxel_two_gpus(oracle, tmp_path):
     want = oracle.voxel_f32(x, y, t, p, 5, (60, 80))
     assert_close_to_max(a[0], want, 1e-5)
     assert_close_to_max(a[1], want, 1e-5)
+
+
+def test_two_threads_two_streams(oracle):
+    """scratch buffers are per stream and the host pipeline per thread: concurrent callers do not disturb
+    each other (device inputs on side streams, host inputs through the pipeline)"""
+    import threading
+    from event_utils_b200.representations.voxel_grid import events_to_voxel_torch
+    sets = [make_events(70 + k, 1 << 21, 60, 80) for k in range(2)]     # >= 2^20 events: the workspace path
+    want = [oracle.voxel_f32(*ev, 5, (60, 80)) for ev in sets]
+    errors = []
+
+    def work(k):
+        try:
+            torch.cuda.set_device(0)
+            side = torch.cuda.Stream()
+            host = [torch.from_numpy(a) for a in sets[k]]
+            with torch.cuda.stream(side):
+                on_dev = [a.cuda() for a in host]
+                for _ in range(10):
+                    got = events_to_voxel_torch(*on_dev, 5, sensor_size=(60, 80))
+                    side.synchronize()
+                    assert_close_to_max(got.cpu().numpy(), want[k], 1e-5)
+                    got_h = events_to_voxel_torch(*host, 5, sensor_size=(60, 80))
+                    assert_close_to_max(got_h.numpy(), want[k], 1e-5)
+        except Exception as exc:      # surfaced in the main thread
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
