@@ -28,6 +28,53 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(L.evk_last_error(), bytes)
 
 
+def declared_prototypes():
+    """name -> list of parameter type strings, parsed from include/evk.h"""
+    src = open(os.path.join(ROOT, "include", "evk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|size_t|const char \*|void)\s*\*?\s*(evk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        protos[m.group(1)] = [] if params in ([""], ["void"]) else params
+    return protos
+
+
+def test_ctypes_declarations_match_the_header():
+    """every prototype of include/evk.h against the argtypes event_utils_b200/_lib.py binds: same number of
+    parameters, pointers bound as pointers, 64-bit integers as 64-bit, floats / doubles as such"""
+    from event_utils_b200 import _lib
+    L = _lib.load()
+    protos = declared_prototypes()
+    assert len(protos) == len(declared_symbols()) and "evk_voxel_f32" in protos and "evk_voxel_fold_allreduce_f32" in protos
+
+    def kind(c_type):
+        c = c_type.replace("const ", "").strip()
+        c = re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*$", "", c).strip() if not c.endswith("*") else c   # drop the parameter name
+        if "*" in c_type:
+            return "ptr"
+        for key, val in (("int64_t", "i64"), ("size_t", "size"), ("unsigned", "u32"), ("double", "f64"), ("float", "f32"), ("int", "i32")):
+            if re.search(r"\b%s\b" % key, c_type):
+                return val
+        raise AssertionError("unparsed parameter type %r" % c_type)
+
+    bound = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int64: "i64", ctypes.c_longlong: "i64", ctypes.c_size_t: "size",
+             ctypes.c_uint: "u32", ctypes.c_double: "f64", ctypes.c_float: "f32", ctypes.c_int: "i32"}
+    checked = 0
+    for name, params in protos.items():
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue                      # not bound by the python layer (e.g. used from C only)
+        assert len(fn.argtypes) == len(params), "%s: header has %d parameters, _lib.py binds %d" % (name, len(params), len(fn.argtypes))
+        for i, (c_type, at) in enumerate(zip(params, fn.argtypes)):
+            got = "ptr" if (isinstance(at, type) and issubclass(at, ctypes._Pointer)) else bound.get(at)
+            want = kind(c_type)
+            if want == "size" and got == "i64":
+                got = "size"
+            assert got == want, "%s parameter %d (%s): bound as %s" % (name, i, c_type, at)
+        checked += 1
+    assert checked >= 30
+
+
 def test_workspace_queries_need_no_gpu():
     from event_utils_b200 import _lib
     L = _lib.load()
