@@ -21,6 +21,7 @@ NEGPOS_TRUTHY = 0x8
 WINDOW_PAIRS = 0x100000
 WINDOW_NEGPOS = 0x400000
 NO_FOLD = 0x800000
+PEER_MULTICAST = 0x1000000
 AUTO_SPAN = 0x200000
 VARIANT_AUTO = 0 << 8
 VARIANT_GLOBAL_RED = 1 << 8

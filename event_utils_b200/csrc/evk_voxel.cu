@@ -450,6 +450,46 @@ __global__ void __launch_bounds__(256) voxel_fold_allreduce_kernel(const VoxelPe
     }
 }
 
+// The same step through the NVSwitch (NVLS): `ws_mc` / `out_mc` are MULTICAST addresses bound to every
+// rank's workspace / grid.  One multimem.ld_reduce returns the sum of a quad over all ranks (the switch
+// reduces, one 16-byte response crosses this GPU's link instead of N-1), one multimem.st writes a bin value
+// into every rank's grid.  Per GPU: 9.8 MB / N in, 6.1 MB / N out at 5x480x640, whatever N is.
+__device__ __forceinline__ float4 multimem_ld_reduce_add4(const float4 *mc)
+{
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void multimem_st(float *mc, float v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(128) voxel_fold_allreduce_nvls_kernel(const float4 *__restrict__ ws_mc, float *__restrict__ out_mc,
+                                                                        int64_t pix_lo, int64_t pix_hi, int64_t npix, int B, int nq)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t pix = pix_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < pix_hi; pix += stride) {
+        float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < nq; ++q) {
+            const float4 cur = multimem_ld_reduce_add4(ws_mc + pix * nq + q);
+            const float vals[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int b = 3 * q + s;
+                if (b >= B) break;
+                if (s == 3 && q + 1 < nq) continue;  // emitted with slot 0 of the next quad
+                float v = vals[s];
+                if (s == 0 && q > 0) v += prev.w;
+                multimem_st(out_mc + (int64_t)b * npix + pix, v);
+            }
+            prev = cur;
+        }
+    }
+}
+
 // Batched windows: CTA (w, s) scatters slice s of window w into out[w] with that window's own
 // t0 / dt (voxel_grid.py:133-134 applied per window, as voxel_grids_fixed_n_torch :53-56 does).
 __global__ void __launch_bounds__(kThreads) voxel_windows_kernel(const VoxelArgs A, const int64_t *__restrict__ offsets,
@@ -685,10 +725,25 @@ int evk_voxel_fold_allreduce_f32(const void *const *peer_workspaces, float *cons
                                  int W, unsigned flags, void *stream)
 {
     using namespace evk;
-    (void)flags;
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || B < 1 || H < 1 || W < 1 || !peer_workspaces || !peer_outs) {
         set_error("evk_voxel_fold_allreduce_f32: bad arguments (world=%d rank=%d, at most %d peers)", world, rank, kMaxPeers);
         return EVK_E_ARG;
+    }
+    if (flags & EVK_PEER_MULTICAST) {
+        // entry 0 of both arrays is the multicast address of the buffer
+        if (!peer_workspaces[0] || !peer_outs[0] || ((uintptr_t)peer_workspaces[0] & 15)) {
+            set_error("evk_voxel_fold_allreduce_f32: null or misaligned multicast pointer");
+            return EVK_E_ARG;
+        }
+        const int64_t npix_mc = (int64_t)H * W;
+        const int64_t lo_mc = npix_mc * rank / world, hi_mc = npix_mc * (rank + 1) / world;
+        if (hi_mc > lo_mc) {
+            prof_count(1);
+            voxel_fold_allreduce_nvls_kernel<<<grid_simple(hi_mc - lo_mc, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+                static_cast<const float4 *>(peer_workspaces[0]), peer_outs[0], lo_mc, hi_mc, npix_mc, B, quads_for_bins(B));
+            EVK_CUDA(cudaGetLastError());
+        }
+        return EVK_OK;
     }
     VoxelPeers P{};
     for (int r = 0; r < world; ++r) {

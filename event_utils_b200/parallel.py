@@ -120,7 +120,11 @@ class PeerReducedVoxel:
     runs barrier + reduce kernel + barrier of build k on a communication stream while build k+1 scatters
     (the interface of ShardedVoxelStream); `__call__` is the synchronous single build."""
 
-    def __init__(self, B, sensor_size, device, group=None, depth=1):
+    def __init__(self, B, sensor_size, device, group=None, depth=1, multicast=False):
+        """multicast=True: reduce and fan out through the NVSwitch (NVLS multimem.ld_reduce / multimem.st on the
+        buffers' multicast addresses) where the symmetric-memory backend provides them; the per-GPU link traffic
+        then stays 9.8 MB / N in + 6.1 MB / N out for any N.  Falls back to the peer-pointer kernel otherwise
+        (`self.multicast` says which is in use)."""
         import ctypes
         import torch.distributed._symmetric_memory as symm
         from . import _lib
@@ -135,10 +139,15 @@ class PeerReducedVoxel:
             ws = symm.empty(ws_bytes, dtype=torch.uint8, device=self.device)
             out = symm.empty((self.B, self.H, self.W), dtype=torch.float32, device=self.device)
             h_ws, h_out = symm.rendezvous(ws, group), symm.rendezvous(out, group)
-            self.bufs.append(dict(ws=ws, out=out, h_ws=h_ws, h_out=h_out,
-                                  peer_ws=(ctypes.c_void_p * self.world)(*[int(a) for a in h_ws.buffer_ptrs]),
-                                  peer_out=(ctypes.c_void_p * self.world)(*[int(a) for a in h_out.buffer_ptrs]),
-                                  done=torch.cuda.Event()))
+            buf = dict(ws=ws, out=out, h_ws=h_ws, h_out=h_out,
+                       peer_ws=(ctypes.c_void_p * self.world)(*[int(a) for a in h_ws.buffer_ptrs]),
+                       peer_out=(ctypes.c_void_p * self.world)(*[int(a) for a in h_out.buffer_ptrs]),
+                       done=torch.cuda.Event(), mc_ws=None, mc_out=None)
+            if multicast and int(getattr(h_ws, "multicast_ptr", 0) or 0) and int(getattr(h_out, "multicast_ptr", 0) or 0):
+                buf["mc_ws"] = (ctypes.c_void_p * self.world)(*([int(h_ws.multicast_ptr)] * self.world))
+                buf["mc_out"] = (ctypes.c_void_p * self.world)(*([int(h_out.multicast_ptr)] * self.world))
+            self.bufs.append(buf)
+        self.multicast = all(b["mc_ws"] is not None for b in self.bufs)
         self.oob = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.comm = torch.cuda.Stream(self.device) if depth > 1 else None
         self.k = 0
@@ -146,8 +155,12 @@ class PeerReducedVoxel:
     def _reduce(self, buf, stream_handle):
         _lib, L = self._lib, self.L
         buf["h_ws"].barrier(channel=0)            # every rank's reductions have landed in its workspace
-        _lib.check(L.evk_voxel_fold_allreduce_f32(buf["peer_ws"], buf["peer_out"], self.world, self.rank, self.B, self.H,
-                                                  self.W, 0, stream_handle))
+        if self.multicast:
+            _lib.check(L.evk_voxel_fold_allreduce_f32(buf["mc_ws"], buf["mc_out"], self.world, self.rank, self.B, self.H,
+                                                      self.W, _lib.PEER_MULTICAST, stream_handle))
+        else:
+            _lib.check(L.evk_voxel_fold_allreduce_f32(buf["peer_ws"], buf["peer_out"], self.world, self.rank, self.B, self.H,
+                                                      self.W, 0, stream_handle))
         buf["h_ws"].barrier(channel=1)            # every rank's slice has been written into every grid
 
     def submit(self, xs, ys, ts, ps, t0, dt):

@@ -48,6 +48,7 @@ extern "C" {
 #define EVK_AUTO_SPAN 0x200000u    /* voxel: ignore the t0/dt arguments, take t[0] and t[n-1]-t[0] on the device */
 #define EVK_WINDOW_PAIRS 0x100000u /* evk_voxel_windows_f32: offsets are (start,end) pairs, 2*n_windows entries */
 #define EVK_NO_FOLD 0x800000u /* evk_voxel_f32: leave the sums in the quad workspace (out may be NULL); evk_voxel_fold_allreduce_f32 finishes */
+#define EVK_PEER_MULTICAST 0x1000000u /* evk_voxel_fold_allreduce_f32: entry 0 of both pointer arrays is an NVLS multicast address */
 #define EVK_WINDOW_NEGPOS 0x400000u /* evk_voxel_windows_f32: out is [n_windows][2][B][H][W], the [p>0] / [p<=0] split per window */
 #define EVK_NEGPOS_TRUTHY 0x8u /* neg/pos split on numpy truthiness (p != 0) instead of p > 0 */
 /* kernel variant selection, bits 8..11 (0 = pick automatically) */
@@ -130,7 +131,10 @@ int evk_voxel_packed_f32(const int16_t *x, const int16_t *y, const double *t, co
  * this once: it reduces ITS slice of the pixels over all ranks' workspaces, folds the temporal quads into
  * the B bins and writes the result into every rank's [B][H][W] grid -- fold and all-reduce in one kernel
  * over peer memory.  A second cross-GPU barrier must follow before the grids are read or the workspaces
- * reused.  peer_workspaces / peer_outs: HOST arrays of `world` device pointers, index = rank. */
+ * reused.  peer_workspaces / peer_outs: HOST arrays of `world` device pointers, index = rank.
+ * With EVK_PEER_MULTICAST entry 0 of each array is the buffer's NVLS multicast address instead (the
+ * other entries are ignored): the NVSwitch sums the quads (multimem.ld_reduce) and fans the result out
+ * (multimem.st), so the per-GPU link traffic no longer grows with the number of ranks. */
 int evk_voxel_fold_allreduce_f32(const void *const *peer_workspaces, float *const *peer_outs, int world,
                                  int rank, int B, int H, int W, unsigned flags, void *stream);
 

@@ -460,7 +460,9 @@ def _peer_worker(rank, world, port, out_dir):
     for _ in range(3):                                    # the buffers are reused call after call
         grid = fused(*sh, t0, dt).clone()
     nccl = events_to_voxel_sharded(*sh, B, (H, W), t0=t0, dt=dt)
-    np.save(os.path.join(out_dir, "peer%d.npy" % rank), np.stack((grid.cpu().numpy(), nccl.cpu().numpy())))
+    nvls = PeerReducedVoxel(B, (H, W), torch.device("cuda", rank), multicast=True)     # through the switch where available
+    grid_mc = nvls(*sh, t0, dt).clone() if nvls.multicast else grid
+    np.save(os.path.join(out_dir, "peer%d.npy" % rank), np.stack((grid.cpu().numpy(), nccl.cpu().numpy(), grid_mc.cpu().numpy())))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -477,6 +479,8 @@ def test_peer_reduced_voxel_two_gpus(oracle, tmp_path):
     want = oracle.voxel_f32(x, y, t, p, 5, (60, 80))
     assert_close_to_max(a[0], want, 1e-5)
     assert_close_to_max(a[1], want, 1e-5)
+    assert np.array_equal(a[2], b[2])
+    assert_close_to_max(a[2], want, 1e-5)
 
 
 def test_two_threads_two_streams(oracle):

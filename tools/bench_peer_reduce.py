@@ -40,11 +40,20 @@ def timed(fn, iters=20):
     return best
 
 
+nvls = PeerReducedVoxel(B, (H, W), dev, multicast=True)
 ga = fused(x, y, t, p, t0, dt).clone()
 gb = events_to_voxel_sharded(x, y, t, p, B, (H, W), t0=t0, dt=dt)
 err = float((ga - gb).abs().max() / gb.abs().max())
 ms_f = timed(lambda: fused(x, y, t, p, t0, dt))
 ms_n = timed(lambda: events_to_voxel_sharded(x, y, t, p, B, (H, W), t0=t0, dt=dt))
+if nvls.multicast:
+    gc = nvls(x, y, t, p, t0, dt).clone()
+    err_mc = float((gc - gb).abs().max() / gb.abs().max())
+    ms_mc = timed(lambda: nvls(x, y, t, p, t0, dt))
+    if rank == 0:
+        print("world %d: NVLS multimem fold+all-reduce %.3f ms, max rel diff vs NCCL %.2e" % (world, ms_mc, err_mc), flush=True)
+elif rank == 0:
+    print("no multicast support reported by the symmetric-memory backend", flush=True)
 if rank == 0:
     print("world %d, %d M events/GPU: fused fold+peer all-reduce %.3f ms | scatter+fold+NCCL all-reduce %.3f ms | max rel diff %.2e"
           % (world, N // 1000000, ms_f, ms_n, err), flush=True)
