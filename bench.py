@@ -18,7 +18,6 @@ import argparse
 import ctypes
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

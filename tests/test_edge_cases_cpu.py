@@ -1,6 +1,5 @@
 """Adversarial small cases: the oracle must agree with the real reference on results AND on error
 behaviour (skipped where the reference tree is absent)."""
-import numpy as np
 import pytest
 import torch
 

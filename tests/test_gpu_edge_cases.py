@@ -1,5 +1,4 @@
 """Adversarial small cases through the CUDA path: results and IndexError behaviour == the oracle's."""
-import numpy as np
 import pytest
 import torch
 
