@@ -1,2 +1,5 @@
-# the reference's lib/util/__init__.py star-exports event_util (and util, which is not on the path)
-from .event_util import *    # noqa: F401,F403
+"""Helpers shared by the hot path and its drivers; the public names of `event_util` are re-exported,
+as the reference's `lib.util` package does for its own event_util module."""
+from . import event_util as _event_util
+
+globals().update({_name: getattr(_event_util, _name) for _name in dir(_event_util) if not _name.startswith("_")})
