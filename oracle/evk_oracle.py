@@ -228,3 +228,69 @@ def robust_norm_f32(x, low_perc=0, top_perc=95):
     c = np.clip(a, t_min, t_max)
     return ((c - c.min()) / np.float32(c.max() + np.float32(1e-6))).astype(np.float32)
 
+
+
+# ---- the other objective functions, image-space part (objectives.py:266-596) ------------------------
+OBJECTIVE_DEFAULTS = {   # name: (use_polarity, default_blur, parameter)
+    "variance": (True, 1.0, None), "rms": (True, 1.0, None), "sos": (True, 1.0, None), "soe": (False, 2.5, None),
+    "moa": (False, 3.0, None), "isoa": (False, 1.0, 0.5), "sosa": (False, 2.0, 3.0), "r1": (False, 1.0, 3.0),
+}
+
+
+def objective_of_images(name, iwe, d_iwe=None, blur_sigma=None, param=None):
+    """f (and g, when d_iwe is given and the objective has a derivative) of a precomputed image of warped
+    events -- the part of every evaluate_function / evaluate_gradient after get_iwe:
+        rms   :266-307   f = -||G||_2^2 / P (spectral norm),  g_k = -2 mean(I  * G3(D)_k)
+        sos   :308-357   f = -mean(G^2),                      g_k = -mean(G3(D)_k * 2 I)
+        soe   :358-400   f = -mean(exp G),                    g_k = -mean(exp(G) * G3(D)_k)
+        moa   :401-430   f = -max G
+        isoa  :431-477   f = +#(G > thresh),                  g_k = -sum([G > thresh] * G3(D)_k)
+        sosa  :478-523   f = -sum(exp(-p G)),                 g_k = -sum(-p exp(-p G) * G3(D)_k)
+        r1    :560-596   f = -mean(G^2): with last_sosa initialised to 0 the branch `sosa > last_sosa` is always
+                         taken and last_sosa never updated, so the product form -sos*sosa is unreachable
+    with G = gaussian_filter(I), G3 = gaussian_filter of the (2,H,W) stack (all three axes), I un-blurred.
+    Returns (f, g or None)."""
+    _, default_blur, default_param = OBJECTIVE_DEFAULTS[name]
+    sigma = default_blur if blur_sigma is None else blur_sigma
+    prm = default_param if param is None else param
+    img = np.asarray(iwe, dtype=np.float32)
+    blurred = gaussian_filter_f32(img, sigma) if sigma > 0 else img
+    npix = img.shape[0] * img.shape[1]
+    if name == "rms":
+        f = -(np.linalg.norm(blurred, 2) ** 2) / npix
+    elif name == "sos":
+        f = -np.mean(blurred * blurred)
+    elif name == "soe":
+        f = -np.mean(np.exp(blurred.astype(np.float64)))
+    elif name == "moa":
+        f = -np.max(blurred)
+    elif name == "isoa":
+        f = int(np.sum(blurred > prm))
+    elif name == "sosa":
+        f = -np.sum(np.exp(-prm * blurred.astype(np.float64)))
+    elif name == "r1":
+        f = -np.mean(blurred * blurred)
+    else:
+        raise KeyError(name)
+    if d_iwe is None or name in ("moa", "r1"):
+        return float(f), None
+    stack = np.asarray(d_iwe, dtype=np.float32)
+    stack = gaussian_filter_f32(stack, sigma) if sigma > 0 else stack
+    if name == "rms":
+        g = [-2.0 * np.mean(img * stack[k]) for k in range(2)]
+    elif name == "sos":
+        g = [-np.mean(stack[k] * (img * 2.0)) for k in range(2)]
+    elif name == "soe":
+        g = [-np.mean(np.exp(blurred.astype(np.float64)) * stack[k]) for k in range(2)]
+    elif name == "isoa":
+        g = [-np.sum(stack[k] * (blurred > prm).astype(np.float32)) for k in range(2)]
+    else:  # sosa
+        g = [-np.sum(stack[k] * (-prm * np.exp((-prm * blurred).astype(np.float64)))) for k in range(2)]
+    return float(f), np.array(g, dtype=np.float64)
+
+
+def cmax_objective(name, params, xs, ys, ts, ps, img_size=(180, 240), blur_sigma=None, param=None, want_grad=True):
+    """Any of the objectives above with linvel_warp on raw events."""
+    use_polarity = OBJECTIVE_DEFAULTS[name][0]
+    iwe, d = iwe_linvel(params, xs, ys, ts, ps, img_size, compute_gradient=want_grad, use_polarity=use_polarity)
+    return objective_of_images(name, iwe, d, blur_sigma, param)

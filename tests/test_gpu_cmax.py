@@ -293,6 +293,35 @@ def test_other_objectives_against_reference_goldens():
     assert o.lifespan == 1.0
 
 
+@pytest.mark.parametrize("name", ["rms", "sos", "soe", "moa", "isoa", "sosa", "r1"])
+def test_other_objectives_random_scene_vs_oracle(oracle, name):
+    """every objective on a random +-1 scene against the oracle's restatement (itself pinned to the reference on
+    random scenes, tests/test_oracle_vs_reference.py), default blur / no blur / sigma 1.7"""
+    from event_utils_b200.contrast_max import objectives as O
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    x, y, t, p = make_events(19, 250000, 180, 240, dtype=np.float64)
+    warp = linvel_warp()
+    for params in [(25.0, -40.0), (-300.0, 120.0), (0.0, 0.0)]:
+        for sigma in (None, 0.0, 1.7):
+            obj = getattr(O, name + "_objective")()
+            f = obj.evaluate_function(params, x, y, t, p, warp, (180, 240), sigma)
+            gr = obj.evaluate_gradient(params, x, y, t, p, warp, (180, 240), sigma)
+            fo, go = oracle.cmax_objective(name, params, x, y, t, p, blur_sigma=sigma)
+            if name == "isoa":
+                assert abs(f - fo) <= 3, (params, sigma, f, fo)          # pixels within an ulp of the threshold may flip
+                assert np.abs(gr - go).max() <= 2e-3 * np.abs(go).max() + 1e-3
+                continue
+            assert abs(f - fo) <= 1e-5 * abs(fo), (params, sigma, f, fo)
+            if go is None:
+                assert gr is None
+            else:
+                use_pol = oracle.OBJECTIVE_DEFAULTS[name][0]
+                iwe, d = oracle.iwe_linvel(params, x, y, t, p, (180, 240), True, use_polarity=use_pol)
+                scale = np.sqrt(np.mean(iwe.astype(np.float64) ** 2) * np.mean(d.astype(np.float64) ** 2))
+                bound = {"rms": 2.0, "sos": 2.0}.get(name, max(1.0, float(np.abs(go).max() / max(scale, 1e-30)))) * scale
+                assert np.abs(gr - go).max() <= 1e-5 * max(bound, np.abs(go).max()), (params, sigma, gr, go)
+
+
 def test_candidate_batch_and_grid_search():
     """K parameter points in one pass over the events == K separate evaluations; the grid-search and
     optimize_contrast drivers run on top of it."""

@@ -176,3 +176,20 @@ def test_zhu_objective_composition(oracle):
             pos, neg = oracle.gaussian_filter_f32(pos, sigma), oracle.gaussian_filter_f32(neg, sigma)
         f = -(np.sum(pos * pos) + np.sum(neg * neg))
         assert abs(f - float(z[key])) <= 1e-5 * abs(float(z[key])), (key, f, float(z[key]))
+
+
+def test_other_objectives(oracle):
+    """rms / sos / soe / moa / isoa / sosa / r1 restated in the oracle against the reference's goldens"""
+    g, c = golden("objectives"), golden("cmax")
+    ev = [c["lat" + k] for k in ("_x", "_y", "_t", "_p")]
+    for key in g.files:
+        name, vx, vy, tag = key.split("_")
+        ref = g[key]
+        f, gr = oracle.cmax_objective(name, (float(vx), float(vy)), *ev, blur_sigma=None if tag == "d" else 0.0)
+        assert abs(f - ref[0]) <= 1e-6 * abs(ref[0]), (key, f, ref[0])
+        if name == "sos":
+            assert gr is not None                       # the reference raises NameError; formula as written there
+        elif np.isnan(ref[1]):
+            assert gr is None
+        else:
+            assert np.abs(gr - ref[1:]).max() <= 1e-5 * np.abs(ref[1:]).max(), (key, gr, ref[1:])

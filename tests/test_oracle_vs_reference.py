@@ -114,3 +114,17 @@ def test_window_tables_match_reference_loader(ref):
     assert np.array_equal(np.asarray(d.event_indices), Wn.between_frame_indices(ts, d.frame_ts))
     with pytest.raises(Exception):
         Wn.check_event_indices(Wn.k_event_indices(1000, 300, 0).tolist() + [[900, 1200]], 1000)
+
+
+@pytest.mark.parametrize("name", ["rms", "sos", "soe", "moa", "isoa", "sosa", "r1"])
+def test_other_objectives_random_scene(ref, oracle, name):
+    x, y, t, p = make_events(17, 60000, 180, 240, dtype=np.float64)
+    obj, warp = getattr(ref.objectives, name + "_objective")(), ref.warps.linvel_warp()
+    for params in [(25.0, -40.0), (-300.0, 120.0)]:
+        for sigma in (None, 0.0, 1.7):
+            f = obj.evaluate_function(params, x, y, t, p, warp, (180, 240), sigma)
+            fo, go = oracle.cmax_objective(name, params, x, y, t, p, blur_sigma=sigma)
+            assert abs(fo - f) <= 1e-6 * max(abs(f), 1e-12), (name, params, sigma)
+            if name in ("rms", "soe", "isoa", "sosa"):
+                g = obj.evaluate_gradient(params, x, y, t, p, warp, (180, 240), sigma)
+                assert np.abs(go - g).max() <= 1e-5 * max(np.abs(g).max(), 1e-9), (name, params, sigma)
