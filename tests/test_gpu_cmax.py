@@ -315,11 +315,12 @@ def test_other_objectives_random_scene_vs_oracle(oracle, name):
             if go is None:
                 assert gr is None
             else:
+                # gradients of a random +-1 scene nearly cancel: bound the error by the scale of the summands
+                # (SURVEY 8d), sqrt(mean(I^2) mean(D^2)), as well as by the gradient itself
                 use_pol = oracle.OBJECTIVE_DEFAULTS[name][0]
                 iwe, d = oracle.iwe_linvel(params, x, y, t, p, (180, 240), True, use_polarity=use_pol)
-                scale = np.sqrt(np.mean(iwe.astype(np.float64) ** 2) * np.mean(d.astype(np.float64) ** 2))
-                bound = {"rms": 2.0, "sos": 2.0}.get(name, max(1.0, float(np.abs(go).max() / max(scale, 1e-30)))) * scale
-                assert np.abs(gr - go).max() <= 1e-5 * max(bound, np.abs(go).max()), (params, sigma, gr, go)
+                scale = 2.0 * np.sqrt(np.mean(iwe.astype(np.float64) ** 2) * np.mean(d.astype(np.float64) ** 2))
+                assert np.abs(gr - go).max() <= 1e-5 * max(scale, np.abs(go).max()), (params, sigma, gr, go)
 
 
 def test_candidate_batch_and_grid_search():
