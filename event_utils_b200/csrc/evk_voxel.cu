@@ -323,14 +323,12 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
     // write-combining cache (SINK_QUAD_HOT only; the arrays vanish from the other instantiations)
     __shared__ unsigned hot_keys[SINK == SINK_QUAD_HOT ? kVoxHotSlots : 1];
     __shared__ float4 hot_vals[SINK == SINK_QUAD_HOT ? kVoxHotSlots : 1];
-    __shared__ int hot_dups;
     HotCtx hc{hot_keys, hot_vals, false};
     if (SINK == SINK_QUAD_HOT) {
-        if (threadIdx.x == 0) hot_dups = 0;
-        __syncthreads();
         hc.on = A.hot_force != 0;
         if (!hc.on) {
-            // contention probe: lanes whose first event shares its pixel with another lane of the warp
+            // contention probe: lanes whose first event shares its pixel with another lane of the warp,
+            // counted over the CTA by the barrier itself (one __syncthreads_count, no shared-memory traffic)
             unsigned long long key = ~0ull - (threadIdx.x & 31);
             if (tid < A.n) {
                 const float ex = (LAYOUT == LAYOUT_PACKED) ? (float)A.px16[tid] : (LAYOUT == LAYOUT_AOS) ? A.x[4 * tid] : A.x[tid];
@@ -338,8 +336,7 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
                 int ux, uy;
                 if (trunc_checked(ex, ux) && trunc_checked(ey, uy)) key = ((unsigned long long)(unsigned)uy << 32) | (unsigned)ux;
             }
-            if (__popc(__match_any_sync(0xffffffffu, key)) > 1) atomicAdd(&hot_dups, 1);
-            __syncthreads();
+            const int hot_dups = __syncthreads_count(__popc(__match_any_sync(0xffffffffu, key)) > 1);
             hc.on = hot_dups * 64 > kThreads;  // > 4 of 256 lanes collide inside their warp (uniform streams: ~0.03)
         }
         if (hc.on) {   // the table is only initialised (40 KB of stores) by CTAs that will use it
