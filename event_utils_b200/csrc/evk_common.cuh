@@ -142,10 +142,9 @@ __device__ __forceinline__ void flush_oob(unsigned long long *oob, unsigned loca
 {
     // one atomic per warp, only when something was out of range
     unsigned tot = __reduce_add_sync(0xffffffffu, local);
-    if (tot != 0 && (threadIdx.x & 31) == 0 && oob != nullptr) atomicAdd(oob, (unsigned long long)tot);
+    if (tot != 0 && (threadIdx.x & 31) == 0 && oob != nullptr)
+        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(oob)), "l"((unsigned long long)tot) : "memory");
 }
-
-#endif  // __CUDACC__
 
 // ---- dense-flow gather (optic_flow.py:37-44 + ATen grid_sampler bilinear/zeros/align_corners) ----
 // the two taps (x0, x0+1) of row yy as {u0, v0, u1, v1}; out-of-image taps are zero (grid_sample zero padding).
@@ -171,5 +170,7 @@ __device__ __forceinline__ float4 flow_row(const float *flow, const float2 *uv, 
     }
     return r;
 }
+
+#endif  // __CUDACC__
 
 }  // namespace evk
