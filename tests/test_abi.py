@@ -150,3 +150,21 @@ def test_argument_errors_are_reported_without_touching_the_gpu():
     assert L.evk_warp_flow_f32(one, one, one, 10, None, 4, 4, 0.0, one, one, None, 0, None) == -1
     assert L.evk_voxel_windows_f32(one, one, one, one, None, 3, 0, 5, 4, 4, 0, one, None, None) == -1
     assert L.evk_voxel_negpos_f32(one, one, one, one, 10, 0.0, 1.0, 5, 4, 4, _lib.BILINEAR, one, None, 0, None, None) == -5
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/evk.h compiles as C99 and as C++ without CUDA or torch headers, and names every entry point"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use_evk.c"
+    uses = "\n".join("    (void)&%s;" % n for n in declared_symbols())
+    src.write_text('#include "evk.h"\nint main(void)\n{\n%s\n    return 0;\n}\n' % uses)
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                ["g++", "-x", "c++", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)]):
+        if shutil.which(cmd[0]) is None:
+            continue
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
