@@ -75,6 +75,13 @@ def clear_cache():
     del _event_cache[:]
 
 
+def _events_key(xs, ys, ts, ps):
+    """Content-based identity of an event set for the (params -> result) memo of the objectives: the
+    fingerprints the device cache uses (pointer, length, dtype and a strided sample per array).  An `id()`
+    would not do: it is recycled as soon as a temporary array is freed, and says nothing about in-place edits."""
+    return tuple(_fingerprint(np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))) for a in (xs, ys, ts, ps))
+
+
 _result_bufs = {}
 
 
@@ -112,11 +119,11 @@ class _on_device:
 
 def _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, want_grad, use_polarity,
                   first=0, last=None, p_scale=1.0, want_images=False, channel_mix=True,
-                  objective=_lib.OBJ_VARIANCE, obj_param=0.0):
+                  objective=_lib.OBJ_VARIANCE, obj_param=0.0, ev=None):
     """One fused evaluation on events [first:last) of the cached device copy.
     Returns (result[8] as numpy f64, iwe or None, d_iwe or None)."""
     L = _lib.lib()
-    ev = _device_events(xs, ys, ts, ps)
+    ev = _device_events(xs, ys, ts, ps) if ev is None else ev
     n_all = ev.n
     last = n_all if last is None else (last if last >= 0 else n_all + last)
     first = first if first >= 0 else n_all + first
@@ -296,13 +303,15 @@ class variance_objective(objective_function):
                 self.recompute_lifespan = False
             first, last, scale = int(self.s_idx), -1, 100.0   # xs[s_idx:-1], ps*100 (objectives.py:224-225)
         blur_sigma = self.default_blur if blur_sigma is None else blur_sigma
-        key = (tuple(float(v) for v in params), id(xs), id(ys), id(ts), id(ps), len(xs), tuple(img_size),
-               float(blur_sigma), first, last, scale, self.use_polarity, precision)
+        fused = getattr(warpfunc, "fused_kind", None) == "linvel"
+        ev = _device_events(xs, ys, ts, ps) if fused else None
+        key = (tuple(float(v) for v in params), ev.key if fused else _events_key(xs, ys, ts, ps), tuple(img_size),
+               float(blur_sigma), first, last, scale, self.use_polarity, precision, fused)
         if self._memo is not None and self._memo[0] == key:
             return self._memo[1], self._memo[2]
-        if getattr(warpfunc, "fused_kind", None) == "linvel":
+        if fused:
             res, _, _ = _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, True, self.use_polarity,
-                                      first=first, last=last, p_scale=scale)
+                                      first=first, last=last, p_scale=scale, ev=ev)
         else:
             sl = slice(first, last)
             iwe, d_iwe = get_iwe(params, xs[sl], ys[sl], ts[sl], ps[sl] * scale, warpfunc, img_size,
@@ -348,14 +357,16 @@ class _fused_objective(objective_function):
         blur_sigma = self.default_blur if blur_sigma is None else blur_sigma
         if iwe is not None:
             return _objective_of_images(iwe, d_iwe, blur_sigma, want_grad and d_iwe is not None, self._kind, self._param())
-        key = (tuple(float(v) for v in params), id(xs), id(ys), id(ts), id(ps), len(xs), tuple(img_size),
-               float(blur_sigma), self.use_polarity, precision, self._kind, self._param())
+        fused = getattr(warpfunc, "fused_kind", None) == "linvel"
+        ev = _device_events(xs, ys, ts, ps) if fused else None
+        key = (tuple(float(v) for v in params), ev.key if fused else _events_key(xs, ys, ts, ps), tuple(img_size),
+               float(blur_sigma), self.use_polarity, precision, self._kind, self._param(), fused)
         memo = getattr(self, "_memo", None)
         if memo is not None and memo[0] == key:
             return memo[1]
-        if getattr(warpfunc, "fused_kind", None) == "linvel":
+        if fused:
             res, _, _ = _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, self.has_derivative, self.use_polarity,
-                                      objective=self._kind, obj_param=self._param())
+                                      objective=self._kind, obj_param=self._param(), ev=ev)
         else:
             img, dimg = get_iwe(params, xs, ys, ts, ps, warpfunc, img_size, use_polarity=self.use_polarity,
                                 compute_gradient=self.has_derivative)

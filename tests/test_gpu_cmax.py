@@ -212,6 +212,28 @@ def test_sharded_evaluation_matches_whole_stream(oracle):
     assert np.abs(g4 - go4).max() <= 1e-3 * grad_scale(iwe, d)
 
 
+def test_cached_results_follow_the_data(oracle):
+    """the device copy of the events and the (params -> f, g) memo are keyed on content: an in-place edit of the
+    caller's arrays, or a new array that happens to reuse a freed one's address, is evaluated afresh"""
+    from event_utils_b200.contrast_max.objectives import variance_objective
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    x, y, t, p = make_events(23, 120000, 180, 240, dtype=np.float64)
+    obj, warp, prm = variance_objective(), linvel_warp(), (20.0, -10.0)
+    f1 = obj.evaluate_function(prm, x, y, t, p, warp, (180, 240), 1.0)
+    assert obj.evaluate_function(prm, x, y, t, p, warp, (180, 240), 1.0) == f1          # memo hit
+    assert abs(f1 - oracle.cmax_variance(prm, x, y, t, p, blur_sigma=1.0, want_grad=False)[0]) <= 1e-5 * abs(f1)
+    x *= 0.5                                                                             # same objects, new content
+    f2 = obj.evaluate_function(prm, x, y, t, p, warp, (180, 240), 1.0)
+    fo2 = oracle.cmax_variance(prm, x, y, t, p, blur_sigma=1.0, want_grad=False)[0]
+    assert abs(f2 - fo2) <= 1e-5 * abs(fo2) and abs(f2 - f1) > 1e-3 * abs(f1)
+    for k in range(4):                                                                   # temporaries of equal length
+        xs = x * (1.0 - 0.1 * k)
+        fk = obj.evaluate_function(prm, xs, y, t, p, warp, (180, 240), 1.0)
+        fok = oracle.cmax_variance(prm, xs, y, t, p, blur_sigma=1.0, want_grad=False)[0]
+        assert abs(fk - fok) <= 1e-5 * abs(fok)
+        del xs
+
+
 def test_f32_fast_mode(oracle):
     from event_utils_b200.contrast_max import objectives
     from event_utils_b200.contrast_max.warps import linvel_warp
