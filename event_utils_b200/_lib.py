@@ -117,6 +117,10 @@ def _declare(L):
     L.evk_robust_norm_workspace_bytes.argtypes = []
     L.evk_robust_norm_f32.restype = ci
     L.evk_robust_norm_f32.argtypes = [vp, i64, i64, i64, vp, vp, vp, sz, vp]
+    L.evk_host_hash64.restype = c.c_uint64
+    L.evk_host_hash64.argtypes = [vp, sz, c.c_uint64]
+    L.evk_host_hash64_multi.restype = None
+    L.evk_host_hash64_multi.argtypes = [c.POINTER(vp), c.POINTER(sz), ci, c.c_uint64, c.POINTER(c.c_uint64)]
     L.evk_pipeline_create.restype = ci
     L.evk_pipeline_create.argtypes = [c.POINTER(vp), i64]
     L.evk_pipeline_destroy.restype = None
@@ -151,17 +155,38 @@ def lib():
         raise EvkError("event_utils_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     dev = torch.cuda.current_device()
     if dev not in _device_ok:
-        torch.cuda.init()
-        torch.empty(1, device="cuda")  # make sure the primary context exists
-        check(L.evk_device_check())
-        _device_ok[dev] = True
+        check_device(dev)
     return L
+
+
+def check_device(dev):
+    """Capability check of the device that will run the kernels (not merely the current one)."""
+    L = load()
+    dev = dev.index if isinstance(dev, torch.device) else int(dev)
+    if dev is None:
+        dev = torch.cuda.current_device()
+    if dev not in _device_ok:
+        torch.cuda.init()
+        with torch.cuda.device(dev):
+            torch.empty(1, device="cuda")  # make sure the primary context exists
+            check(L.evk_device_check())
+        _device_ok[dev] = True
 
 
 def check(rc):
     if rc != 0:
         msg = load().evk_last_error()
         raise EvkError("libevk error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def host_hashes(arrays):
+    """64-bit content hashes of contiguous numpy arrays (every byte enters), one library call for all of them."""
+    k = len(arrays)
+    ptrs = (ctypes.c_void_p * k)(*[a.ctypes.data for a in arrays])
+    sizes = (ctypes.c_size_t * k)(*[a.nbytes for a in arrays])
+    out = (ctypes.c_uint64 * k)()
+    load().evk_host_hash64_multi(ptrs, sizes, k, 0, out)
+    return tuple(out)
 
 
 def stream():
@@ -177,9 +202,12 @@ _scratch = {}
 
 def _stream_key(key, device):
     """Scratch is reused call after call, which is only safe in stream order: one buffer per
-    (purpose, device, stream), so that callers working on several streams or threads do not share one."""
+    (purpose, device, stream, host thread) -- ctypes releases the GIL during a call, so two threads that
+    share a stream (e.g. the default one) must not share a workspace either."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    return (key, idx, torch.cuda.current_stream(idx).cuda_stream)
+    if idx not in _device_ok:
+        check_device(idx)
+    return (key, idx, torch.cuda.current_stream(idx).cuda_stream, threading.get_ident())
 
 
 def scratch(key, nbytes, device):

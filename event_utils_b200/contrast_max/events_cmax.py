@@ -1,17 +1,18 @@
 """Optimiser drivers around the fused objective -- the callers of the hot path in the reference's
 lib/contrast_max/events_cmax.py (`grid_cmax` :28-76, the sampling half of `draw_objective_function`
 :100-158, `find_new_range` :160-182, `grid_search_optimisation` :184-239, `grid_search_initial`
-:241-311, `optimize_contrast` :313-346, `optimize` :348-368).  They are thin: scipy's BFGS stays on the host and calls the fused GPU
+:241-311, `optimize_contrast` :313-346, `optimize` :348-368, `optimize_r2` :370-389).  They are thin: scipy's BFGS stays on the host and calls the fused GPU
 evaluation; the grid search evaluates ALL its sample points with one pass over the events per 32
 candidates (objectives.evaluate_candidates) instead of one full evaluation per point.
 """
+import contextlib
 import copy
 
 import numpy as np
 import scipy.optimize as opt
 
 from ..util.event_util import infer_resolution
-from .objectives import evaluate_candidates, get_iwe, variance_objective
+from .objectives import evaluate_candidates, get_iwe, pinned_events, soe_objective, variance_objective
 from .warps import linvel_warp
 
 
@@ -60,25 +61,39 @@ def optimize_contrast(xs, ys, ts, ps, warp_function, objective, optimizer=opt.fm
     undefined `recursive_search` there, events_cmax.py:336).
     @returns the maximising warp parameters
     """
-    if grid_search_init and x0 is None:
-        init_obj = copy.deepcopy(objective)
-        init_obj.adaptive_lifespan = False
-        x0 = grid_search_initial(xs, ys, ts, ps, warp_function, init_obj, img_size, log_scale=False)["min_params"]
-        x0 = np.array([0, 0]) if x0 is None else np.array(x0)
-    elif x0 is None:
-        x0 = np.array([0, 0])
-    objective.iter_update(x0)
-    args = (xs, ys, ts, ps, warp_function, img_size, blur_sigma)
-    if numeric_grads:
-        return optimizer(objective.evaluate_function, x0, args=args, epsilon=1, disp=False, callback=objective.iter_update)
-    return optimizer(objective.evaluate_function, x0, fprime=objective.evaluate_gradient, args=args, disp=False,
-                     callback=objective.iter_update)
+    # nothing between here and the return modifies the event arrays (scipy hands the same `args` objects to
+    # every f / f' call), so the event set is uploaded and hashed ONCE for the whole optimisation
+    fused = getattr(warp_function, "fused_kind", None) == "linvel"
+    with (pinned_events(xs, ys, ts, ps) if fused else contextlib.nullcontext()):
+        if grid_search_init and x0 is None:
+            init_obj = copy.deepcopy(objective)
+            init_obj.adaptive_lifespan = False
+            x0 = grid_search_initial(xs, ys, ts, ps, warp_function, init_obj, img_size, log_scale=False)["min_params"]
+            x0 = np.array([0, 0]) if x0 is None else np.array(x0)
+        elif x0 is None:
+            x0 = np.array([0, 0])
+        objective.iter_update(x0)
+        args = (xs, ys, ts, ps, warp_function, img_size, blur_sigma)
+        if numeric_grads:
+            return optimizer(objective.evaluate_function, x0, args=args, epsilon=1, disp=False, callback=objective.iter_update)
+        return optimizer(objective.evaluate_function, x0, fprime=objective.evaluate_gradient, args=args, disp=False,
+                         callback=objective.iter_update)
 
 
 def optimize(xs, ys, ts, ps, warp, obj, numeric_grads=True, img_size=(180, 240)):
     """events_cmax.py:348-368: optimize_contrast with blur 1.0, numeric gradients unless the objective has analytic ones."""
     numeric_grads = numeric_grads if obj.has_derivative else True
     return optimize_contrast(xs, ys, ts, ps, warp, obj, numeric_grads=numeric_grads, blur_sigma=1.0, img_size=img_size)
+
+
+def optimize_r2(xs, ys, ts, ps, warp, obj, numeric_grads=True, img_size=(180, 240)):
+    """events_cmax.py:370-389: optimise `obj` at its default blur, then refine from that optimum with the
+    sum-of-exponentials objective at blur 1.0.  As in the reference `img_size` is accepted but NOT forwarded
+    (both stages run at optimize_contrast's default (180, 240))."""
+    soe_obj = soe_objective()
+    numeric_grads = numeric_grads if obj.has_derivative else True
+    argmax_an = optimize_contrast(xs, ys, ts, ps, warp, obj, numeric_grads=numeric_grads, blur_sigma=None)
+    return optimize_contrast(xs, ys, ts, ps, warp, soe_obj, x0=argmax_an, numeric_grads=numeric_grads, blur_sigma=1.0)
 
 
 def find_new_range(search_axes, param):

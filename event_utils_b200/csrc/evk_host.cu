@@ -6,8 +6,98 @@
 // compute stream, chunk k+1 is in flight on the copy stream.  The accumulation grid stays on the
 // device (L2 resident) for the whole call and is read back once.
 #include <stdlib.h>
+#include <string.h>
+
+#include <thread>
+#include <vector>
 
 #include "evk_common.cuh"
+
+// ---- content hash of a host buffer (identity of a cached event set) ---------------------------------
+// Four independent multiply-rotate lanes over 32-byte stripes (the structure of XXH64), merged and
+// avalanched; the tail is zero-padded into one more stripe and the length is mixed in.  Every byte of
+// the buffer enters the result.  Large buffers are cut into equal pieces hashed on separate threads and
+// the piece hashes are chained in order, so the value does not depend on the thread count.
+namespace {
+constexpr uint64_t kP1 = 0x9E3779B185EBCA87ull, kP2 = 0xC2B2AE3D27D4EB4Full, kP3 = 0x165667B19E3779F9ull,
+                   kP4 = 0x85EBCA77C2B2AE63ull, kP5 = 0x27D4EB2F165667C5ull;
+inline uint64_t rotl64(uint64_t v, int r) { return (v << r) | (v >> (64 - r)); }
+inline uint64_t lane_round(uint64_t acc, uint64_t in) { return rotl64(acc + in * kP2, 31) * kP1; }
+inline uint64_t lane_merge(uint64_t h, uint64_t v) { return (h ^ lane_round(0, v)) * kP1 + kP4; }
+
+uint64_t hash_piece(const unsigned char *p, size_t n, uint64_t seed)
+{
+    uint64_t v0 = seed + kP1 + kP2, v1 = seed + kP2, v2 = seed, v3 = seed - kP1;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        uint64_t w[4];
+        memcpy(w, p + i, 32);
+        v0 = lane_round(v0, w[0]); v1 = lane_round(v1, w[1]); v2 = lane_round(v2, w[2]); v3 = lane_round(v3, w[3]);
+    }
+    if (i < n) {
+        uint64_t w[4] = {0, 0, 0, 0};
+        memcpy(w, p + i, n - i);
+        v0 = lane_round(v0, w[0]); v1 = lane_round(v1, w[1]); v2 = lane_round(v2, w[2]); v3 = lane_round(v3, w[3]);
+    }
+    uint64_t h = rotl64(v0, 1) + rotl64(v1, 7) + rotl64(v2, 12) + rotl64(v3, 18);
+    h = lane_merge(h, v0); h = lane_merge(h, v1); h = lane_merge(h, v2); h = lane_merge(h, v3);
+    h += (uint64_t)n * kP5;
+    h ^= h >> 33; h *= kP2; h ^= h >> 29; h *= kP3; h ^= h >> 32;
+    return h;
+}
+}  // namespace
+
+// hash k buffers at once: all 1 MiB pieces of all buffers are spread over one set of threads
+static void hash_many(const void *const *ptrs, const size_t *nbytes, int k, const uint64_t *seeds, uint64_t *out)
+{
+    constexpr size_t kPiece = (size_t)1 << 20;               // fixed piece size: the result is thread-count independent
+    struct Job { const unsigned char *p; size_t len; uint64_t seed; uint64_t *dst; };
+    std::vector<Job> jobs;
+    std::vector<std::vector<uint64_t>> piece_hash(k);
+    for (int a = 0; a < k; ++a) {
+        const unsigned char *p = (const unsigned char *)ptrs[a];
+        const size_t n = p ? nbytes[a] : 0;
+        const size_t pieces = n ? (n + kPiece - 1) / kPiece : 1;
+        piece_hash[a].resize(pieces);
+        for (size_t j = 0; j < pieces; ++j) {
+            const size_t off = j * kPiece, len = n ? ((n - off < kPiece) ? n - off : kPiece) : 0;
+            jobs.push_back({n ? p + off : (const unsigned char *)"", len, seeds[a] + j, &piece_hash[a][j]});
+        }
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nthreads = hw ? hw : 4;
+    if (nthreads > 8) nthreads = 8;
+    if (nthreads > jobs.size() / 2) nthreads = jobs.size() / 2 ? jobs.size() / 2 : 1;
+    auto work = [&](size_t first, size_t step) {
+        for (size_t j = first; j < jobs.size(); j += step) *jobs[j].dst = hash_piece(jobs[j].p, jobs[j].len, jobs[j].seed);
+    };
+    if (nthreads <= 1) work(0, 1);
+    else {
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nthreads; ++t) th.emplace_back(work, t, nthreads);
+        work(0, nthreads);
+        for (auto &t : th) t.join();
+    }
+    for (int a = 0; a < k; ++a) {
+        const std::vector<uint64_t> &h = piece_hash[a];
+        out[a] = (h.size() == 1) ? h[0] : hash_piece((const unsigned char *)h.data(), h.size() * sizeof(uint64_t), seeds[a] ^ (uint64_t)nbytes[a]);
+    }
+}
+
+extern "C" uint64_t evk_host_hash64(const void *data, size_t nbytes, uint64_t seed)
+{
+    uint64_t out = 0;
+    hash_many(&data, &nbytes, 1, &seed, &out);
+    return out;
+}
+
+extern "C" void evk_host_hash64_multi(const void *const *ptrs, const size_t *nbytes, int k, uint64_t seed, uint64_t *out)
+{
+    if (k <= 0 || !ptrs || !nbytes || !out) return;
+    std::vector<uint64_t> seeds(k);
+    for (int a = 0; a < k; ++a) seeds[a] = seed + 0x9E3779B97F4A7C15ull * (uint64_t)a;
+    hash_many(ptrs, nbytes, k, seeds.data(), out);
+}
 
 struct evk_pipeline {
     int64_t chunk;            // events per chunk

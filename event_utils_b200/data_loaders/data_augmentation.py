@@ -44,8 +44,13 @@ class RobustNorm(object):
         return float(stats[0].item())
 
     def __call__(self, x, is_flow=False):
-        out, _ = self._run(x, self._rank(x.numel(), self.low_perc), self._rank(x.numel(), self.top_perc))
+        out, stats = self._run(x, self._rank(x.numel(), self.low_perc), self._rank(x.numel(), self.top_perc))
+        t_min, t_max = stats.tolist()
+        if t_max == 0 and t_min == 0:
+            return x                            # data_augmentation.py:122-123: the input object itself
         out = out.reshape(x.shape)
+        if out.dtype != x.dtype and x.dtype.is_floating_point:
+            out = out.to(x.dtype)               # the reference's clamp / divide keep the input dtype
         return out if out.device == x.device else out.to(x.device)
 
     def __repr__(self):

@@ -244,7 +244,8 @@ def _cmax_images_cuda(params, xs, ys, ts, ps, t_ref, img_size, want_grad, use_po
                                                       _lib.ptr(diwe), _lib.ptr(ws), ws.numel(), _lib.stream()))
         else:
             x, y, p = (a.to(torch.float32).contiguous() for a in (xs, ys, ps))
-            t = (ts.to(torch.float32) - float(t_ref)).contiguous()      # fast mode: t relative to the reference time
+            # fast mode: t relative to the reference time, formed in f64 (integer / large absolute stamps), then f32
+            t = (ts.to(torch.float64) - float(t_ref)).to(torch.float32).contiguous()
             _lib.check(L.evk_cmax_linvel_variance_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), n, 1.0,
                                                       float(params[0]), float(params[1]), int(img_size[0]), int(img_size[1]),
                                                       Hs, Ws, 0.0, flags, _lib.ptr(result), _lib.ptr(images[0]), _lib.ptr(diwe),

@@ -31,7 +31,15 @@ def warp_events_flow_torch(xt, yt, tt, pt, flow_field, t0=None,
         raise RuntimeError("flow_field must have shape (2,H,W) or (1,2,H,W), got %s" % (tuple(flow_field.shape),))
     dev = E.compute_device(xt, yt, tt, flow)
     with torch.cuda.device(dev):
-        x, y, t = (a.reshape(-1).to(dev).to(torch.float32).contiguous() for a in (xt, yt, tt))
+        x, y = (a.reshape(-1).to(dev).to(torch.float32).contiguous() for a in (xt, yt))
+        t = tt.reshape(-1).to(dev)
+        if t.dtype != torch.float32:
+            # the reference forms dt = tt - t0 in the INPUT dtype (optic_flow.py:33): absolute float64 / integer
+            # stamps must not be rounded to float32 before the subtraction.  Pass the relative times, t0 = 0.
+            t = (t - t0).to(torch.float32).contiguous()
+            t0 = 0.0
+        else:
+            t = t.contiguous()
         f = flow[0].to(dev).to(torch.float32).contiguous()
         xw, yw = torch.empty_like(x), torch.empty_like(y)
         ws = _lib.scratch("flow_ws", L.evk_warp_flow_workspace_bytes(f.shape[1], f.shape[2]), dev)

@@ -339,6 +339,18 @@ int evk_voxel_host_packed_f32(evk_pipeline_t *pipe, const int16_t *x, const int1
                               const uint8_t *p, int64_t n, double t_first, double t_last, int B, int H,
                               int W, unsigned flags, float *out_host, unsigned long long *oob_host);
 
+/* ---------------------------------------------------------------------------------------------
+ * 64-bit content hash of a HOST buffer (every byte enters; multi-threaded above 2 MiB, result independent
+ * of the thread count).  The identity of an event set in the host-side cache of uploaded events: the
+ * reference's objective is a pure function of the arrays it is handed at every call
+ * (lib/contrast_max/objectives.py:211-236), so a cached device copy may only be reused when the host
+ * arrays are byte-identical to the ones that were uploaded.  No device work.
+ * --------------------------------------------------------------------------------------------- */
+uint64_t evk_host_hash64(const void *data, size_t nbytes, uint64_t seed);
+/* k buffers in one call (one pool of threads for all of them); out[a] = hash of buffer a under a seed derived from
+ * `seed` and a, so equal contents at different positions hash differently. */
+void evk_host_hash64_multi(const void *const *ptrs, const size_t *nbytes, int k, uint64_t seed, uint64_t *out);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -33,7 +33,7 @@ def declared_prototypes():
     src = open(os.path.join(ROOT, "include", "evk.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     protos = {}
-    for m in re.finditer(r"\b(?:int|size_t|const char \*|void)\s*\*?\s*(evk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(?:int|size_t|uint64_t|const char \*|void)\s*\*?\s*(evk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
         params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
         protos[m.group(1)] = [] if params in ([""], ["void"]) else params
     return protos
@@ -52,7 +52,7 @@ def test_ctypes_declarations_match_the_header():
         c = re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*$", "", c).strip() if not c.endswith("*") else c   # drop the parameter name
         if "*" in c_type:
             return "ptr"
-        for key, val in (("int64_t", "i64"), ("size_t", "size"), ("unsigned", "u32"), ("double", "f64"), ("float", "f32"), ("int", "i32")):
+        for key, val in (("uint64_t", "size"), ("int64_t", "i64"), ("size_t", "size"), ("unsigned", "u32"), ("double", "f64"), ("float", "f32"), ("int", "i32")):
             if re.search(r"\b%s\b" % key, c_type):
                 return val
         raise AssertionError("unparsed parameter type %r" % c_type)

