@@ -29,6 +29,7 @@ VARIANT_VECTOR_RED = 2 << 8
 VARIANT_SMEM_TILE = 3 << 8
 VARIANT_WARP_AGG = 4 << 8
 TS_REVERSE = 0x80
+TS_RAW = 0x1000
 CMAX_WANT_GRAD = 0x10
 CMAX_ABS_POLARITY = 0x20
 CMAX_NO_CHANNEL_MIX = 0x40

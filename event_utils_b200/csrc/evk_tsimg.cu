@@ -118,6 +118,7 @@ int evk_timestamp_image_f32(const float *x, const float *y, const float *t, cons
     A.x = x; A.y = y; A.t = t; A.p = p; A.n = n;
     A.t_first = t_first; A.t_last = t_last;
     A.denom = (t_last - t_first) + 1e-6f;  // f32: ts[-1]-ts[0]+epsilon (image.py:317-321)
+    if (flags & EVK_TS_RAW) { A.t_first = 0.0f; A.denom = 1.0f; }  // (t - 0) / 1 == t exactly: normalize_timestamps=False (image.py:261)
     A.reverse = (flags & EVK_TS_REVERSE) ? 1 : 0;
     A.H = Himg; A.W = Wimg; A.clip = (flags & EVK_CLIP) ? 1 : 0; A.clipx = clipx; A.clipy = clipy;
     A.ws = static_cast<float *>(workspace); A.oob = oob;

@@ -182,7 +182,8 @@ def image_to_event_weights(xs, ys, img):
         return out.cpu().numpy()
 
 
-def _timestamp_images(x, y, t, p, t_first, t_last, sensor_size, clip_out_of_range, interpolation, padding, reverse):
+def _timestamp_images(x, y, t, p, t_first, t_last, sensor_size, clip_out_of_range, interpolation, padding, reverse,
+                      raw=False):
     L = _lib.lib()
     dev = x.device
     if padding:
@@ -196,7 +197,7 @@ def _timestamp_images(x, y, t, p, t_first, t_last, sensor_size, clip_out_of_rang
         neg = torch.empty(img_size, dtype=torch.float32, device=dev)
         ws = _lib.scratch("tsimg_ws", L.evk_timestamp_image_workspace_bytes(*img_size), dev)
         oob = _lib.oob_counter(dev)
-        flags = (_lib.CLIP if clip_out_of_range else 0) | (_lib.TS_REVERSE if reverse else 0)
+        flags = (_lib.CLIP if clip_out_of_range else 0) | (_lib.TS_REVERSE if reverse else 0) | (_lib.TS_RAW if raw else 0)
         _lib.check(L.evk_timestamp_image_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), x.shape[0], t_first, t_last,
                                              img_size[0], img_size[1], float(clipx), float(clipy), flags, _lib.ptr(pos),
                                              _lib.ptr(neg), _lib.ptr(ws), ws.numel(), _lib.ptr(oob), _lib.stream()))
@@ -233,9 +234,8 @@ def events_to_timestamp_image(xn, yn, ts, pn,
     """
     numpy flavour; drop-in for image.py:219-284 (numpy in, numpy float32 out).  Timestamps are made
     relative to ts[0] in float64 before the cast to float32, like the reference (:241-243).
+    normalize_timestamps=False (:261): the weights are those relative stamps themselves (EVK_TS_RAW).
     """
-    if not normalize_timestamps:
-        raise NotImplementedError("normalize_timestamps=False is not provided by the GPU path")
     dev = E.compute_device()
     ts = np.asarray(ts, dtype=np.float64).reshape(-1)
     rel = ts - ts[0]
@@ -243,7 +243,7 @@ def events_to_timestamp_image(xn, yn, ts, pn,
     t = torch.from_numpy(rel).to(dev).float().contiguous()
     # the reference divides by (ts[-1] + 1e-6) of the RELATIVE stamps (image.py:261): first = 0
     pos, neg = _timestamp_images(x, y, t, p, 0.0, float(np.float32(rel[-1])), sensor_size, clip_out_of_range,
-                                 interpolation, padding, False)
+                                 interpolation, padding, False, raw=not normalize_timestamps)
     return pos.cpu().numpy(), neg.cpu().numpy()
 
 

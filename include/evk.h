@@ -61,6 +61,7 @@ extern "C" {
 #define EVK_VARIANT_WARP_AGG (4u << EVK_VARIANT_SHIFT)   /* warp-aggregated (match.any) global reds, for hot-spot streams */
 
 #define EVK_TS_REVERSE 0x80u  /* timestamp images: timestamp_reverse=True (image.py:318-319) */
+#define EVK_TS_RAW 0x1000u    /* timestamp images: normalize_timestamps=False (image.py:261): weights = t as given */
 
 /* cmax flags */
 #define EVK_CMAX_WANT_GRAD 0x10u    /* also produce the analytic gradient */

@@ -382,7 +382,8 @@ EVO_API void evo_bounds_mask_f64(const double *x, const double *y, int64_t n, do
 /* ------------------------------------------------------------------------------------------
  * image.py:286-353 events_to_timestamp_image_torch (and :219-284, same arithmetic after its
  * casts): average-timestamp images of the positive / negative events.
- *   tn = (t - t_first) / (t_last - t_first + 1e-6)        (reverse: (-t + t_last) / (...))
+ *   tn = (t - t_first) / (t_last - t_first + 1e-6)        (reverse: (-t + t_last) / (...);
+ *   reverse == 2: tn = t, the numpy flavour's normalize_timestamps=False, image.py:261)
  *   four bilinear accumulations: tn*[p>0], [p>0], tn*[p<=0], [p<=0]; the two count images
  *   start at ONE (image.py:333,335); the clip mask zeroes the INDEX only, never the weights
  *   (masked_ps is computed but unused, image.py:330); result = sum / count with count==0 -> 1.
@@ -406,7 +407,7 @@ EVO_API int64_t evo_timestamp_image_f32(const float *x, const float *y, const fl
         int64_t x0, x1, y0, y1;
         if (!wrap_index(px, Wimg, &x0) || !wrap_index(px + 1, Wimg, &x1) ||
             !wrap_index(py, Himg, &y0) || !wrap_index(py + 1, Himg, &y1)) { ++oob; continue; }
-        float tn = reverse ? ((-t[i] + t_last) / denom) : ((t[i] - t_first) / denom);
+        float tn = (reverse == 2) ? t[i] : (reverse ? ((-t[i] + t_last) / denom) : ((t[i] - t_first) / denom));
         float pm = (p[i] > 0.0f) ? 1.0f : 0.0f, nm = (p[i] <= 0.0f) ? 1.0f : 0.0f;
         float w[4] = {tn * pm, pm, tn * nm, nm};
         float ox = 1.0f - dx, oy = 1.0f - dy;

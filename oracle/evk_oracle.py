@@ -121,8 +121,9 @@ def image_torch_f32(xs, ys, ps, sensor_size=(180, 240), clip_out_of_range=True,
 
 
 def timestamp_image_f32(xs, ys, ts, ps, sensor_size=(180, 240), clip_out_of_range=True, interpolation='bilinear',
-                        padding=True, timestamp_reverse=False):
-    """events_to_timestamp_image_torch, image.py:286-353 -> (img_pos, img_neg)."""
+                        padding=True, timestamp_reverse=False, normalize_timestamps=True):
+    """events_to_timestamp_image_torch, image.py:286-353 -> (img_pos, img_neg).
+    normalize_timestamps=False: the numpy flavour's raw-stamp weights (image.py:261)."""
     x, y, t, p = (_c(np.asarray(a).reshape(-1), np.float32) for a in (xs, ys, ts, ps))
     H, W = int(sensor_size[0]), int(sensor_size[1])
     if padding:
@@ -133,7 +134,8 @@ def timestamp_image_f32(xs, ys, ts, ps, sensor_size=(180, 240), clip_out_of_rang
         clipx, clipy = W - 1, H - 1
     out = np.zeros((2, H, W), np.float32)
     oob = lib().evo_timestamp_image_f32(_p(x), _p(y), _p(t), _p(p), x.shape[0], float(t[0]), float(t[-1]),
-                                        int(bool(timestamp_reverse)), H, W, int(bool(clip_out_of_range)),
+                                        int(bool(timestamp_reverse)) if normalize_timestamps else 2, H, W,
+                                        int(bool(clip_out_of_range)),
                                         float(clipx), float(clipy), _p(out))
     if oob:
         raise OracleIndexError("%d events index outside the image" % oob)

@@ -150,6 +150,10 @@ for tag, kw in {"default": dict(), "reverse": dict(timestamp_reverse=True), "nop
 t64 = ts.astype(np.float64) + 1.6e9
 a, b = ref.image.events_to_timestamp_image(xs.astype(np.float64), ys.astype(np.float64), t64, ps.astype(np.float64), sensor_size=(40, 56))
 cases.update(dict(np_t=t64, np_pos=a, np_neg=b))
+# normalize_timestamps=False (image.py:261): the weights are the stamps relative to ts[0], not divided by the span
+a, b = ref.image.events_to_timestamp_image(xs.astype(np.float64), ys.astype(np.float64), t64, ps.astype(np.float64), sensor_size=(40, 56),
+                                           normalize_timestamps=False)
+cases.update(dict(np_raw_pos=a, np_raw_neg=b))
 save("tsimg", **cases)
 
 # ---- lower-level helpers (image.py:102-160) and the bounds mask -------------------------------

@@ -164,6 +164,10 @@ def test_timestamp_images(oracle):
     assert pos.dtype == np.float32
     assert_close_to_max(pos, g["np_pos"], 1e-5)
     assert_close_to_max(neg, g["np_neg"], 1e-5)
+    pos, neg = events_to_timestamp_image(g["x"].astype(np.float64), g["y"].astype(np.float64), g["np_t"], g["p"].astype(np.float64),
+                                         sensor_size=(40, 56), normalize_timestamps=False)        # image.py:261
+    assert_close_to_max(pos, g["np_raw_pos"], 1e-5)
+    assert_close_to_max(neg, g["np_raw_neg"], 1e-5)
     # larger random case against the oracle
     xe, ye, te, pe = make_events(17, 700000, 180, 240)
     pos, neg = events_to_timestamp_image_torch(*dev(xe, ye, te, pe))

@@ -94,6 +94,9 @@ def test_timestamp_images(oracle):
     pos, neg = oracle.timestamp_image_f32(g["x"], g["y"], rel, g["p"], sensor_size=(40, 56))
     assert_close_to_max(pos, g["np_pos"], 2e-6)
     assert_close_to_max(neg, g["np_neg"], 2e-6)
+    pos, neg = oracle.timestamp_image_f32(g["x"], g["y"], rel, g["p"], sensor_size=(40, 56), normalize_timestamps=False)
+    assert_close_to_max(pos, g["np_raw_pos"], 2e-6)
+    assert_close_to_max(neg, g["np_raw_neg"], 2e-6)
 
 
 def test_flow_warp(oracle):
