@@ -37,6 +37,7 @@ class _DeviceEvents:
 
 _event_cache = []          # most recent first, at most _CACHE_SLOTS entries
 _CACHE_SLOTS = 2
+event_pass = None          # None: automatic; "onchip": shared-memory IWE (cmax_onchip_kernel); "l2": L2 vector reductions
 precision = "f64"          # "f64": parity mode (events kept as f64, 32 B/event)
                            # "f32": fast mode (x, y, t - t_last, p as f32, 16 B/event)
 
@@ -167,7 +168,8 @@ def _fused_linvel(params, xs, ys, ts, ps, img_size, blur_sigma, want_grad, use_p
         iwe = torch.empty((Hs + 1, Ws + 1), dtype=torch.float32, device=dev) if want_images else None
         d_iwe = torch.empty((2, Hs + 1, Ws + 1), dtype=torch.float32, device=dev) if (want_images and want_grad) else None
         flags = (_lib.CMAX_WANT_GRAD if want_grad else 0) | (0 if use_polarity else _lib.CMAX_ABS_POLARITY) \
-            | (0 if channel_mix else _lib.CMAX_NO_CHANNEL_MIX)
+            | (0 if channel_mix else _lib.CMAX_NO_CHANNEL_MIX) \
+            | {None: 0, "onchip": _lib.VARIANT_SMEM_TILE, "l2": _lib.VARIANT_VECTOR_RED}[event_pass]
         sigma = float(blur_sigma) if blur_sigma is not None else 0.0
         # the reference warps to the LAST timestamp of the (possibly sliced) event set (objectives.py:186)
         if ev.mode == "f64":

@@ -23,6 +23,19 @@
 //     whatever its width (scalar, v2, v4) and whether or not lanes share a sector -- the count of
 //     reduction operations is what has to be minimised.  The accumulator (181*241*32 B = 1.4 MB
 //     per replica, R <= 8 replicas against same-address serialisation) never leaves L2.
+//   * ON-CHIP IWE (round 2, large event counts): the whole 181x241 image of warped events is 174 KB -- it
+//     fits in ONE SM's shared memory.  cmax_onchip_kernel runs one 1024-thread CTA per SM, each with a
+//     PRIVATE fixed-point image in shared memory; the four bilinear taps are native integer shared-memory
+//     atomics (ATOMS.ADD; measured: 4 per event are hidden under the HBM read of the events, while f32
+//     shared atomics are CAS loops and L2 reductions cost ~0.3 ms per 50 M).  Fixed point = value * 2^22 in
+//     a biased u32 cell; the RETURNING atomic tells the thread whether ITS add wrapped the 32-bit cell and
+//     that thread carries +-2^10 out to the global accumulator, so the sum is exact integer arithmetic with
+//     no overflow whatever the stream (per-tap quantisation 2^-23, below f32 rounding of the reference's
+//     own accumulation).  Events with |p*mask| > 1 or non-finite weights take the global f32 path.  At
+//     the end every CTA converts its image to f32 in place and adds it to a planar global image with TMA
+//     bulk reductions (cp.reduce.async.bulk.global.shared::cta.add.f32, SASS UBLKRED) -- "finished tiles
+//     leave through TMA".  The derivative images do not fit next to the IWE (3 x 174 KB), so with the
+//     gradient their four free values per event remain ONE vector reduction to the L2 block accumulator.
 //   * The reference blurs both derivative images and multiplies by the un-blurred IWE.  The
 //     reflect-boundary Gaussian is self-adjoint, so  sum(2(I-mu) * G(D_k)) == sum(G(2(I-mu)) * D_k)
 //     and G(2(I-mu)) = 2(G(I)-mu): ONE blur of ONE image (which f needs anyway) serves f and g.
@@ -30,6 +43,7 @@
 //     (objectives.py:253), mixing the two gradient components by [[a,b],[b,a]]; applied to the
 //     two scalars at the end (host supplies a,b).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "evk_common.cuh"
@@ -58,7 +72,8 @@ struct CmaxArgs {
     int Hc, Wc;  // canvas = sensor + 1
     int abs_polarity;
     int replicas;
-    float *acc;  // [R][Hc*Wc][4]
+    float *acc;  // [R][Hc*Wc][8]
+    float *planar;  // on-chip path: planar f32 image [npix padded to 4] the CTAs' shared-memory images are reduced into
     unsigned long long *oob;
 };
 
@@ -71,50 +86,115 @@ enum { WARP_LINVEL_F64 = 0, WARP_LINVEL_F32 = 1, WARP_FLOW_F32 = 2 };
 // contiguous bytes (pixels x0, x0+1 of the interleaved accumulator) in the same instruction, which
 // the LSU merges into one L2 request per row: half the L2 tag look-ups of the one-lane-per-event
 // form (the measured limiter, lts__t_tag_requests ~75 % of peak).
+struct Taps {
+    int x0, x1, y0, y1;
+    float wm;     // masked weight (|wm| <= 1 is the fast-path condition of the on-chip image)
+    float4 ti;    // IWE taps TL, TR, BL, BR
+    float4 td;    // free values of the derivative taps: a = am*oy, b = am*dy, c = am*ox, d = am*dx
+};
+
+// The arithmetic of one bilinear splat (image.py:199-207, :131-135), shared by the two accumulator back ends.
+// Returns false when the event contributes nothing (out of the canvas -> counted, or all-zero weights).
 template <bool GRAD>
-__device__ __forceinline__ void splat(const CmaxArgs &A, float *acc, float xf, float yf, float w, float a,
-                                      bool clip, unsigned &oob)
+__device__ __forceinline__ bool splat_taps(const CmaxArgs &A, float xf, float yf, float w, float a, bool clip, unsigned &oob, Taps &T)
 {
     const float clipx = (float)(A.Wc - 1), clipy = (float)(A.Hc - 1);
     float m2 = 1.0f;
     if (clip) m2 = (xf >= clipx ? 0.0f : 1.0f) * (yf >= clipy ? 0.0f : 1.0f);
     const float pxf = floorf(xf), pyf = floorf(yf);
     const float dx = __fsub_rn(xf, pxf), dy = __fsub_rn(yf, pyf);
-    int upx, upy, x0, x1, y0, y1;
+    int upx, upy;
     if (!trunc_checked(__fmul_rn(pxf, m2), upx) || !trunc_checked(__fmul_rn(pyf, m2), upy) ||
-        !wrap_int_index(upx, A.Wc, x0) || !wrap_int_index(upx + 1, A.Wc, x1) ||
-        !wrap_int_index(upy, A.Hc, y0) || !wrap_int_index(upy + 1, A.Hc, y1)) { ++oob; return; }
+        !wrap_int_index(upx, A.Wc, T.x0) || !wrap_int_index(upx + 1, A.Wc, T.x1) ||
+        !wrap_int_index(upy, A.Hc, T.y0) || !wrap_int_index(upy + 1, A.Hc, T.y1)) { ++oob; return false; }
     const float wm = __fmul_rn(w, m2);
     const float am = GRAD ? __fmul_rn(a, wm) : 0.0f;  // jacobian * masked_ps (image.py:211-212)
-    if (wm == 0.0f && am == 0.0f) return;
+    if (wm == 0.0f && am == 0.0f) return false;
     const float ox = __fsub_rn(1.0f, dx), oy = __fsub_rn(1.0f, dy);
     const float wl = __fmul_rn(wm, ox), wr = __fmul_rn(wm, dx);
+    T.wm = wm;
     // tap order inside a block: TL (y0,x0), TR (y0,x1), BL (y1,x0), BR (y1,x1)
-    const float4 ti = make_float4(__fmul_rn(wl, oy), __fmul_rn(wr, oy), __fmul_rn(wl, dy), __fmul_rn(wr, dy));
+    T.ti = make_float4(__fmul_rn(wl, oy), __fmul_rn(wr, oy), __fmul_rn(wl, dy), __fmul_rn(wr, dy));
     // image.py:131-135 with w1 = [am;0], w2 = [0;am]:
     //   D0 taps = am*{-oy, +oy, -dy, +dy}   -> TL = -TR, BL = -BR : two free values a = am*oy, b = am*dy
     //   D1 taps = am*{-ox, -dx, +ox, +dx}   -> TL = -BL, TR = -BR : two free values c = am*ox, d = am*dx
     // (negation is exact and commutes with the sums, so accumulating a,b,c,d and restoring the
     // signs in the fold gives the same images) -> both derivative images are ONE vector reduction.
-    float4 td = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (GRAD) td = make_float4(__fmul_rn(am, oy), __fmul_rn(am, dy), __fmul_rn(am, ox), __fmul_rn(am, dx));
-    if (x1 == x0 + 1 && y1 == y0 + 1) {
-        float *blk = acc + ((int64_t)y0 * A.Wc + x0) * kBlockFloats;
-        red_add4(blk, ti);
-        if (GRAD) red_add4(blk + 4, td);
+    T.td = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (GRAD) T.td = make_float4(__fmul_rn(am, oy), __fmul_rn(am, dy), __fmul_rn(am, ox), __fmul_rn(am, dx));
+    return true;
+}
+
+// taps -> the global block accumulator.  WANT_I / WANT_D select the image taps and the derivative values.
+template <bool WANT_I, bool WANT_D>
+__device__ __forceinline__ void emit_global(const CmaxArgs &A, float *acc, const Taps &T)
+{
+    if (T.x1 == T.x0 + 1 && T.y1 == T.y0 + 1) {
+        float *blk = acc + ((int64_t)T.y0 * A.Wc + T.x0) * kBlockFloats;
+        if (WANT_I) red_add4(blk, T.ti);
+        if (WANT_D) red_add4(blk + 4, T.td);
         return;
     }
     // wrapped footprint (negative coordinates, only reachable without the bounds mask): every tap
     // becomes the TL tap of its own pixel's block (TL of D0 is -a, TL of D1 is -c)
-    const float vi[4] = {ti.x, ti.y, ti.z, ti.w};
-    const float v0[4] = {-td.x, td.x, -td.y, td.y}, v1[4] = {-td.z, -td.w, td.z, td.w};
-    const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
+    const float vi[4] = {T.ti.x, T.ti.y, T.ti.z, T.ti.w};
+    const float v0[4] = {-T.td.x, T.td.x, -T.td.y, T.td.y}, v1[4] = {-T.td.z, -T.td.w, T.td.z, T.td.w};
+    const int ys[4] = {T.y0, T.y0, T.y1, T.y1}, xs[4] = {T.x0, T.x1, T.x0, T.x1};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         float *bk = acc + ((int64_t)ys[k] * A.Wc + xs[k]) * kBlockFloats;
-        if (vi[k] != 0.0f) red_add(bk, vi[k]);
-        if (GRAD && v0[k] != 0.0f) red_add(bk + 4, -v0[k]);
-        if (GRAD && v1[k] != 0.0f) red_add(bk + 6, -v1[k]);
+        if (WANT_I && vi[k] != 0.0f) red_add(bk, vi[k]);
+        if (WANT_D && v0[k] != 0.0f) red_add(bk + 4, -v0[k]);
+        if (WANT_D && v1[k] != 0.0f) red_add(bk + 6, -v1[k]);
+    }
+}
+
+// bilinear splat of weight w (and derivative weight a) at (xf, yf) on the canvas, L2 back end
+template <bool GRAD>
+__device__ __forceinline__ void splat(const CmaxArgs &A, float *acc, float xf, float yf, float w, float a,
+                                      bool clip, unsigned &oob)
+{
+    Taps T;
+    if (!splat_taps<GRAD>(A, xf, yf, w, a, clip, oob, T)) return;
+    emit_global<true, GRAD>(A, acc, T);
+}
+
+// ---- on-chip back end: the IWE lives in the CTA's shared memory as biased fixed point ----------------
+constexpr int kFixBits = 22;
+constexpr float kFixScale = (float)(1 << kFixBits);
+constexpr float kFixCarry = (float)(1u << (32 - kFixBits));   // value of one 2^32 wrap of a cell
+constexpr unsigned kFixBias = 0x80000000u;
+
+__device__ __forceinline__ void onchip_tap(unsigned *simg, float *acc_tl, int pix, float v)
+{
+    const int q = __float2int_rn(__fmul_rn(v, kFixScale));      // |v| <= 1 -> |q| <= 2^22
+    if (q == 0) return;
+    unsigned old;
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(simg + pix);
+    asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"((unsigned)q));
+    // did THIS add wrap the 32-bit cell?  The wrap is carried to the global accumulator (TL slot of the
+    // pixel's own block, which the fold adds to the pixel), so the total is exact for any event count.
+    if (q > 0) {
+        if (old + (unsigned)q < old) red_add(acc_tl + (int64_t)pix * kBlockFloats, kFixCarry);
+    } else {
+        if (old < (unsigned)(-q)) red_add(acc_tl + (int64_t)pix * kBlockFloats, -kFixCarry);
+    }
+}
+
+template <bool GRAD>
+__device__ __forceinline__ void splat_onchip(const CmaxArgs &A, float *acc, unsigned *simg, float xf, float yf, float w, float a,
+                                             bool clip, unsigned &oob)
+{
+    Taps T;
+    if (!splat_taps<GRAD>(A, xf, yf, w, a, clip, oob, T)) return;
+    if (fabsf(T.wm) <= 1.0f) {      // false for NaN / inf as well
+        onchip_tap(simg, acc, T.y0 * A.Wc + T.x0, T.ti.x);
+        onchip_tap(simg, acc, T.y0 * A.Wc + T.x1, T.ti.y);
+        onchip_tap(simg, acc, T.y1 * A.Wc + T.x0, T.ti.z);
+        onchip_tap(simg, acc, T.y1 * A.Wc + T.x1, T.ti.w);
+        if (GRAD) emit_global<false, true>(A, acc, T);
+    } else {
+        emit_global<true, GRAD>(A, acc, T);
     }
 }
 
@@ -139,9 +219,9 @@ __device__ __forceinline__ Event<WARP> load_event(const CmaxArgs &A, int64_t i)
     return e;
 }
 
-template <int WARP, bool GRAD>
+template <int WARP, bool GRAD, bool ONCHIP = false>
 __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const Event<WARP> &e, unsigned &oob, double cvx,
-                                           double cvy)
+                                           double cvy, unsigned *simg = nullptr)
 {
     if (WARP == WARP_LINVEL_F64) {
         const double x = e.x, y = e.y, t = e.t;
@@ -154,7 +234,8 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const 
         // event_util.py:26-27: keep iff 0 < x' <= Wm and 0 < y' <= Hm (NaN compares false -> kept)
         const bool keep = !(xw <= 0.0 || xw > (double)A.Wm) && !(yw <= 0.0 || yw > (double)A.Hm);
         if (!keep) return;  // x,y,p,j all multiplied by 0: only exact zeros are added at (0,0)..(1,1)
-        splat<GRAD>(A, acc, (float)xw, (float)yw, (float)p, (float)(-d), true, oob);  // image.py:180-183 casts
+        if (ONCHIP) splat_onchip<GRAD>(A, acc, simg, (float)xw, (float)yw, (float)p, (float)(-d), true, oob);
+        else splat<GRAD>(A, acc, (float)xw, (float)yw, (float)p, (float)(-d), true, oob);  // image.py:180-183 casts
     } else if (WARP == WARP_LINVEL_F32) {
         const float x = e.x, y = e.y;
         const float d = e.t;  // already t - t_ref
@@ -165,7 +246,8 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const 
         const float xw = __fsub_rn(x, __fmul_rn(d, vx)), yw = __fsub_rn(y, __fmul_rn(d, vy));
         const bool keep = !(xw <= 0.0f || xw > (float)A.Wm) && !(yw <= 0.0f || yw > (float)A.Hm);
         if (!keep) return;
-        splat<GRAD>(A, acc, xw, yw, p, -d, true, oob);
+        if (ONCHIP) splat_onchip<GRAD>(A, acc, simg, xw, yw, p, -d, true, oob);
+        else splat<GRAD>(A, acc, xw, yw, p, -d, true, oob);
     } else {
         // optic_flow.py:37-44 then events_to_image_torch(..., interpolation='bilinear') defaults
         const float xe = e.x, ye = e.y, te = e.t;
@@ -193,7 +275,8 @@ __device__ __forceinline__ void cmax_event(const CmaxArgs &A, float *acc, const 
             u = __fadd_rn(u, __fmul_rn(bot.z, se)); v = __fadd_rn(v, __fmul_rn(bot.w, se));
         }
         const float d = __fsub_rn(te, A.flow_t0);
-        splat<false>(A, acc, __fadd_rn(xe, __fmul_rn(u, d)), __fadd_rn(ye, __fmul_rn(v, d)), p, 0.0f, true, oob);
+        if (ONCHIP) splat_onchip<false>(A, acc, simg, __fadd_rn(xe, __fmul_rn(u, d)), __fadd_rn(ye, __fmul_rn(v, d)), p, 0.0f, true, oob);
+        else splat<false>(A, acc, __fadd_rn(xe, __fmul_rn(u, d)), __fadd_rn(ye, __fmul_rn(v, d)), p, 0.0f, true, oob);
     }
 }
 
@@ -219,6 +302,53 @@ __global__ void __launch_bounds__(256) cmax_scatter_kernel(const CmaxArgs A)
     }
     for (; i < A.n; i += stride) cmax_event<WARP, GRAD>(A, acc, load_event<WARP>(A, i), oob, A.vx, A.vy);
     flush_oob(A.oob, oob);
+}
+
+// The on-chip event pass: one persistent 1024-thread CTA per SM, private fixed-point IWE in shared memory.
+constexpr int kOnchipThreads = 1024;
+constexpr int kBulkFloats = 4096;   // 16 KB per TMA bulk reduction
+
+template <int WARP, bool GRAD>
+__global__ void __launch_bounds__(kOnchipThreads, 1) cmax_onchip_kernel(const CmaxArgs A)
+{
+    extern __shared__ __align__(128) unsigned simg[];   // [npad] biased fixed point, then f32 in place
+    const int npix = A.Hc * A.Wc, npad = (npix + 3) & ~3;
+    for (int i = threadIdx.x; i < npad; i += kOnchipThreads) simg[i] = kFixBias;
+    __syncthreads();
+    unsigned oob = 0;
+    // derivative reductions and carries go to the L2 block accumulator (replicas against same-address serialisation)
+    float *acc = A.acc + (int64_t)(blockIdx.x % A.replicas) * A.Hc * A.Wc * kBlockFloats;
+    const int64_t stride = (int64_t)gridDim.x * kOnchipThreads;
+    int64_t i = (int64_t)blockIdx.x * kOnchipThreads + threadIdx.x;
+    constexpr int kB = (WARP == WARP_LINVEL_F64) ? 2 : 4;   // loads in flight per thread (64-register budget at 1024 threads)
+    for (; i + (kB - 1) * stride < A.n; i += kB * stride) {
+        Event<WARP> ev[kB];
+#pragma unroll
+        for (int k = 0; k < kB; ++k) ev[k] = load_event<WARP>(A, i + k * stride);
+#pragma unroll
+        for (int k = 0; k < kB; ++k) cmax_event<WARP, GRAD, true>(A, acc, ev[k], oob, A.vx, A.vy, simg);
+    }
+    for (; i < A.n; i += stride) cmax_event<WARP, GRAD, true>(A, acc, load_event<WARP>(A, i), oob, A.vx, A.vy, simg);
+    flush_oob(A.oob, oob);
+    __syncthreads();
+    // fixed point -> f32 in place (an int32 sum rounds to f32 once, like a float accumulator's final value)
+    float *fimg = reinterpret_cast<float *>(simg);
+    for (int j = threadIdx.x; j < npad; j += kOnchipThreads)
+        fimg[j] = __fmul_rn((float)(int)(simg[j] - kFixBias), 1.0f / kFixScale);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
+    __syncthreads();
+    // the finished image leaves through TMA: bulk add-reductions of 16 KB pieces into the planar global image
+    if ((threadIdx.x & 31) == 0) {
+        for (int c = threadIdx.x >> 5; c * kBulkFloats < npad; c += kOnchipThreads / 32) {
+            const int off = c * kBulkFloats;
+            const int cnt = (npad - off < kBulkFloats) ? (npad - off) : kBulkFloats;
+            const unsigned src = (unsigned)__cvta_generic_to_shared(fimg + off);
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
+                             __cvta_generic_to_global(A.planar + off)), "r"(src), "r"(cnt * 4) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the engine's reads
+    }
 }
 
 // K candidate parameter points in ONE pass over the events (grid_search_initial evaluates 25 points per
@@ -268,7 +398,8 @@ __device__ __forceinline__ void block_add(double v, double *dst)
 // Blocks -> planar images.  Block (y,x) holds the 2x2 footprint anchored at (y,x) in tap order
 // TL,TR,BL,BR, so pixel (y,x) collects TL of block (y,x), TR of (y,x-1), BL of (y-1,x) and BR of
 // (y-1,x-1), over all replicas.
-__global__ void __launch_bounds__(256) cmax_gather_kernel(const float *__restrict__ acc, int replicas, int Hc, int Wc,
+__global__ void __launch_bounds__(256) cmax_gather_kernel(const float *__restrict__ acc, const float *__restrict__ planar,
+                                                          int replicas, int Hc, int Wc,
                                                           float *__restrict__ I, float *__restrict__ D0,
                                                           float *__restrict__ D1, float *__restrict__ iwe_out,
                                                           float *__restrict__ diwe_out, double *sums)
@@ -278,6 +409,7 @@ __global__ void __launch_bounds__(256) cmax_gather_kernel(const float *__restric
     float a = 0.f, b = 0.f, c = 0.f;
     if (i < npix) {
         const int y = i / Wc, x = i - y * Wc;
+        if (planar) a = planar[i];      // the on-chip images (cmax_onchip_kernel); the blocks then hold carries / slow-path taps only
         for (int r = 0; r < replicas; ++r) {
             const float *base = acc + (int64_t)r * npix * kBlockFloats;
 #pragma unroll
@@ -517,11 +649,11 @@ __global__ void cmax_obj_final_kernel(int kind, const double *gsums, const unsig
 // evaluation is launch-bound.
 constexpr int kTileY = 8, kTileX = 32, kFusedMaxR = 8;
 
-__device__ __forceinline__ float gather_pixel(const float *acc, int replicas, int Hc, int Wc, int y, int x, int comp)
+__device__ __forceinline__ float gather_pixel(const float *acc, const float *planar, int replicas, int Hc, int Wc, int y, int x, int comp)
 {
     // comp 0: I, 1: D0, 2: D1 (see cmax_gather_kernel for the block / sign conventions)
     const int64_t npix = (int64_t)Hc * Wc;
-    float v = 0.f;
+    float v = (comp == 0 && planar) ? planar[(int64_t)y * Wc + x] : 0.f;
     for (int r = 0; r < replicas; ++r) {
         const float *base = acc + (int64_t)r * npix * kBlockFloats;
 #pragma unroll
@@ -537,7 +669,7 @@ __device__ __forceinline__ float gather_pixel(const float *acc, int replicas, in
     return v;
 }
 
-__global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel(const float *__restrict__ acc, int replicas, int Hc, int Wc,
+__global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel(const float *__restrict__ acc, const float *__restrict__ planar, int replicas, int Hc, int Wc,
                                                                               const BlurTaps taps, int do_blur, int want_grad,
                                                                               double mix_a, double mix_b, float *__restrict__ iwe_out,
                                                                               float *__restrict__ diwe_out, double *sums,
@@ -558,14 +690,14 @@ __global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel(con
     // 1. halo tile of the un-blurred IWE
     for (int j = tid; j < hh * hw; j += kTileY * kTileX) {
         const int ly = j / hw, lx = j - ly * hw;
-        tileI[j] = gather_pixel(acc, replicas, Hc, Wc, reflect_idx(y0 - r + ly, Hc), reflect_idx(x0 - r + lx, Wc), 0);
+        tileI[j] = gather_pixel(acc, planar, replicas, Hc, Wc, reflect_idx(y0 - r + ly, Hc), reflect_idx(x0 - r + lx, Wc), 0);
     }
     const int y = y0 + threadIdx.y, x = x0 + threadIdx.x;
     const bool inside = y < Hc && x < Wc;
     float vi = 0.f, d0 = 0.f, d1 = 0.f;
     if (inside) {
-        d0 = gather_pixel(acc, replicas, Hc, Wc, y, x, 1);
-        d1 = gather_pixel(acc, replicas, Hc, Wc, y, x, 2);
+        d0 = gather_pixel(acc, nullptr, replicas, Hc, Wc, y, x, 1);
+        d1 = gather_pixel(acc, nullptr, replicas, Hc, Wc, y, x, 2);
     }
     __syncthreads();
     if (inside) {
@@ -626,6 +758,7 @@ __global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel(con
 }
 
 struct CmaxWorkspace {
+    float *planar;              // on-chip path: planar IWE the CTAs' shared-memory images are bulk-reduced into
     float *acc, *I, *D0, *D1, *tmp, *G;
     double *bsums;              // [kMaxCandidates][8] sums of a batched evaluation
     unsigned *btickets;         // [kMaxCandidates]
@@ -652,6 +785,7 @@ static size_t carve(void *base, int Hs, int Ws, CmaxWorkspace *ws)
     unsigned *gmax = (unsigned *)take(sizeof(unsigned));
     double *sums = (double *)take(8 * sizeof(double));
     unsigned long long *oob = (unsigned long long *)take(sizeof(unsigned long long));
+    float *planar = (float *)take(((npix + 3) & ~(size_t)3) * sizeof(float));
     float *acc = (float *)take(npix * kBlockFloats * sizeof(float) * (kMaxCandidates > kMaxReplicas ? kMaxCandidates : kMaxReplicas));
     float *I = (float *)take(npix * sizeof(float));
     float *D0 = (float *)take(npix * sizeof(float));
@@ -661,7 +795,7 @@ static size_t carve(void *base, int Hs, int Ws, CmaxWorkspace *ws)
     double *w = (double *)take(npix * sizeof(double));
     double *wt = (double *)take(npix * sizeof(double));
     if (ws) {
-        ws->acc = acc; ws->I = I; ws->D0 = D0; ws->D1 = D1; ws->tmp = tmp; ws->G = G; ws->w = w; ws->wt = wt;
+        ws->planar = planar; ws->acc = acc; ws->I = I; ws->D0 = D0; ws->D1 = D1; ws->tmp = tmp; ws->G = G; ws->w = w; ws->wt = wt;
         ws->gsums = gsums; ws->gmax = gmax; ws->sums = sums; ws->oob = oob; ws->bsums = bsums; ws->btickets = btickets;
     }
     return off;
@@ -728,6 +862,17 @@ static int launch_tail(const CmaxWorkspace &ws, int Hc, int Wc, double sigma, un
     return EVK_OK;
 }
 
+// event count from which the on-chip IWE pays (EVK_CMAX_ONCHIP_MIN overrides; measured crossover)
+static int64_t onchip_min_events()
+{
+    static int64_t v = -1;
+    if (v < 0) {
+        const char *e = getenv("EVK_CMAX_ONCHIP_MIN");
+        v = (e && *e) ? atoll(e) : ((int64_t)4 << 20);
+    }
+    return v;
+}
+
 template <int WARP>
 static int run_cmax(CmaxArgs A, double sigma, unsigned flags, int objective, double obj_param, double *result,
                     float *iwe_out, float *diwe_out, void *workspace, size_t workspace_bytes, cudaStream_t st)
@@ -747,7 +892,17 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, int objective, dou
     A.replicas = R;
     A.acc = ws.acc;
     A.oob = ws.oob;
-    // counters (gsums, gmax, sums, oob) and the R accumulator replicas are contiguous: one memset
+    // on-chip IWE: worth its fixed cost (174 KB of shared memory initialised and bulk-reduced per CTA) for
+    // large event sets only; EVK_VARIANT_SMEM_TILE / EVK_VARIANT_VECTOR_RED force one or the other
+    const size_t onchip_smem = (((size_t)npix + 3) & ~(size_t)3) * sizeof(float);
+    const unsigned variant = variant_of(flags);
+    bool onchip = onchip_smem <= (size_t)200 * 1024 && A.n > 0 &&
+                  (variant == EVK_VARIANT_SMEM_TILE || (variant == EVK_VARIANT_AUTO && A.n >= onchip_min_events()));
+    if (variant == EVK_VARIANT_VECTOR_RED || variant == EVK_VARIANT_GLOBAL_RED) onchip = false;
+    A.planar = onchip ? ws.planar : nullptr;
+    const float *planar = A.planar;
+    if (onchip && !grad) { R = 1; A.replicas = 1; }   // the blocks only receive carries and slow-path taps
+    // counters (gsums, gmax, sums, oob), the planar image and the R accumulator replicas are contiguous: one memset
     EVK_CUDA(cudaMemsetAsync(ws.gsums, 0, (size_t)((char *)ws.acc - (char *)ws.gsums) + (size_t)R * npix * kBlockFloats * sizeof(float), st));
     if (WARP == WARP_FLOW_F32 && A.n > 0) {
         // the generic objectives' weight image (unused by the variance tail) holds the interleaved flow
@@ -755,7 +910,20 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, int objective, dou
         launch_flow_interleave(A.flow, (int64_t)Hs * Ws, reinterpret_cast<float2 *>(ws.w), st);
         A.flow_uv = reinterpret_cast<const float2 *>(ws.w);
     }
-    if (A.n > 0) {
+    if (onchip) {
+        ProfScope prof(st);
+        prof_count(1);
+        int64_t need_ctas = (A.n + kOnchipThreads * 8 - 1) / (kOnchipThreads * 8);
+        const int g = (int)(need_ctas < num_sms() ? need_ctas : num_sms());
+        if (grad) {
+            EVK_CUDA(cudaFuncSetAttribute(cmax_onchip_kernel<WARP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onchip_smem));
+            cmax_onchip_kernel<WARP, true><<<g, kOnchipThreads, onchip_smem, st>>>(A);
+        } else {
+            EVK_CUDA(cudaFuncSetAttribute(cmax_onchip_kernel<WARP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onchip_smem));
+            cmax_onchip_kernel<WARP, false><<<g, kOnchipThreads, onchip_smem, st>>>(A);
+        }
+        EVK_CUDA(cudaGetLastError());
+    } else if (A.n > 0) {
         ProfScope prof(st);
         prof_count(1);
         if (grad) cmax_scatter_kernel<WARP, true><<<grid_for(cmax_scatter_kernel<WARP, true>, 256, A.n, 256 * 4), 256, 0, st>>>(A);
@@ -773,13 +941,13 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, int objective, dou
         }
         prof_count(1);
         dim3 tgrid((A.Wc + kTileX - 1) / kTileX, (A.Hc + kTileY - 1) / kTileY), tblock(kTileX, kTileY);
-        cmax_fused_var_tail_kernel<<<tgrid, tblock, 0, st>>>(ws.acc, R, A.Hc, A.Wc, taps, do_blur, grad ? 1 : 0, mix_a, mix_b, iwe_out,
+        cmax_fused_var_tail_kernel<<<tgrid, tblock, 0, st>>>(ws.acc, planar, R, A.Hc, A.Wc, taps, do_blur, grad ? 1 : 0, mix_a, mix_b, iwe_out,
                                                                diwe_out, ws.sums, ws.gmax, ws.oob, result);
         EVK_CUDA(cudaGetLastError());
         return EVK_OK;
     }
     prof_count(1);
-    cmax_gather_kernel<<<(npix + 255) / 256, 256, 0, st>>>(ws.acc, R, A.Hc, A.Wc, ws.I, ws.D0, ws.D1, iwe_out, diwe_out, ws.sums);
+    cmax_gather_kernel<<<(npix + 255) / 256, 256, 0, st>>>(ws.acc, planar, R, A.Hc, A.Wc, ws.I, ws.D0, ws.D1, iwe_out, diwe_out, ws.sums);
     return launch_tail(ws, A.Hc, A.Wc, sigma, flags, objective, obj_param, grad, result, st);
 }
 
@@ -963,7 +1131,7 @@ int evk_cmax_linvel_objective_batch_f64(const double *x, const double *y, const 
         }
         prof_count(1);
         dim3 tgrid((A.Wc + kTileX - 1) / kTileX, (A.Hc + kTileY - 1) / kTileY, n_params), tblock(kTileX, kTileY);
-        cmax_fused_var_tail_kernel<<<tgrid, tblock, 0, st>>>(ws.acc, 1, A.Hc, A.Wc, taps, do_blur, grad ? 1 : 0, mix_a, mix_b, nullptr,
+        cmax_fused_var_tail_kernel<<<tgrid, tblock, 0, st>>>(ws.acc, nullptr, 1, A.Hc, A.Wc, taps, do_blur, grad ? 1 : 0, mix_a, mix_b, nullptr,
                                                                nullptr, ws.bsums, ws.btickets, ws.oob, results);
         EVK_CUDA(cudaGetLastError());
         return EVK_OK;
@@ -972,7 +1140,7 @@ int evk_cmax_linvel_objective_batch_f64(const double *x, const double *y, const 
         // per-candidate image-space tail on the shared scratch images (stream-ordered)
         EVK_CUDA(cudaMemsetAsync(ws.gsums, 0, (size_t)((char *)ws.oob - (char *)ws.gsums), st));   // keep the oob counter
         prof_count(1);
-        cmax_gather_kernel<<<(npix + 255) / 256, 256, 0, st>>>(ws.acc + (size_t)k * npix * kBlockFloats, 1, A.Hc, A.Wc, ws.I, ws.D0,
+        cmax_gather_kernel<<<(npix + 255) / 256, 256, 0, st>>>(ws.acc + (size_t)k * npix * kBlockFloats, nullptr, 1, A.Hc, A.Wc, ws.I, ws.D0,
                                                                 ws.D1, nullptr, nullptr, ws.sums);
         int rc = launch_tail(ws, A.Hc, A.Wc, sigma, flags, objective, obj_param, grad, results + 12 * k, st);
         if (rc) return rc;

@@ -1,8 +1,11 @@
-"""Loader for the UNMODIFIED reference (TimoStoff/event_utils) -- TEST INFRASTRUCTURE ONLY.
+"""Loader for the UNMODIFIED reference (TimoStoff/event_utils) -- TEST / BASELINE INFRASTRUCTURE ONLY.
 
-Only usable where ``/root/reference`` exists (the build container; never the GPU box).
-It is used by ``tests/golden/make_golden.py`` to generate the committed golden vectors and
-by the ``not gpu`` tests that pin the oracle restatement against the real reference.
+Where the reference lives: ``$EVK_REFERENCE_ROOT``, else ``/root/reference`` (the build container), else the
+unmodified copy of its ``lib/`` package that ``__graft_entry__.build()`` places in the git-ignored
+``baseline/_ref/`` (which travels to the GPU box with the gpurun snapshot; /root/reference does not).
+It is used by ``tests/golden/make_golden.py`` to generate the committed golden vectors, by the ``not gpu``
+tests that pin the oracle restatement against the real reference, by ``bench.py --impl reference`` /
+``cpu_baseline`` (the reference's own functions timed on the host cores) and by the module-swap tests.
 
 Two of the hot-path files do not parse as shipped:
   * lib/contrast_max/warps.py:7-10  class docstring at column 0, :81 stray text, :3 bogus import
@@ -16,7 +19,19 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("EVK_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    cands = [os.environ.get("EVK_REFERENCE_ROOT"), "/root/reference",
+             os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "lib", "representations")):
+            return c
+    return cands[0] or cands[1]
+
+
+REF_ROOT = _find_root()
 
 
 def available():

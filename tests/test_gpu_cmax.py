@@ -478,6 +478,60 @@ def test_paired_and_single_lane_kernels_agree(oracle):
     assert np.abs(out[0][:3] - out[1][:3]).max() <= 1e-6 * np.abs(out[1][:3]).max()
 
 
+@pytest.mark.parametrize("pol", ["pm1", "real"])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_onchip_event_pass_vs_oracle(oracle, pol, precision):
+    """cmax_onchip_kernel (IWE in shared memory as fixed point + TMA bulk reduction) forced at a size the
+    oracle handles in a second: f, g and both images against the oracle.  pol="real" draws N(0,1)
+    polarities, so a third of the events (|p| > 1) take the kernel's global-f32 slow path."""
+    from event_utils_b200.contrast_max import objectives as O
+    from event_utils_b200.contrast_max.warps import linvel_warp
+    x, y, t, p = make_events(41, 600001, 180, 240, dtype=np.float64, pol=pol)
+    O.event_pass, O.precision = "onchip", precision
+    tol = 1e-5 if precision == "f64" else 1e-4
+    try:
+        obj, warp = O.variance_objective(), linvel_warp()
+        for params in [(30.0, -20.0), (-400.0, 900.0), (0.0, 0.0)]:
+            f = obj.evaluate_function(params, x, y, t, p, warp, (180, 240), 1.0)
+            g = obj.evaluate_gradient(params, x, y, t, p, warp, (180, 240), 1.0)
+            fo, go = oracle.cmax_variance(params, x, y, t, p, blur_sigma=1.0)
+            iwe, d = oracle.iwe_linvel(params, x, y, t, p, (180, 240), True)
+            assert abs(f - fo) <= tol * abs(fo), (params, f, fo)
+            assert np.abs(g - go).max() <= tol * grad_scale(iwe, d), (params, g, go)
+            img, dimg = O.get_iwe(params, x, y, t, p, warp, (180, 240), compute_gradient=True)
+            assert_close_to_max(img, iwe, tol)
+            assert_close_to_max(dimg, d, tol)
+    finally:
+        O.event_pass, O.precision = None, "f64"
+
+
+def test_onchip_cells_carry_exactly(oracle):
+    """3 M unit events on ONE sub-pixel position: every CTA's shared-memory cell wraps its 32 bits several times
+    (2^22 fixed point -> a carry every 512 units) and the carries go to the global accumulator.  The sums are
+    exact integers in f32, so the image must be exactly n * tap weight."""
+    import torch
+    from event_utils_b200 import _lib
+    L = _lib.lib()
+    n = 3_000_000
+    X = torch.full((n,), 10.25, dtype=torch.float64, device="cuda")
+    Y = torch.full((n,), 20.5, dtype=torch.float64, device="cuda")
+    T = torch.linspace(0, 0.01, n, dtype=torch.float64, device="cuda")
+    ws = torch.empty(L.evk_cmax_workspace_bytes(180, 240), dtype=torch.uint8, device="cuda")
+    res = torch.empty(12, dtype=torch.float64, device="cuda")
+    iwe = torch.empty((181, 241), device="cuda")
+    for sign in (1.0, -1.0):
+        P = torch.full((n,), sign, dtype=torch.float64, device="cuda")
+        _lib.check(L.evk_cmax_linvel_variance_f64(X.data_ptr(), Y.data_ptr(), T.data_ptr(), P.data_ptr(), n, 1.0, 0.0, 0.0, 0.01,
+                                                  180, 240, 180, 240, 0.0, _lib.VARIANT_SMEM_TILE, res.data_ptr(), iwe.data_ptr(),
+                                                  None, ws.data_ptr(), ws.numel(), None))
+        torch.cuda.synchronize()
+        img = iwe.cpu().numpy()
+        expect = np.zeros((181, 241), np.float32)
+        expect[20, 10], expect[20, 11], expect[21, 10], expect[21, 11] = (sign * n * w for w in (0.375, 0.125, 0.375, 0.125))
+        assert np.array_equal(img, expect), (img[20:22, 10:12], expect[20:22, 10:12])
+        assert res[3].item() == sign * n and res[4].item() == 0
+
+
 def test_full_size_properties():
     """BASELINE config 3 size (50 M events): properties that do not need the CPU oracle."""
     import torch
