@@ -28,6 +28,7 @@ VARIANT_GLOBAL_RED = 1 << 8
 VARIANT_VECTOR_RED = 2 << 8
 VARIANT_SMEM_TILE = 3 << 8
 VARIANT_WARP_AGG = 4 << 8
+VARIANT_ROUTED = 5 << 8
 TS_REVERSE = 0x80
 TS_RAW = 0x1000
 CMAX_WANT_GRAD = 0x10

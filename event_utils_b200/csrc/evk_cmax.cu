@@ -73,6 +73,7 @@ struct CmaxArgs {
     int abs_polarity;
     int replicas;
     float *acc;  // [R][Hc*Wc][8]
+    int vec16;      // on-chip path: all four event arrays are 16-byte aligned
     float *planar;  // on-chip path: planar f32 image [npix padded to 4] the CTAs' shared-memory images are reduced into
     unsigned long long *oob;
 };
@@ -165,19 +166,35 @@ constexpr float kFixScale = (float)(1 << kFixBits);
 constexpr float kFixCarry = (float)(1u << (32 - kFixBits));   // value of one 2^32 wrap of a cell
 constexpr unsigned kFixBias = 0x80000000u;
 
-__device__ __forceinline__ void onchip_tap(unsigned *simg, float *acc_tl, int pix, float v)
+__device__ __forceinline__ unsigned atoms_add_ret(unsigned *cell, unsigned v)
 {
-    const int q = __float2int_rn(__fmul_rn(v, kFixScale));      // |v| <= 1 -> |q| <= 2^22
-    if (q == 0) return;
     unsigned old;
-    const unsigned saddr = (unsigned)__cvta_generic_to_shared(simg + pix);
-    asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"((unsigned)q));
-    // did THIS add wrap the 32-bit cell?  The wrap is carried to the global accumulator (TL slot of the
-    // pixel's own block, which the fold adds to the pixel), so the total is exact for any event count.
-    if (q > 0) {
-        if (old + (unsigned)q < old) red_add(acc_tl + (int64_t)pix * kBlockFloats, kFixCarry);
-    } else {
-        if (old < (unsigned)(-q)) red_add(acc_tl + (int64_t)pix * kBlockFloats, -kFixCarry);
+    asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(cell)), "r"(v));
+    return old;
+}
+
+// Did adding the signed increment q to the biased cell (old -> old + q mod 2^32) wrap the 32 bits?  A wrap flips the
+// top bit TOWARDS the sign of q (carry: 1 -> 0 with q >= 0; borrow: 0 -> 1 with q < 0); the other top-bit flip is the
+// true value crossing zero.  Bit 31 of the result is the answer; q == 0 never wraps.
+__device__ __forceinline__ unsigned wrap_bit(unsigned old, unsigned q) { const unsigned nw = old + q; return (old ^ nw) & ~(nw ^ q); }
+
+// The four taps of one event: four independent native shared-memory atomics, ONE rarely taken branch.
+// A wrap of a cell is carried to the global accumulator (TL slot of the pixel's own block, which the fold
+// adds to the pixel), so the total is exact integer arithmetic for any event count.
+__device__ __forceinline__ void onchip_taps(unsigned *simg, float *acc, int p00, int p01, int p10, int p11, float4 ti)
+{
+    const unsigned q0 = (unsigned)__float2int_rn(__fmul_rn(ti.x, kFixScale));   // |tap| <= 1 -> |q| <= 2^22
+    const unsigned q1 = (unsigned)__float2int_rn(__fmul_rn(ti.y, kFixScale));
+    const unsigned q2 = (unsigned)__float2int_rn(__fmul_rn(ti.z, kFixScale));
+    const unsigned q3 = (unsigned)__float2int_rn(__fmul_rn(ti.w, kFixScale));
+    const unsigned o0 = atoms_add_ret(simg + p00, q0), o1 = atoms_add_ret(simg + p01, q1);
+    const unsigned o2 = atoms_add_ret(simg + p10, q2), o3 = atoms_add_ret(simg + p11, q3);
+    const unsigned w0 = wrap_bit(o0, q0), w1 = wrap_bit(o1, q1), w2 = wrap_bit(o2, q2), w3 = wrap_bit(o3, q3);
+    if ((w0 | w1 | w2 | w3) >> 31) {
+        if (w0 >> 31) red_add(acc + (int64_t)p00 * kBlockFloats, (int)q0 >= 0 ? kFixCarry : -kFixCarry);
+        if (w1 >> 31) red_add(acc + (int64_t)p01 * kBlockFloats, (int)q1 >= 0 ? kFixCarry : -kFixCarry);
+        if (w2 >> 31) red_add(acc + (int64_t)p10 * kBlockFloats, (int)q2 >= 0 ? kFixCarry : -kFixCarry);
+        if (w3 >> 31) red_add(acc + (int64_t)p11 * kBlockFloats, (int)q3 >= 0 ? kFixCarry : -kFixCarry);
     }
 }
 
@@ -188,10 +205,8 @@ __device__ __forceinline__ void splat_onchip(const CmaxArgs &A, float *acc, unsi
     Taps T;
     if (!splat_taps<GRAD>(A, xf, yf, w, a, clip, oob, T)) return;
     if (fabsf(T.wm) <= 1.0f) {      // false for NaN / inf as well
-        onchip_tap(simg, acc, T.y0 * A.Wc + T.x0, T.ti.x);
-        onchip_tap(simg, acc, T.y0 * A.Wc + T.x1, T.ti.y);
-        onchip_tap(simg, acc, T.y1 * A.Wc + T.x0, T.ti.z);
-        onchip_tap(simg, acc, T.y1 * A.Wc + T.x1, T.ti.w);
+        const int r0 = T.y0 * A.Wc, r1 = T.y1 * A.Wc;
+        onchip_taps(simg, acc, r0 + T.x0, r0 + T.x1, r1 + T.x0, r1 + T.x1, T.ti);
         if (GRAD) emit_global<false, true>(A, acc, T);
     } else {
         emit_global<true, GRAD>(A, acc, T);
@@ -217,6 +232,17 @@ __device__ __forceinline__ Event<WARP> load_event(const CmaxArgs &A, int64_t i)
     e.t = ld_stream((const T *)A.t + i);
     e.p = ld_stream((const T *)A.p + i);
     return e;
+}
+
+__device__ __forceinline__ void ld_vec16(const float *p, float (&v)[4])
+{
+    const float4 q = ld_stream4(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+__device__ __forceinline__ void ld_vec16(const double *p, double (&v)[2])
+{
+    const double2 q = ld_stream2(p);
+    v[0] = q.x; v[1] = q.y;
 }
 
 template <int WARP, bool GRAD, bool ONCHIP = false>
@@ -320,15 +346,41 @@ __global__ void __launch_bounds__(kOnchipThreads, 1) cmax_onchip_kernel(const Cm
     float *acc = A.acc + (int64_t)(blockIdx.x % A.replicas) * A.Hc * A.Wc * kBlockFloats;
     const int64_t stride = (int64_t)gridDim.x * kOnchipThreads;
     int64_t i = (int64_t)blockIdx.x * kOnchipThreads + threadIdx.x;
-    constexpr int kB = (WARP == WARP_LINVEL_F64) ? 2 : 4;   // loads in flight per thread (64-register budget at 1024 threads)
-    for (; i + (kB - 1) * stride < A.n; i += kB * stride) {
-        Event<WARP> ev[kB];
+    if (A.vec16) {
+        // 16-byte loads: 4 f32 events / 2 f64 events per vector, two vectors of every array in flight per thread
+        using T = typename EvT<WARP>::type;
+        constexpr int EPV = 16 / (int)sizeof(T);
+        const int64_t nv = A.n / EPV;
+        const T *px = (const T *)A.x, *py = (const T *)A.y, *pt = (const T *)A.t, *pp = (const T *)A.p;
+        for (int64_t v = i; v < nv; v += 2 * stride) {
+            const bool two = v + stride < nv;
+            const int64_t v2 = two ? v + stride : v;
+            T ex[2][EPV], ey[2][EPV], et[2][EPV], ep[2][EPV];
+            ld_vec16(px + v * EPV, ex[0]); ld_vec16(py + v * EPV, ey[0]); ld_vec16(pt + v * EPV, et[0]); ld_vec16(pp + v * EPV, ep[0]);
+            ld_vec16(px + v2 * EPV, ex[1]); ld_vec16(py + v2 * EPV, ey[1]); ld_vec16(pt + v2 * EPV, et[1]); ld_vec16(pp + v2 * EPV, ep[1]);
 #pragma unroll
-        for (int k = 0; k < kB; ++k) ev[k] = load_event<WARP>(A, i + k * stride);
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !two) break;
 #pragma unroll
-        for (int k = 0; k < kB; ++k) cmax_event<WARP, GRAD, true>(A, acc, ev[k], oob, A.vx, A.vy, simg);
+                for (int k = 0; k < EPV; ++k) {
+                    Event<WARP> e;
+                    e.x = ex[h][k]; e.y = ey[h][k]; e.t = et[h][k]; e.p = ep[h][k];
+                    cmax_event<WARP, GRAD, true>(A, acc, e, oob, A.vx, A.vy, simg);
+                }
+            }
+        }
+        for (int64_t j = nv * EPV + i; j < A.n; j += stride) cmax_event<WARP, GRAD, true>(A, acc, load_event<WARP>(A, j), oob, A.vx, A.vy, simg);
+    } else {
+        constexpr int kB = (WARP == WARP_LINVEL_F64) ? 2 : 4;   // loads in flight per thread (64-register budget at 1024 threads)
+        for (; i + (kB - 1) * stride < A.n; i += kB * stride) {
+            Event<WARP> ev[kB];
+#pragma unroll
+            for (int k = 0; k < kB; ++k) ev[k] = load_event<WARP>(A, i + k * stride);
+#pragma unroll
+            for (int k = 0; k < kB; ++k) cmax_event<WARP, GRAD, true>(A, acc, ev[k], oob, A.vx, A.vy, simg);
+        }
+        for (; i < A.n; i += stride) cmax_event<WARP, GRAD, true>(A, acc, load_event<WARP>(A, i), oob, A.vx, A.vy, simg);
     }
-    for (; i < A.n; i += stride) cmax_event<WARP, GRAD, true>(A, acc, load_event<WARP>(A, i), oob, A.vx, A.vy, simg);
     flush_oob(A.oob, oob);
     __syncthreads();
     // fixed point -> f32 in place (an int32 sum rounds to f32 once, like a float accumulator's final value)
@@ -900,6 +952,7 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, int objective, dou
                   (variant == EVK_VARIANT_SMEM_TILE || (variant == EVK_VARIANT_AUTO && A.n >= onchip_min_events()));
     if (variant == EVK_VARIANT_VECTOR_RED || variant == EVK_VARIANT_GLOBAL_RED) onchip = false;
     A.planar = onchip ? ws.planar : nullptr;
+    A.vec16 = ((((uintptr_t)A.x | (uintptr_t)A.y | (uintptr_t)A.t | (uintptr_t)A.p) & 15) == 0) ? 1 : 0;
     const float *planar = A.planar;
     if (onchip && !grad) { R = 1; A.replicas = 1; }   // the blocks only receive carries and slow-path taps
     // counters (gsums, gmax, sums, oob), the planar image and the R accumulator replicas are contiguous: one memset

@@ -44,6 +44,13 @@ struct VoxelArgs {
 
 enum { SINK_SCALAR = 0, SINK_QUAD = 1, SINK_QUAD_HOT = 2 };
 
+// evk_voxel_routed.cu: output tiles in shared memory, events routed to the owning SM through L2-resident rings
+size_t voxel_routed_workspace_bytes(int B, int H, int W);
+bool voxel_routed_supported(int B, int H, int W);
+int launch_voxel_routed(const float *x, const float *y, const float *t, const float *p, int64_t n, int64_t head, float t0, float dt,
+                        int B, int H, int W, int auto_span, float *out, void *workspace, size_t workspace_bytes,
+                        unsigned long long *oob, cudaStream_t st);
+
 // Per-CTA write-combining cache in front of the vector reductions (SINK_QUAD_HOT): a direct-mapped
 // {quad index -> float4 partial sum} table in shared memory, same idea as evk_hot.cu.  Real sensors
 // have hot pixels (the reference ships remove_hot_pixels for them, event_util.py:166-187); every
@@ -547,6 +554,20 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
         A.hot_force = 1;
     }
     const bool no_fold = (flags & EVK_NO_FOLD) != 0;
+    if (variant == EVK_VARIANT_ROUTED &&
+        (bil || A.negpos || no_fold || layout != LAYOUT_SOA4 || !voxel_routed_supported(A.B, A.H, A.W) ||
+         workspace == nullptr || workspace_bytes < voxel_routed_workspace_bytes(A.B, A.H, A.W))) {
+        // the routed kernel covers the plain (nearest, combined) grid on f32 SoA arrays with a common alignment whose
+        // B*H*W/SMs cells fit in shared memory; everything else takes the automatic choice
+        variant = (A.n >= (int64_t)1 << 20 && workspace != nullptr) ? EVK_VARIANT_VECTOR_RED : EVK_VARIANT_GLOBAL_RED;
+        hot = variant == EVK_VARIANT_VECTOR_RED && !bil;
+    }
+    if (variant == EVK_VARIANT_ROUTED) {
+        if (!accum) EVK_CUDA(cudaMemsetAsync(A.out, 0, (size_t)npix * A.B * sizeof(float), st));
+        if (A.n == 0) return EVK_OK;
+        return launch_voxel_routed(A.x, A.y, A.t, A.p, A.n, A.head, A.t0, A.dt, A.B, A.H, A.W, A.auto_span, A.out, workspace,
+                                   workspace_bytes, A.oob, st);
+    }
     if (no_fold) {
         // the caller folds (and reduces across GPUs) itself: the sums stay in the quad workspace
         if (bil || A.negpos || workspace == nullptr) { set_error("evk_voxel: EVK_NO_FOLD needs a workspace and the plain (nearest, combined) grid"); return EVK_E_UNSUPPORTED; }
@@ -632,7 +653,13 @@ size_t evk_voxel_workspace_bytes(int B, int H, int W, unsigned flags)
 {
     if (B < 1 || H < 1 || W < 1) return 0;
     if (flags & EVK_BILINEAR) return (size_t)B * H * W * 4 * sizeof(float);   // 2x2 blocks per bin
-    return (size_t)H * W * evk::quads_for_bins(B) * 4 * sizeof(float);      // temporal quads per pixel
+    size_t need = (size_t)H * W * evk::quads_for_bins(B) * 4 * sizeof(float);      // temporal quads per pixel
+    const unsigned v = evk::variant_of(flags);
+    if ((v == EVK_VARIANT_AUTO || v == EVK_VARIANT_ROUTED) && evk::voxel_routed_supported(B, H, W)) {
+        const size_t r = evk::voxel_routed_workspace_bytes(B, H, W);   // the routed kernel's rings
+        if (r > need) need = r;
+    }
+    return need;
 }
 
 int evk_voxel_f32(const float *x, const float *y, const float *t, const float *p, int64_t n, float t0,

@@ -10,7 +10,7 @@ def variant_flag():
     if v is None:
         return _lib.VARIANT_AUTO
     return {"global_red": _lib.VARIANT_GLOBAL_RED, "vector_red": _lib.VARIANT_VECTOR_RED,
-            "warp_agg": _lib.VARIANT_WARP_AGG, "smem_cache": _lib.VARIANT_SMEM_TILE, "auto": _lib.VARIANT_AUTO}[v]
+            "warp_agg": _lib.VARIANT_WARP_AGG, "routed": _lib.VARIANT_ROUTED, "smem_cache": _lib.VARIANT_SMEM_TILE, "auto": _lib.VARIANT_AUTO}[v]
 
 
 def as_tensor(a):

@@ -10,7 +10,7 @@ from conftest import assert_close_to_max, golden, make_events
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = ["global_red", "vector_red", "smem_cache", None]
+VARIANTS = ["global_red", "vector_red", "smem_cache", "routed", None]
 
 
 @pytest.fixture(autouse=True)
