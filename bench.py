@@ -11,7 +11,9 @@ A "step" is one voxel-grid build over one batch of synthetic events:
 `value` is whole-job Mevents/s with the events resident in HBM, timed with CUDA events over
 exactly K steps, max over ranks.  `e2e` is the same metric through the public python API with
 pinned HOST tensors in and a host tensor out (H2D + D2H inside the timed region).
-`--impl reference` times the CPU port of the reference (oracle/ref_port.py) on the host cores.
+`--impl reference` times the reference's OWN events_to_voxel_torch (the unmodified lib/ package that
+__graft_entry__.build() copies to the git-ignored baseline/_ref/, loaded through oracle/ref_loader.py) on the
+host cores; where that copy is missing it falls back to the library-op port (oracle/ref_port.py) and says so.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -178,27 +180,46 @@ def thread_candidates():
     return sorted(set(c for c in (1, 4, 8, 16, 32, 64, cores) if c <= cores))
 
 
-def time_cpu_port(n, repeats):
+def reference_functions():
+    """(kind, voxel_torch(xs,ys,ts,ps) -> grid, voxel_numpy(xs_int,ys_int,ts,ps) -> grid): the reference's own
+    events_to_voxel_torch / events_to_voxel (kind "reference", the unmodified lib/ copy in baseline/_ref/), or the
+    library-op port (kind "port") where that copy is not present."""
+    try:
+        from oracle import ref_loader
+        if ref_loader.available():
+            ref = ref_loader.load()
+            return ("reference",
+                    lambda xs, ys, ts, ps: ref.voxel_grid.events_to_voxel_torch(xs, ys, ts, ps, B, sensor_size=(H, W)),
+                    lambda xs, ys, ts, ps: ref.voxel_grid.events_to_voxel(xs, ys, ts, ps, B, sensor_size=(H, W)),
+                    ref_loader.REF_ROOT)
+    except Exception as exc:       # a broken copy must not cost the line: fall back and say so
+        print("bench: reference package unusable (%r), timing the library-op port" % (exc,), file=sys.stderr)
     from oracle import ref_port
+    return ("port", lambda xs, ys, ts, ps: ref_port.voxel_torch_cpu(xs, ys, ts, ps, B, (H, W)),
+            lambda xs, ys, ts, ps: ref_port.voxel_numpy(xs, ys, ts, ps, B, (H, W)), "oracle/ref_port.py")
+
+
+def time_cpu_port(n, repeats):
+    kind, voxel_torch, voxel_numpy, where = reference_functions()
     cores = os.cpu_count() or 1
     x, y, t, p = cpu_sample_events(n)
     xt, yt, tt, pt = (torch.from_numpy(a) for a in (x, y, t, p))
     # calibrate on the full sample: the best thread count at 0.5 M events is not the best at 5 M
-    threads = best_torch_threads(lambda: ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W)), thread_candidates())
+    threads = best_torch_threads(lambda: voxel_torch(xt, yt, tt, pt), thread_candidates())
     best_t = float("inf")
     for _ in range(repeats):
         s = time.perf_counter()
-        ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W))
+        voxel_torch(xt, yt, tt, pt)
         best_t = min(best_t, time.perf_counter() - s)
     xi, yi = x.astype(np.int64), y.astype(np.int64)
     t64, p64 = t.astype(np.float64), p.astype(np.float64)
     best_n = float("inf")
     for _ in range(max(1, repeats - 1)):
         s = time.perf_counter()
-        ref_port.voxel_numpy(xi, yi, t64, p64, B, (H, W))
+        voxel_numpy(xi, yi, t64, p64)
         best_n = min(best_n, time.perf_counter() - s)
     return {"torch_cpu_mevs": n / best_t / 1e6, "numpy_mevs": n / best_n / 1e6, "cores": cores,
-            "torch_threads": threads}
+            "torch_threads": threads, "kind": kind, "where": where}
 
 
 def cpu_model():
@@ -213,32 +234,47 @@ def cpu_model():
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU path (library-op port, see oracle/ref_port.py)."""
+    """--impl reference: the reference's own CPU path on the host cores (see reference_functions)."""
     if rank != 0:
         return
-    from oracle import ref_port
+    kind, voxel_torch, _, where = reference_functions()
     cores = os.cpu_count() or 1
-    n = CPU_SAMPLE
-    x, y, t, p = cpu_sample_events(n)
-    xt, yt, tt, pt = (torch.from_numpy(a) for a in (x, y, t, p))
-    best_torch_threads(lambda: ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W)), thread_candidates())
+    # thread count: the reference's index_put_(accumulate=True) gets SLOWER with many threads; give it its best
+    xs, ys, ts, ps = (torch.from_numpy(a) for a in cpu_sample_events(CPU_SAMPLE))
+    best_torch_threads(lambda: voxel_torch(xs, ys, ts, ps), thread_candidates())
+    s = time.perf_counter()
+    voxel_torch(xs, ys, ts, ps)
+    t_sample = time.perf_counter() - s
+    # the whole 50 M-event workload per step if the run then ends within a few minutes, else a bounded sample of it
+    budget_s = float(os.environ.get("EVK_BENCH_REF_BUDGET_S", 150.0))
+    per_step = budget_s / max(1, args.steps + args.warmup)
+    n = N_PER_GPU if t_sample * (N_PER_GPU / CPU_SAMPLE) <= per_step else int(CPU_SAMPLE * per_step / t_sample)
+    n = max(1_000_000, min(N_PER_GPU, n // 1_000_000 * 1_000_000))
+    if n != CPU_SAMPLE:
+        del xs, ys, ts, ps
+        xs, ys, ts, ps = (torch.from_numpy(a) for a in cpu_sample_events(n))
     for _ in range(args.warmup):
-        ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W))
+        voxel_torch(xs, ys, ts, ps)
     s = time.perf_counter()
     for _ in range(args.steps):
-        ref_port.voxel_torch_cpu(xt, yt, tt, pt, B, (H, W))
+        voxel_torch(xs, ys, ts, ps)
     el = time.perf_counter() - s
     value = n * args.steps / el / 1e6
-    sample = ("events_to_voxel_torch library-op port (torch CPU f32, %d threads = the fastest of %s on this host) "
-              "on a %d-event sample of the 50M-event workload per step; the reference itself is pure Python and "
-              "cannot travel to the box" % (torch.get_num_threads(), thread_candidates(), n))
+    what = ("the reference's own events_to_voxel_torch (unmodified lib/ package from %s)" % where if kind == "reference" else
+            "events_to_voxel_torch library-op port (oracle/ref_port.py; the reference package is not present here)")
+    sample = ("%s, torch CPU f32, %d threads = the fastest of %s on this host; %s per step" % (
+        what, torch.get_num_threads(), thread_candidates(),
+        "the FULL 50M-event workload" if n == N_PER_GPU else
+        "a %d-event sample of the 50M-event workload (bounded so that %d steps end within %.0f s)" % (n, args.steps + args.warmup, budget_s)))
+    cfg = workload_config(args.gpus, "peer" if args.gpus > 1 else None)
+    cfg["reference_events_per_step"] = n
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mevents/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, "peer" if args.gpus > 1 else None),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "Mevents/s", "cores": torch.get_num_threads(), "host_cores": cores,
-                         "kind": "port", "sample": sample, "cpu": cpu_model()},
+                         "kind": kind, "sample": sample, "cpu": cpu_model()},
         "e2e": {"value": value, "unit": "Mevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -256,6 +292,9 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # bind the rank to its GPU's NUMA node before any pinned buffer exists (the e2e arm streams 800 MB per step per GPU)
+    from event_utils_b200.parallel import bind_to_gpu_numa_node
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if os.environ.get("EVK_BENCH_NUMA_BIND", "1") == "1" else None
     # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner) write to
     # file descriptor 1 directly, so point it at stderr until the line is printed
     sys.stdout.flush()
@@ -361,16 +400,18 @@ def run_ours(args, rank, local_rank, world):
         def e2e_step():
             return events_to_voxel_torch(hx, hy, ht, hp, B, sensor_size=(H, W))
     else:
-        pipe = _lib.pipeline()
-        gdev = torch.empty((B, H, W), dtype=torch.float32, device=device)
+        # the product path end to end: pinned host shard -> H2D -> scatter into the symmetric-memory quad workspace ->
+        # fused fold + all-reduce over NVLink peer memory (or the NCCL stream where symmetric memory is unavailable) ->
+        # D2H of the reduced grid on every rank
         ghost = torch.empty((B, H, W), dtype=torch.float32, pin_memory=True)
-        bad = ctypes.c_ulonglong(0)
+        e2e_pipe = pipe_mg
 
         def e2e_step():
-            _lib.check(L.evk_voxel_host_f32(pipe, hx.data_ptr(), hy.data_ptr(), ht.data_ptr(), hp.data_ptr(), n,
-                                            t0, dt, B, H, W, 0, gdev.data_ptr(), ctypes.byref(bad)))
-            dist.all_reduce(gdev, op=dist.ReduceOp.SUM)
-            ghost.copy_(gdev)
+            x.copy_(hx, non_blocking=True); y.copy_(hy, non_blocking=True)
+            t.copy_(ht, non_blocking=True); p.copy_(hp, non_blocking=True)
+            grid, done = e2e_pipe.submit(x, y, t, p, t0, dt)
+            torch.cuda.current_stream().wait_event(done)
+            ghost.copy_(grid, non_blocking=True)
             torch.cuda.synchronize()
             return ghost
     e2e_steps = max(3, min(args.steps, 10))
@@ -397,6 +438,21 @@ def run_ours(args, rank, local_rank, world):
         e2e_s = float(el.item())
     assert abs(float(res.double().sum()) - expect) <= 1e-6 * n * world + 4.0
     e2e_value = n * world * e2e_steps / e2e_s / 1e6
+    e2e_pageable = None
+    if world == 1:
+        # what a user of the drop-in sees: the reference's callers hand over ORDINARY (pageable) CPU tensors / numpy
+        # arrays at every call (events_cmax.py:341, base_dataset.py:446-453)
+        qx, qy, qt, qp = (h.clone() for h in (hx, hy, ht, hp))          # clone() of a pinned tensor is pageable
+        assert not qx.is_pinned()
+        events_to_voxel_torch(qx, qy, qt, qp, B, sensor_size=(H, W))
+        sq = time.perf_counter()
+        for _ in range(3):
+            resq = events_to_voxel_torch(qx, qy, qt, qp, B, sensor_size=(H, W))
+        tq = (time.perf_counter() - sq) / 3
+        assert abs(float(resq.double().sum()) - expect) <= 1e-6 * n + 4.0
+        e2e_pageable = {"value": n / tq / 1e6, "unit": "Mevents/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 4 * B * H * W,
+                        "api": "events_to_voxel_torch(ordinary pageable CPU tensors) -> CPU tensor", "steps": 3}
+        del qx, qy, qt, qp
     del hx, hy, ht, hp
     e2e_packed = None
     if world == 1:
@@ -424,10 +480,11 @@ def run_ours(args, rank, local_rank, world):
         cpu_t = time_cpu_port(CPU_SAMPLE, repeats=3)
         best = max(cpu_t["torch_cpu_mevs"], cpu_t["numpy_mevs"])
         used = cpu_t["torch_threads"] if cpu_t["torch_cpu_mevs"] >= cpu_t["numpy_mevs"] else 1
-        cpu = {"value": best, "unit": "Mevents/s", "cores": used, "host_cores": cpu_t["cores"], "kind": "port",
-               "sample": "%d-event sample of the workload, best of 3; faster of torch-CPU events_to_voxel_torch port "
-                         "(%.1f Mev/s, %d threads) and numpy events_to_voxel port (%.1f Mev/s, 1 thread)"
-                         % (CPU_SAMPLE, cpu_t["torch_cpu_mevs"], cpu_t["torch_threads"], cpu_t["numpy_mevs"]),
+        cpu = {"value": best, "unit": "Mevents/s", "cores": used, "host_cores": cpu_t["cores"], "kind": cpu_t["kind"],
+               "sample": "%d-event sample of the workload, best of 3; faster of the %s events_to_voxel_torch on torch-CPU "
+                         "(%.1f Mev/s, %d threads) and events_to_voxel on numpy (%.1f Mev/s, 1 thread); from %s"
+                         % (CPU_SAMPLE, "reference's own" if cpu_t["kind"] == "reference" else "library-op port of",
+                            cpu_t["torch_cpu_mevs"], cpu_t["torch_threads"], cpu_t["numpy_mevs"], cpu_t["where"]),
                "cpu": cpu_model()}
         if not args.no_extra:
             del x, y, t, p
@@ -437,6 +494,9 @@ def run_ours(args, rank, local_rank, world):
             except Exception as exc:   # a secondary number must never cost the headline line
                 extra = {"error": repr(exc)}
 
+    if world > 1:
+        m_chk = min(n, 2_500_000)
+        x_chk, y_chk, t_chk, p_chk = (a[:m_chk].clone() for a in (x, y, t, p))
     if world > 1 and not args.no_extra:
         try:
             peer = peer_reduce_metric(device, x, y, t, p, t0, dt)
@@ -450,6 +510,12 @@ def run_ours(args, rank, local_rank, world):
             sharded = {"error": repr(exc)}
         if rank == 0:
             extra = {"cmax_sharded": sharded, "voxel_single_call_latency": peer}
+    if world > 1:
+        # parity of the product kernels vs the oracle (runs with --no-extra too; an assertion failure fails the bench)
+        oracle_check = peer_oracle_check(device, world, rank, x_chk, y_chk, t_chk, p_chk, t0, dt)
+        if rank == 0:
+            extra = dict(extra or {})
+            extra["multi_gpu_parity"] = oracle_check
 
     if rank == 0:
         line = {
@@ -461,10 +527,15 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": "Mevents/s", "h2d_bytes_per_step": 16 * n,
                     "d2h_bytes_per_step": 4 * B * H * W, "steps": e2e_steps,
                     "api": "events_to_voxel_torch(pinned CPU tensors) -> CPU tensor" if world == 1 else
-                           "evk_voxel_host_f32 (pinned host shard) + NCCL all-reduce + D2H per rank"},
+                           ("pinned host shard -> H2D -> %s.submit (the device-timed product path) -> D2H of the reduced grid on every rank"
+                            % type(pipe_mg).__name__),
+                    "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None)},
             "gpu_launches": int(klaunch.value),
+            "max_rel_err_vs_oracle": ((extra or {}).get("multi_gpu_parity", {}).get("peer", {}) or {}).get("max_rel_err_vs_oracle")
+            if world > 1 and isinstance((extra or {}).get("multi_gpu_parity", {}).get("peer"), dict) else None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_source": "profiles/ncu_summary.json (dram__bytes_read+write of this kernel from the committed ncu --set full capture; NOT measured in this run)",
                          "kernel": "voxel_scatter_kernel<QUAD_HOT> (one red.global.add.v4.f32 per event; adaptive hot-pixel cache, off for this uniform stream)",
                          "kernel_ms": k_ms, "launches_timed": int(ktimed.value),
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
@@ -478,6 +549,9 @@ def run_ours(args, rank, local_rank, world):
         if e2e_packed:
             extra = dict(extra or {})
             extra["e2e_storage_layout"] = e2e_packed
+        if e2e_pageable:
+            extra = dict(extra or {})
+            extra["e2e_pageable"] = e2e_pageable
         if extra:
             line["extra"] = extra
         sys.stdout.flush()
@@ -519,6 +593,44 @@ def peer_reduce_metric(device, x, y, t, p, t0, dt):
     return {"fused_fold_peer_allreduce_ms": ms_f, "fold_plus_nccl_allreduce_ms": ms_n, "max_rel_diff": diff,
             "what": "one call, %d M events per GPU; the fused kernel reads every rank's quad workspace and writes every rank's grid "
                     "over NVLink (symmetric memory), two cross-GPU barriers" % (N_PER_GPU // 1000000)}
+
+
+def peer_oracle_check(device, world, rank, x, y, t, p, t0, dt):
+    """Parity of the multi-GPU PRODUCT kernels against the CPU oracle on a sub-stream: every rank
+    contributes the first `m` events of its shard, the fused fold + all-reduce kernel (peer-pointer form, and the NVLS
+    multimem form where the symmetric-memory backend offers multicast) builds their grid with the stream's global
+    (t0, dt), the sub-shards are gathered and rank 0 runs oracle.voxel_f32 on the same events.  Checker only."""
+    import torch.distributed as dist
+    from event_utils_b200.parallel import PeerReducedVoxel
+    m = max(1, min(int(x.shape[0]), (2_000_000 + world - 1) // world + 250_000))
+    sub = [a[:m].contiguous() for a in (x, y, t, p)]
+    out = {"events": m * world}
+    grids = {}
+    for name, mc in (("peer", False), ("nvls", True)):
+        try:
+            pr = PeerReducedVoxel(B, (H, W), device, multicast=mc)
+            if mc and not pr.multicast:
+                out[name] = "multicast addresses not available on this box"
+                continue
+            grids[name] = pr(sub[0], sub[1], sub[2], sub[3], t0, dt).clone()
+        except Exception as exc:
+            out[name] = "unavailable: %r" % (exc,)
+    gathered = []
+    for a in sub:
+        parts = [torch.empty_like(a) for _ in range(world)] if rank == 0 else None
+        dist.gather(a, parts, dst=0)
+        gathered.append(parts)
+    if rank == 0:
+        from oracle import evk_oracle
+        evk_oracle.build()
+        ex, ey, et, ep = (torch.cat(parts).cpu().numpy() for parts in gathered)
+        ref = evk_oracle.voxel_f32(ex, ey, et, ep, B, (H, W), t0=t0, dt=dt)
+        scale = float(np.abs(ref).max())
+        for name, g in grids.items():
+            err = float(np.abs(g.cpu().numpy() - ref).max() / scale)
+            out[name] = {"max_rel_err_vs_oracle": err}
+            assert err <= 1e-5, "multi-GPU %s kernel vs oracle: %.3e" % (name, err)
+    return out
 
 
 def sharded_cmax_metric(device, world, rank):
@@ -581,8 +693,20 @@ def secondary_metrics(L, _lib, device, peak):
         x.data_ptr(), y.data_ptr(), t.data_ptr(), p.data_ptr(), n, 1.0, 45.0, -20.0, tl, 180, 240, 180, 240, 1.0,
         _lib.CMAX_WANT_GRAD, res.data_ptr(), None, None, ws.data_ptr(), ws.numel(), _lib.stream())))
     out["cmax_f64"] = {"iter_per_s": 1e3 / ms, "ms_per_iter": ms, "events": n, "what": "one fused (f, g) evaluation, "
-                       "linvel warp, 181x241 IWE, sigma=1, f64 inputs (32 B/event)",
+                       "linvel warp, 181x241 IWE, sigma=1, f64 inputs (32 B/event); IWE in shared memory "
+                       "(cmax_onchip_kernel), derivative values one L2 vector reduction per event",
                        "roofline_frac": 32.0 * n / (ms * 1e-3) / 1e9 / peak}
+    ms_f = best_of(lambda: _lib.check(L.evk_cmax_linvel_variance_f64(
+        x.data_ptr(), y.data_ptr(), t.data_ptr(), p.data_ptr(), n, 1.0, 45.0, -20.0, tl, 180, 240, 180, 240, 1.0,
+        0, res.data_ptr(), None, None, ws.data_ptr(), ws.numel(), _lib.stream())))
+    out["cmax_f64_f_only"] = {"iter_per_s": 1e3 / ms_f, "ms_per_iter": ms_f, "events": n,
+                              "what": "objective only (what a numeric-gradient / grid-search evaluation costs): no L2 reduction at all, "
+                                      "the finished image leaves each SM by TMA bulk reduction",
+                              "roofline_frac": 32.0 * n / (ms_f * 1e-3) / 1e9 / peak}
+    ms_l2 = best_of(lambda: _lib.check(L.evk_cmax_linvel_variance_f64(
+        x.data_ptr(), y.data_ptr(), t.data_ptr(), p.data_ptr(), n, 1.0, 45.0, -20.0, tl, 180, 240, 180, 240, 1.0,
+        _lib.CMAX_WANT_GRAD | _lib.VARIANT_VECTOR_RED, res.data_ptr(), None, None, ws.data_ptr(), ws.numel(), _lib.stream())))
+    out["cmax_f64"]["ms_per_iter_l2_block_accumulator"] = ms_l2
     # CPU port of one reference iteration (f then g) on a 1M-event sample
     try:
         from oracle import ref_port
