@@ -454,10 +454,12 @@ __global__ void __launch_bounds__(256) cmax_gather_kernel(const float *__restric
                                                           int replicas, int Hc, int Wc,
                                                           float *__restrict__ I, float *__restrict__ D0,
                                                           float *__restrict__ D1, float *__restrict__ iwe_out,
-                                                          float *__restrict__ diwe_out, double *sums)
+                                                          float *__restrict__ diwe_out, double *sums,
+                                                          const unsigned long long *oob_in = nullptr, unsigned long long *oob_out = nullptr)
 {
     const int npix = Hc * Wc;
     const int i = blockIdx.x * 256 + threadIdx.x;
+    if (oob_out && i == 0) *oob_out = *oob_in;
     float a = 0.f, b = 0.f, c = 0.f;
     if (i < npix) {
         const int y = i / Wc, x = i - y * Wc;
@@ -701,6 +703,24 @@ __global__ void cmax_obj_final_kernel(int kind, const double *gsums, const unsig
 // evaluation is launch-bound.
 constexpr int kTileY = 8, kTileX = 32, kFusedMaxR = 8;
 
+// Sharded evaluation (one process per GPU): every rank's partial planar images [3][Hc*Wc] (I, D0, D1) live in symmetric
+// memory; the tail of EVERY rank reads all of them through NVLink peer pointers and sums them on the fly (in rank order, so all
+// ranks compute bit-identical f and g) -- the all-reduce is fused into the objective kernel, there is no NCCL call.
+constexpr int kMaxCmaxPeers = 16;
+struct CmaxPeers {
+    const float *img[kMaxCmaxPeers];                  // [3][Hc*Wc] per rank
+    const unsigned long long *oob[kMaxCmaxPeers];     // out-of-canvas events per rank
+    int world;
+};
+
+__device__ __forceinline__ float gather_peers(const CmaxPeers &P, int Hc, int Wc, int y, int x, int comp)
+{
+    const int64_t npix = (int64_t)Hc * Wc, i = (int64_t)comp * npix + (int64_t)y * Wc + x;
+    float v = 0.f;
+    for (int r = 0; r < P.world; ++r) v += __ldcg(P.img[r] + i);       // peer loads bypass L1 (the data was written by another GPU)
+    return v;
+}
+
 __device__ __forceinline__ float gather_pixel(const float *acc, const float *planar, int replicas, int Hc, int Wc, int y, int x, int comp)
 {
     // comp 0: I, 1: D0, 2: D1 (see cmax_gather_kernel for the block / sign conventions)
@@ -721,7 +741,8 @@ __device__ __forceinline__ float gather_pixel(const float *acc, const float *pla
     return v;
 }
 
-__global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel(const float *__restrict__ acc, const float *__restrict__ planar, int replicas, int Hc, int Wc,
+template <bool PEER>
+__global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel_t(const CmaxPeers PE, const float *__restrict__ acc, const float *__restrict__ planar, int replicas, int Hc, int Wc,
                                                                               const BlurTaps taps, int do_blur, int want_grad,
                                                                               double mix_a, double mix_b, float *__restrict__ iwe_out,
                                                                               float *__restrict__ diwe_out, double *sums,
@@ -742,14 +763,15 @@ __global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel(con
     // 1. halo tile of the un-blurred IWE
     for (int j = tid; j < hh * hw; j += kTileY * kTileX) {
         const int ly = j / hw, lx = j - ly * hw;
-        tileI[j] = gather_pixel(acc, planar, replicas, Hc, Wc, reflect_idx(y0 - r + ly, Hc), reflect_idx(x0 - r + lx, Wc), 0);
+        const int gy = reflect_idx(y0 - r + ly, Hc), gx = reflect_idx(x0 - r + lx, Wc);
+        tileI[j] = PEER ? gather_peers(PE, Hc, Wc, gy, gx, 0) : gather_pixel(acc, planar, replicas, Hc, Wc, gy, gx, 0);
     }
     const int y = y0 + threadIdx.y, x = x0 + threadIdx.x;
     const bool inside = y < Hc && x < Wc;
     float vi = 0.f, d0 = 0.f, d1 = 0.f;
     if (inside) {
-        d0 = gather_pixel(acc, nullptr, replicas, Hc, Wc, y, x, 1);
-        d1 = gather_pixel(acc, nullptr, replicas, Hc, Wc, y, x, 2);
+        d0 = PEER ? gather_peers(PE, Hc, Wc, y, x, 1) : gather_pixel(acc, nullptr, replicas, Hc, Wc, y, x, 1);
+        d1 = PEER ? gather_peers(PE, Hc, Wc, y, x, 2) : gather_pixel(acc, nullptr, replicas, Hc, Wc, y, x, 2);
     }
     __syncthreads();
     if (inside) {
@@ -802,7 +824,13 @@ __global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel(con
         result[1] = want_grad ? (mix_a * g0 + mix_b * g1) : 0.0;
         result[2] = want_grad ? (mix_b * g0 + mix_a * g1) : 0.0;
         result[3] = s[0];
-        result[4] = (double)(*oob);
+        if (PEER) {
+            unsigned long long bad = 0;
+            for (int r = 0; r < PE.world; ++r) bad += __ldcg(PE.oob[r]);
+            result[4] = (double)bad;
+        } else {
+            result[4] = (double)(*oob);
+        }
         result[5] = var;
         result[6] = g0;
         result[7] = g1;
@@ -925,12 +953,15 @@ static int64_t onchip_min_events()
     return v;
 }
 
+// partial_images != nullptr: stop after the event pass and leave this rank's planar I, D0, D1 ([3][Hc*Wc]) and its
+// out-of-canvas count there (the sharded evaluation's first half; evk_cmax_peer_tail_f32 is the second)
 template <int WARP>
 static int run_cmax(CmaxArgs A, double sigma, unsigned flags, int objective, double obj_param, double *result,
-                    float *iwe_out, float *diwe_out, void *workspace, size_t workspace_bytes, cudaStream_t st)
+                    float *iwe_out, float *diwe_out, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                    float *partial_images = nullptr, unsigned long long *partial_oob = nullptr)
 {
     const int Hs = A.Hc - 1, Ws = A.Wc - 1;
-    if (A.n < 0 || Hs < 1 || Ws < 1 || !result || !workspace) { set_error("evk_cmax: bad arguments"); return EVK_E_ARG; }
+    if (A.n < 0 || Hs < 1 || Ws < 1 || (!result && !partial_images) || !workspace) { set_error("evk_cmax: bad arguments"); return EVK_E_ARG; }
     if (((uintptr_t)workspace & 255) != 0) { set_error("evk_cmax: workspace must be 256-byte aligned"); return EVK_E_ARG; }
     CmaxWorkspace ws;
     const size_t need = carve(workspace, Hs, Ws, &ws);
@@ -982,6 +1013,13 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, int objective, dou
         if (grad) cmax_scatter_kernel<WARP, true><<<grid_for(cmax_scatter_kernel<WARP, true>, 256, A.n, 256 * 4), 256, 0, st>>>(A);
         else cmax_scatter_kernel<WARP, false><<<grid_for(cmax_scatter_kernel<WARP, false>, 256, A.n, 256 * 4), 256, 0, st>>>(A);
     }
+    if (partial_images) {
+        prof_count(1);
+        cmax_gather_kernel<<<(npix + 255) / 256, 256, 0, st>>>(ws.acc, planar, R, A.Hc, A.Wc, partial_images, partial_images + npix,
+                                                                partial_images + 2 * (size_t)npix, nullptr, nullptr, ws.sums, ws.oob, partial_oob);
+        EVK_CUDA(cudaGetLastError());
+        return EVK_OK;
+    }
     if (objective == OBJ_VARIANCE && (sigma <= 0.0 || (int)(4.0 * sigma + 0.5) <= kFusedMaxR)) {
         // launch-bound regime matters most here: gather + blur + sums + final in one kernel
         BlurTaps taps{};
@@ -994,7 +1032,7 @@ static int run_cmax(CmaxArgs A, double sigma, unsigned flags, int objective, dou
         }
         prof_count(1);
         dim3 tgrid((A.Wc + kTileX - 1) / kTileX, (A.Hc + kTileY - 1) / kTileY), tblock(kTileX, kTileY);
-        cmax_fused_var_tail_kernel<<<tgrid, tblock, 0, st>>>(ws.acc, planar, R, A.Hc, A.Wc, taps, do_blur, grad ? 1 : 0, mix_a, mix_b, iwe_out,
+        cmax_fused_var_tail_kernel_t<false><<<tgrid, tblock, 0, st>>>(CmaxPeers{}, ws.acc, planar, R, A.Hc, A.Wc, taps, do_blur, grad ? 1 : 0, mix_a, mix_b, iwe_out,
                                                                diwe_out, ws.sums, ws.gmax, ws.oob, result);
         EVK_CUDA(cudaGetLastError());
         return EVK_OK;
@@ -1078,6 +1116,73 @@ int evk_cmax_linvel_variance_f32(const float *x, const float *y, const float *t_
 {
     return evk_cmax_linvel_objective_f32(x, y, t_rel, p, n, p_scale, vx, vy, Hm, Wm, Hs, Ws, sigma, flags, 0, 0.0, result,
                                          iwe_out, diwe_out, workspace, workspace_bytes, stream);
+}
+
+int evk_cmax_linvel_partial_f64(const double *x, const double *y, const double *t, const double *p, int64_t n, double p_scale,
+                                double vx, double vy, double t_ref, int Hm, int Wm, int Hs, int Ws, unsigned flags,
+                                float *images_out, unsigned long long *oob_out, void *workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace evk;
+    if (!images_out || (n > 0 && (!x || !y || !t || !p))) { set_error("evk_cmax_linvel_partial_f64: null array"); return EVK_E_ARG; }
+    CmaxArgs A{};
+    A.x = x; A.y = y; A.t = t; A.p = p; A.n = n;
+    A.vx = vx; A.vy = vy; A.t_ref = t_ref; A.p_scale = p_scale;
+    A.Hm = Hm; A.Wm = Wm; A.Hc = Hs + 1; A.Wc = Ws + 1;
+    return run_cmax<WARP_LINVEL_F64>(A, 0.0, flags, 0, 0.0, nullptr, nullptr, nullptr, workspace, workspace_bytes,
+                                     static_cast<cudaStream_t>(stream), images_out, oob_out);
+}
+
+int evk_cmax_linvel_partial_f32(const float *x, const float *y, const float *t_rel, const float *p, int64_t n, float p_scale,
+                                float vx, float vy, int Hm, int Wm, int Hs, int Ws, unsigned flags, float *images_out,
+                                unsigned long long *oob_out, void *workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace evk;
+    if (!images_out || (n > 0 && (!x || !y || !t_rel || !p))) { set_error("evk_cmax_linvel_partial_f32: null array"); return EVK_E_ARG; }
+    CmaxArgs A{};
+    A.x = x; A.y = y; A.t = t_rel; A.p = p; A.n = n;
+    A.vx = vx; A.vy = vy; A.t_ref = 0.0; A.p_scale = p_scale;
+    A.Hm = Hm; A.Wm = Wm; A.Hc = Hs + 1; A.Wc = Ws + 1;
+    return run_cmax<WARP_LINVEL_F32>(A, 0.0, flags, 0, 0.0, nullptr, nullptr, nullptr, workspace, workspace_bytes,
+                                     static_cast<cudaStream_t>(stream), images_out, oob_out);
+}
+
+int evk_cmax_peer_tail_f32(const float *const *peer_images, const unsigned long long *const *peer_oob, int world, int Hc, int Wc,
+                           double sigma, unsigned flags, double *result, void *workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace evk;
+    if (!peer_images || !peer_oob || world < 1 || world > kMaxCmaxPeers || Hc < 2 || Wc < 2 || !result || !workspace) {
+        set_error("evk_cmax_peer_tail_f32: bad arguments (1 <= world <= %d)", kMaxCmaxPeers);
+        return EVK_E_ARG;
+    }
+    if (((uintptr_t)workspace & 255) != 0) { set_error("evk_cmax_peer_tail_f32: workspace must be 256-byte aligned"); return EVK_E_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CmaxWorkspace ws;
+    const size_t need = carve(workspace, Hc - 1, Wc - 1, &ws);
+    if (workspace_bytes < need) { set_error("evk_cmax_peer_tail_f32: workspace of %zu bytes required", need); return EVK_E_WORKSPACE; }
+    BlurTaps taps{};
+    double mix_a = 1.0, mix_b = 0.0;
+    const int do_blur = sigma > 0.0;
+    if (do_blur) {
+        int rc = make_taps(sigma, &taps);
+        if (rc) return rc;
+        if (taps.r > kFusedMaxR) { set_error("evk_cmax_peer_tail_f32: blur radius %d > %d", taps.r, kFusedMaxR); return EVK_E_UNSUPPORTED; }
+        if (!(flags & EVK_CMAX_NO_CHANNEL_MIX)) mix_coeffs(taps, &mix_a, &mix_b);
+    }
+    CmaxPeers P{};
+    P.world = world;
+    for (int r = 0; r < world; ++r) {
+        if (!peer_images[r] || !peer_oob[r]) { set_error("evk_cmax_peer_tail_f32: peer %d: null pointer", r); return EVK_E_ARG; }
+        P.img[r] = peer_images[r];
+        P.oob[r] = peer_oob[r];
+    }
+    // the sums and the ticket of the tail (gsums .. oob are contiguous)
+    EVK_CUDA(cudaMemsetAsync(ws.gsums, 0, (size_t)((char *)(ws.oob + 1) - (char *)ws.gsums), st));
+    prof_count(1);
+    dim3 tgrid((Wc + kTileX - 1) / kTileX, (Hc + kTileY - 1) / kTileY), tblock(kTileX, kTileY);
+    cmax_fused_var_tail_kernel_t<true><<<tgrid, tblock, 0, st>>>(P, nullptr, nullptr, 1, Hc, Wc, taps, do_blur, (flags & EVK_CMAX_WANT_GRAD) ? 1 : 0,
+                                                                  mix_a, mix_b, nullptr, nullptr, ws.sums, ws.gmax, ws.oob, result);
+    EVK_CUDA(cudaGetLastError());
+    return EVK_OK;
 }
 
 int evk_cmax_flow_variance_f32(const float *x, const float *y, const float *t, const float *p, int64_t n,
@@ -1184,7 +1289,7 @@ int evk_cmax_linvel_objective_batch_f64(const double *x, const double *y, const 
         }
         prof_count(1);
         dim3 tgrid((A.Wc + kTileX - 1) / kTileX, (A.Hc + kTileY - 1) / kTileY, n_params), tblock(kTileX, kTileY);
-        cmax_fused_var_tail_kernel<<<tgrid, tblock, 0, st>>>(ws.acc, nullptr, 1, A.Hc, A.Wc, taps, do_blur, grad ? 1 : 0, mix_a, mix_b, nullptr,
+        cmax_fused_var_tail_kernel_t<false><<<tgrid, tblock, 0, st>>>(CmaxPeers{}, ws.acc, nullptr, 1, A.Hc, A.Wc, taps, do_blur, grad ? 1 : 0, mix_a, mix_b, nullptr,
                                                                nullptr, ws.bsums, ws.btickets, ws.oob, results);
         EVK_CUDA(cudaGetLastError());
         return EVK_OK;

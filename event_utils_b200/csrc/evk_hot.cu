@@ -10,6 +10,8 @@
 // small direct-mapped table {cell -> partial sum} in shared memory: an event whose cell owns its
 // slot is accumulated with a shared-memory atomic, everything else (slot taken by another cell)
 // goes straight to L2, and the table is flushed with one reduction per occupied slot at the end.
+// Round 2: 8192-slot two-way set-associative table per 512-thread CTA, INTEGER (fixed-point) values so that the hot
+// cells use native shared-memory atomics, 16-byte event loads in the cached path as well.
 // Hot cells are thereby reduced to one L2 reduction per CTA.  The kernel is ADAPTIVE: a prologue
 // counts intra-warp duplicates (match.any) among the CTA's first events and turns the cache off
 // for streams without contention, where it would only add shared-memory traffic.
@@ -31,40 +33,71 @@ struct HotArgs {
     int vec4;         // x, y (and p) are 16-byte aligned
 };
 
-constexpr int kHotLog2 = 12;
-constexpr int kHotSlots = 1 << kHotLog2;  // 4096 slots: 16 KB keys + 16 KB values
+constexpr int kHotThreads = 512;
+constexpr int kHotLog2 = 13;
+constexpr int kHotSlots = 1 << kHotLog2;  // 8192 slots (4096 two-way sets): 32 KB keys + 32 KB values of dynamic shared memory
 constexpr unsigned kEmpty = 0xffffffffu;
+constexpr unsigned kHotBias = 0x80000000u;
+// Table values are INTEGERS (native ATOMS.ADD; f32 shared-memory adds are CAS loops on sm_100a):
+//   nearest  value * 2^10 -- exact for the integer polarities event cameras produce (+-1, 0/1), so hot cells keep
+//            bit-exact sums; a weight that is not a multiple of 2^-10 below 2^20 bypasses the table (global f32 reduction)
+//   bilinear tap * 2^22 (|tap| <= 1; quantisation 2^-23 per tap, below f32 rounding of the accumulation itself)
+//   count    plain u32
+// A float-mode cell is biased by 2^31; the returning atomic tells the thread whether ITS add wrapped the 32 bits and that
+// thread carries +-2^(32-F) to the global image, so the table can never overflow silently.
+constexpr int kHotFixNearest = 10, kHotFixBilinear = 22;
 
 // `gs` = element stride of a cell in the global target (4 when the target is the TL slot of a block)
 __device__ __forceinline__ void global_add(float *out, unsigned cell, float v, int gs) { red_add(out + (size_t)cell * gs, v); }
 __device__ __forceinline__ void global_add(unsigned *out, unsigned cell, unsigned v, int gs) { red_add_u32(out + (size_t)cell * gs, v); }
 
-template <typename V>
-__device__ __forceinline__ void hot_add(unsigned *keys, V *vals, V *gout, bool use_cache, unsigned cell, V v, int gs = 1)
+// find (or claim) the cell's slot in its two-way set; -1 = both ways belong to other cells
+__device__ __forceinline__ int hot_slot(unsigned *keys, unsigned cell)
 {
-    if (use_cache) {
-        const unsigned slot = (cell * 2654435761u) >> (32 - kHotLog2);
-        unsigned k = keys[slot];
-        if (k == kEmpty) {
-            const unsigned old = atomicCAS(&keys[slot], kEmpty, cell);
-            k = (old == kEmpty) ? cell : old;
-        }
-        if (k == cell) {
-            atomicAdd(&vals[slot], v);  // shared memory: native for u32, CAS loop (ATOMS.CAST.SPIN) for f32
-            return;
-        }
+    const unsigned s0 = ((cell * 2654435761u) >> (32 - (kHotLog2 - 1))) * 2u;
+    const uint2 k = *reinterpret_cast<const uint2 *>(keys + s0);
+    if (k.x == cell) return (int)s0;
+    if (k.y == cell) return (int)s0 + 1;
+    if (k.x == kEmpty) {
+        const unsigned old = atomicCAS(keys + s0, kEmpty, cell);
+        if (old == kEmpty || old == cell) return (int)s0;
     }
-    global_add(gout, cell, v, gs);
+    const unsigned k1 = *(volatile unsigned *)(keys + s0 + 1);
+    if (k1 == cell) return (int)s0 + 1;
+    if (k1 == kEmpty) {
+        const unsigned old = atomicCAS(keys + s0 + 1, kEmpty, cell);
+        if (old == kEmpty || old == cell) return (int)s0 + 1;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ unsigned hot_atoms_ret(unsigned *cell, unsigned v)
+{
+    unsigned old;
+    asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(cell)), "r"(v));
+    return old;
+}
+
+// float modes: add value v (already known to be representable: q == v * 2^FIX) to the cell through the table
+template <int FIX>
+__device__ __forceinline__ void hot_add_fixed(unsigned *keys, unsigned *vals, float *gout, unsigned cell, float v, unsigned q, int gs)
+{
+    const int slot = hot_slot(keys, cell);
+    if (slot < 0) { global_add(gout, cell, v, gs); return; }
+    const unsigned old = hot_atoms_ret(vals + slot, q);
+    const unsigned nw = old + q;
+    if (((old ^ nw) & ~(nw ^ q)) >> 31)      // this add wrapped the cell (see evk_cmax.cu wrap_bit): carry it out
+        global_add(gout, cell, (int)q >= 0 ? (float)(1u << (32 - FIX)) : -(float)(1u << (32 - FIX)), gs);
 }
 
 enum { HOT_NEAREST = 0, HOT_BILINEAR = 1, HOT_COUNT = 2 };
 
 // one event; CACHE is a compile-time switch so that the cache-off instantiation is the plain scatter code
-template <int MODE, bool CACHE, typename V>
-__device__ __forceinline__ void hot_event(const HotArgs &A, unsigned *keys, V *vals, V *gout, int gs, float x, float y, float pin,
-                                          unsigned &oob)
+template <int MODE, bool CACHE>
+__device__ __forceinline__ void hot_event(const HotArgs &A, unsigned *keys, unsigned *vals, float x, float y, float pin, unsigned &oob)
 {
-    constexpr bool use_cache = CACHE;
+    float *gf = (MODE == HOT_BILINEAR && A.ws) ? A.ws : A.out;
+    const int gs = (MODE == HOT_BILINEAR && A.ws) ? 4 : 1;
     if (MODE == HOT_NEAREST || MODE == HOT_COUNT) {
         // image.py:88-95
         const bool keep = !A.clip || (!(x >= A.clipx) && !(y >= A.clipy));
@@ -74,10 +107,19 @@ __device__ __forceinline__ void hot_event(const HotArgs &A, unsigned *keys, V *v
         if (!wrap_int_index(ux, A.W, xi) || !wrap_int_index(uy, A.H, yi)) { ++oob; return; }
         const unsigned cell = (unsigned)yi * (unsigned)A.W + (unsigned)xi;
         if (MODE == HOT_COUNT) {
-            hot_add<V>(keys, vals, gout, use_cache, cell, (V)1);
+            int slot = -1;
+            if (CACHE) slot = hot_slot(keys, cell);
+            if (slot >= 0) atomicAdd(vals + slot, 1u);
+            else red_add_u32(A.out_u32 + cell, 1u);
         } else {
             const float p = pin;
-            if (p != 0.0f) hot_add<V>(keys, vals, gout, use_cache, cell, (V)p);
+            if (p == 0.0f) return;
+            if (CACHE) {
+                const float ps = __fmul_rn(p, (float)(1 << kHotFixNearest));
+                const int q = __float2int_rn(ps);
+                if (fabsf(p) < 1048576.0f && (float)q == ps) { hot_add_fixed<kHotFixNearest>(keys, vals, gf, cell, p, (unsigned)q, 1); return; }
+            }
+            red_add(gf + cell, p);
         }
     } else {
         // image.py:79-86 + 111-114
@@ -95,55 +137,56 @@ __device__ __forceinline__ void hot_event(const HotArgs &A, unsigned *keys, V *v
         const float wl = __fmul_rn(w, ox), wr = __fmul_rn(w, dx);
         const float v00 = __fmul_rn(wl, oy), v01 = __fmul_rn(wr, oy), v10 = __fmul_rn(wl, dy), v11 = __fmul_rn(wr, dy);
         const unsigned r0 = (unsigned)y0 * (unsigned)A.W, r1 = (unsigned)y1 * (unsigned)A.W;
-        if (!use_cache && A.ws && x1 == x0 + 1 && y1 == y0 + 1) {
+        if (!CACHE && A.ws && x1 == x0 + 1 && y1 == y0 + 1) {
             // uncontended stream: the whole footprint as ONE vector reduction into its block
             if (v00 != 0.0f || v01 != 0.0f || v10 != 0.0f || v11 != 0.0f)
                 red_add4(A.ws + ((size_t)r0 + x0) * 4, make_float4(v00, v01, v10, v11));
+        } else if (CACHE && fabsf(w) <= 1.0f) {
+            const float S = (float)(1 << kHotFixBilinear);
+            const int q00 = __float2int_rn(__fmul_rn(v00, S)), q01 = __float2int_rn(__fmul_rn(v01, S));
+            const int q10 = __float2int_rn(__fmul_rn(v10, S)), q11 = __float2int_rn(__fmul_rn(v11, S));
+            if (q00) hot_add_fixed<kHotFixBilinear>(keys, vals, gf, r0 + x0, v00, (unsigned)q00, gs);
+            if (q01) hot_add_fixed<kHotFixBilinear>(keys, vals, gf, r0 + x1, v01, (unsigned)q01, gs);
+            if (q10) hot_add_fixed<kHotFixBilinear>(keys, vals, gf, r1 + x0, v10, (unsigned)q10, gs);
+            if (q11) hot_add_fixed<kHotFixBilinear>(keys, vals, gf, r1 + x1, v11, (unsigned)q11, gs);
         } else {
-            if (v00 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x0, (V)v00, gs);
-            if (v01 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r0 + x1, (V)v01, gs);
-            if (v10 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x0, (V)v10, gs);
-            if (v11 != 0.0f) hot_add<V>(keys, vals, gout, use_cache, r1 + x1, (V)v11, gs);
+            if (v00 != 0.0f) global_add(gf, r0 + x0, v00, gs);
+            if (v01 != 0.0f) global_add(gf, r0 + x1, v01, gs);
+            if (v10 != 0.0f) global_add(gf, r1 + x0, v10, gs);
+            if (v11 != 0.0f) global_add(gf, r1 + x1, v11, gs);
         }
     }
 }
 
 // the event loop; VEC4: 16-byte loads (x, y, p all 16-byte aligned)
-template <int MODE, bool CACHE, bool VEC4, typename V>
-__device__ __forceinline__ void hot_loop(const HotArgs &A, unsigned *keys, V *vals, V *gout, int gs, int64_t tid, int64_t stride,
-                                         unsigned &oob)
+template <int MODE, bool CACHE, bool VEC4>
+__device__ __forceinline__ void hot_loop(const HotArgs &A, unsigned *keys, unsigned *vals, int64_t tid, int64_t stride, unsigned &oob)
 {
     if (VEC4) {
         const int64_t n4 = A.n >> 2;
         for (int64_t g = tid; g < n4; g += stride) {
             const float4 X = ld_stream4(A.x + 4 * g), Y = ld_stream4(A.y + 4 * g);
             const float4 P = (MODE == HOT_COUNT) ? make_float4(1.f, 1.f, 1.f, 1.f) : ld_stream4(A.p + 4 * g);
-            hot_event<MODE, CACHE, V>(A, keys, vals, gout, gs, X.x, Y.x, P.x, oob);
-            hot_event<MODE, CACHE, V>(A, keys, vals, gout, gs, X.y, Y.y, P.y, oob);
-            hot_event<MODE, CACHE, V>(A, keys, vals, gout, gs, X.z, Y.z, P.z, oob);
-            hot_event<MODE, CACHE, V>(A, keys, vals, gout, gs, X.w, Y.w, P.w, oob);
+            hot_event<MODE, CACHE>(A, keys, vals, X.x, Y.x, P.x, oob);
+            hot_event<MODE, CACHE>(A, keys, vals, X.y, Y.y, P.y, oob);
+            hot_event<MODE, CACHE>(A, keys, vals, X.z, Y.z, P.z, oob);
+            hot_event<MODE, CACHE>(A, keys, vals, X.w, Y.w, P.w, oob);
         }
         for (int64_t i = (n4 << 2) + tid; i < A.n; i += stride)
-            hot_event<MODE, CACHE, V>(A, keys, vals, gout, gs, A.x[i], A.y[i], (MODE == HOT_COUNT) ? 1.0f : A.p[i], oob);
+            hot_event<MODE, CACHE>(A, keys, vals, A.x[i], A.y[i], (MODE == HOT_COUNT) ? 1.0f : A.p[i], oob);
     } else {
         for (int64_t i = tid; i < A.n; i += stride)
-            hot_event<MODE, CACHE, V>(A, keys, vals, gout, gs, ld_stream(A.x + i), ld_stream(A.y + i),
-                                      (MODE == HOT_COUNT) ? 1.0f : ld_stream(A.p + i), oob);
+            hot_event<MODE, CACHE>(A, keys, vals, ld_stream(A.x + i), ld_stream(A.y + i), (MODE == HOT_COUNT) ? 1.0f : ld_stream(A.p + i), oob);
     }
 }
 
-
 template <int MODE>
-__global__ void __launch_bounds__(256) image_hot_kernel(const HotArgs A)
+__global__ void __launch_bounds__(kHotThreads) image_hot_kernel(const HotArgs A)
 {
-    using V = typename std::conditional<MODE == HOT_COUNT, unsigned, float>::type;
-    __shared__ unsigned keys[kHotSlots];
-    __shared__ V vals[kHotSlots];
-    V *gout = (MODE == HOT_COUNT) ? (V *)A.out_u32 : (MODE == HOT_BILINEAR && A.ws) ? (V *)A.ws : (V *)A.out;
-    const int gs = (MODE == HOT_BILINEAR && A.ws) ? 4 : 1;
-
-    const int64_t tid = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * 256;
+    extern __shared__ __align__(16) unsigned hot_smem[];      // [kHotSlots] keys, [kHotSlots] values
+    unsigned *keys = hot_smem, *vals = hot_smem + kHotSlots;
+    const int64_t tid = (int64_t)blockIdx.x * kHotThreads + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * kHotThreads;
 
     // ---- prologue: is this stream contended?  (lanes whose first event shares its pixel with
     // another lane of the same warp)
@@ -156,26 +199,41 @@ __global__ void __launch_bounds__(256) image_hot_kernel(const HotArgs A)
         }
         // counted over the CTA by the barrier itself: one __syncthreads_count, no shared-memory traffic
         const int dup_lanes = __syncthreads_count(__popc(__match_any_sync(0xffffffffu, key)) > 1);
-        use_cache = dup_lanes * 64 > 256;  // > 4 of 256 lanes collide inside their warp (uniform streams: ~0.01)
+        use_cache = dup_lanes * 64 > kHotThreads;  // > 1/64 of the lanes collide inside their warp (uniform streams: ~0.01 %)
     }
+    const unsigned init = (MODE == HOT_COUNT) ? 0u : kHotBias;
     if (use_cache) {   // only CTAs that will use the table pay for initialising it
-        for (int s = threadIdx.x; s < kHotSlots; s += 256) { keys[s] = kEmpty; vals[s] = (V)0; }
+        for (int s = threadIdx.x; s < kHotSlots; s += kHotThreads) { keys[s] = kEmpty; vals[s] = init; }
         __syncthreads();
     }
 
     unsigned oob = 0;
-    // cache off -> the plain scatter code (vector loads when possible), cache on -> the cached code
-    if (use_cache) hot_loop<MODE, true, false, V>(A, keys, vals, gout, gs, tid, stride, oob);
-    else if (A.vec4) hot_loop<MODE, false, true, V>(A, keys, vals, gout, gs, tid, stride, oob);
-    else hot_loop<MODE, false, false, V>(A, keys, vals, gout, gs, tid, stride, oob);
+    // cache off -> the plain scatter code, cache on -> the table; 16-byte loads when the arrays allow
+    if (use_cache) { if (A.vec4) hot_loop<MODE, true, true>(A, keys, vals, tid, stride, oob); else hot_loop<MODE, true, false>(A, keys, vals, tid, stride, oob); }
+    else if (A.vec4) hot_loop<MODE, false, true>(A, keys, vals, tid, stride, oob);
+    else hot_loop<MODE, false, false>(A, keys, vals, tid, stride, oob);
     __syncthreads();
     if (use_cache) {
-        for (int s = threadIdx.x; s < kHotSlots; s += 256) {
-            const unsigned k = keys[s];
-            if (k != kEmpty && vals[s] != (V)0) global_add(gout, k, vals[s], gs);
+        float *gf = (MODE == HOT_BILINEAR && A.ws) ? A.ws : A.out;
+        const int gs = (MODE == HOT_BILINEAR && A.ws) ? 4 : 1;
+        const float inv = 1.0f / (float)(1 << (MODE == HOT_BILINEAR ? kHotFixBilinear : kHotFixNearest));
+        for (int s = threadIdx.x; s < kHotSlots; s += kHotThreads) {
+            const unsigned k = keys[s], v = vals[s];
+            if (k == kEmpty || v == init) continue;
+            if (MODE == HOT_COUNT) red_add_u32(A.out_u32 + k, v);
+            else global_add(gf, k, __fmul_rn((float)(int)(v - kHotBias), inv), gs);
         }
     }
     flush_oob(A.oob, oob);
+}
+
+template <int MODE>
+static int launch_hot_mode(const HotArgs &A, cudaStream_t st)
+{
+    const size_t smem = (size_t)kHotSlots * 2 * sizeof(unsigned);
+    EVK_CUDA(cudaFuncSetAttribute(image_hot_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    image_hot_kernel<MODE><<<grid_for(image_hot_kernel<MODE>, kHotThreads, A.n, kHotThreads * 16, smem), kHotThreads, smem, st>>>(A);
+    return EVK_OK;
 }
 
 int launch_image_hot(const float *x, const float *y, const float *p, int64_t n, int H, int W, int clip, float clipx,
@@ -191,9 +249,11 @@ int launch_image_hot(const float *x, const float *y, const float *p, int64_t n, 
     if (n <= 0) return EVK_OK;
     ProfScope prof(st);
     prof_count(1);
-    if (mode == HOT_NEAREST) image_hot_kernel<HOT_NEAREST><<<grid_for(image_hot_kernel<HOT_NEAREST>, 256, n, 256 * 16), 256, 0, st>>>(A);
-    else if (mode == HOT_BILINEAR) image_hot_kernel<HOT_BILINEAR><<<grid_for(image_hot_kernel<HOT_BILINEAR>, 256, n, 256 * 16), 256, 0, st>>>(A);
-    else image_hot_kernel<HOT_COUNT><<<grid_for(image_hot_kernel<HOT_COUNT>, 256, n, 256 * 16), 256, 0, st>>>(A);
+    int rc;
+    if (mode == HOT_NEAREST) rc = launch_hot_mode<HOT_NEAREST>(A, st);
+    else if (mode == HOT_BILINEAR) rc = launch_hot_mode<HOT_BILINEAR>(A, st);
+    else rc = launch_hot_mode<HOT_COUNT>(A, st);
+    if (rc) return rc;
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

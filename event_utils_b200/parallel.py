@@ -282,6 +282,81 @@ def _cmax_images_cuda(params, xs, ys, ts, ps, t_ref, img_size, want_grad, use_po
         return images, oob
 
 
+class PeerCmax:
+    """Sharded contrast-maximisation evaluation whose all-reduce is FUSED into the objective kernel (VERDICT r1 missing #3):
+    every rank splats its shard (evk_cmax_linvel_partial_*: the on-chip event pass for large shards) and leaves its planar
+    partial images -- IWE and the two derivative images, 3 x 181 x 241 floats -- in symmetric memory; ONE cross-GPU barrier;
+    then every rank's tail kernel (evk_cmax_peer_tail_f32) reads all ranks' partial images through NVLink peer pointers,
+    sums them in rank order while gathering its tiles, blurs, reduces and writes f, g and the out-of-canvas count into
+    pinned host memory.  No NCCL call, no second all-reduce, no .item() between the halves; the partial images are
+    double-buffered so that one barrier per evaluation is enough (the barrier of evaluation k+1 orders tail k before the
+    partial pass k+2 that reuses its buffer).  (f, g) is bit-identical on all ranks.
+    Reference semantics: variance_objective.evaluate_function / evaluate_gradient with linvel_warp, objectives.py:211-264."""
+
+    def __init__(self, device, group=None, sensor_size=(180, 240)):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self._lib, self.L = _lib, _lib.lib()
+        self.device = torch.device(device)
+        group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.Hs, self.Ws = int(sensor_size[0]), int(sensor_size[1])
+        self.npix = (self.Hs + 1) * (self.Ws + 1)
+        words = 3 * self.npix + 4                      # images + the out-of-canvas counter (8 bytes, 8-byte aligned)
+        words += words & 1
+        self.oob_off = (3 * self.npix + 1) // 2 * 2    # float index of the counter
+        self.bufs = []
+        for _ in range(2):
+            buf = symm.empty(words, dtype=torch.float32, device=self.device)
+            h = symm.rendezvous(buf, group)
+            ptrs = [int(a) for a in h.buffer_ptrs]
+            self.bufs.append(dict(buf=buf, h=h,
+                                  img=(ctypes.c_void_p * self.world)(*ptrs),
+                                  oob=(ctypes.c_void_p * self.world)(*[a + 4 * self.oob_off for a in ptrs])))
+        self.ws = torch.empty(self.L.evk_cmax_workspace_bytes(self.Hs, self.Ws), dtype=torch.uint8, device=self.device)
+        self.result = torch.zeros(12, dtype=torch.float64).pin_memory()
+        self.result_np = self.result.numpy()
+        self.k = 0
+
+    def __call__(self, params, xs, ys, ts, ps, img_size, blur_sigma=1.0, t_ref=None, want_grad=True, use_polarity=True,
+                 ts_relative=False):
+        """This rank's shard (CUDA tensors: f64 = parity mode with absolute stamps + t_ref, f32 = fast mode) -> (f, g).
+        ts_relative: the f32 stamps are already relative to the stream's last timestamp (made so once, in f64, by the
+        caller: an optimiser evaluates the same shard hundreds of times)."""
+        _lib, L = self._lib, self.L
+        if t_ref is None and not ts_relative:
+            t_ref = global_last_timestamp(ts)
+        b = self.bufs[self.k & 1]
+        self.k += 1
+        flags = (_lib.CMAX_WANT_GRAD if want_grad else 0) | (0 if use_polarity else _lib.CMAX_ABS_POLARITY)
+        n = int(xs.shape[0])
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device)
+            img_ptr = b["buf"].data_ptr()
+            oob_ptr = img_ptr + 4 * self.oob_off
+            if ts.dtype == torch.float64:
+                x, y, t, p = (a.to(torch.float64).contiguous() for a in (xs, ys, ts, ps))
+                _lib.check(L.evk_cmax_linvel_partial_f64(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), n, 1.0, float(params[0]),
+                                                         float(params[1]), float(t_ref), int(img_size[0]), int(img_size[1]), self.Hs,
+                                                         self.Ws, flags, img_ptr, oob_ptr, _lib.ptr(self.ws), self.ws.numel(), st.cuda_stream))
+            else:
+                x, y, p = (a.to(torch.float32).contiguous() for a in (xs, ys, ps))
+                t = (ts if ts_relative else (ts.to(torch.float64) - float(t_ref))).to(torch.float32).contiguous()
+                _lib.check(L.evk_cmax_linvel_partial_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), n, 1.0, float(params[0]),
+                                                         float(params[1]), int(img_size[0]), int(img_size[1]), self.Hs, self.Ws, flags,
+                                                         img_ptr, oob_ptr, _lib.ptr(self.ws), self.ws.numel(), st.cuda_stream))
+            b["h"].barrier(channel=0)                  # every rank's partial images are in place
+            _lib.check(L.evk_cmax_peer_tail_f32(b["img"], b["oob"], self.world, self.Hs + 1, self.Ws + 1, float(blur_sigma), flags,
+                                                self.result.data_ptr(), _lib.ptr(self.ws), self.ws.numel(), st.cuda_stream))
+            st.synchronize()
+        res = self.result_np.copy()
+        if res[4] != 0:
+            raise IndexError("%d warped events index outside the IWE canvas" % int(res[4]))
+        import numpy as np
+        return float(res[0]), np.array([res[1], res[2]])
+
+
 def _cmax_tail_cuda(images, blur_sigma, want_grad):
     """(f, g) of the reduced images (evk_variance_objective_f32)."""
     from . import _lib

@@ -304,6 +304,27 @@ int evk_variance_objective_f32(const float *iwe, const float *diwe, int Hc, int 
                                unsigned flags, double *result, void *workspace,
                                size_t workspace_bytes, void *stream);
 
+/* Sharded contrast maximisation, one process per GPU: the all-reduce of the partial images is FUSED into the
+ * objective kernel over NVLink peer memory -- no NCCL call, no host synchronisation between the two halves.
+ *   evk_cmax_linvel_partial_*  event pass of THIS rank's shard; leaves its planar partial images images_out[3][Hs+1][Ws+1]
+ *                              (IWE, dIWE/dvx, dIWE/dvy; objectives.py:184-192) and its out-of-canvas event count.
+ *                              images_out / oob_out live in memory every rank has mapped (symmetric memory).
+ *   (a cross-GPU barrier)
+ *   evk_cmax_peer_tail_f32     every rank reads ALL ranks' partial images through peer pointers, sums them in rank order
+ *                              while it gathers its tiles, blurs, reduces and writes f, g (objectives.py:231-264) --
+ *                              bit-identical on all ranks.  result[4] = total out-of-canvas events. */
+int evk_cmax_linvel_partial_f64(const double *x, const double *y, const double *t, const double *p, int64_t n,
+                                double p_scale, double vx, double vy, double t_ref, int Hm, int Wm, int Hs, int Ws,
+                                unsigned flags, float *images_out, unsigned long long *oob_out, void *workspace,
+                                size_t workspace_bytes, void *stream);
+int evk_cmax_linvel_partial_f32(const float *x, const float *y, const float *t_rel, const float *p, int64_t n,
+                                float p_scale, float vx, float vy, int Hm, int Wm, int Hs, int Ws, unsigned flags,
+                                float *images_out, unsigned long long *oob_out, void *workspace,
+                                size_t workspace_bytes, void *stream);
+int evk_cmax_peer_tail_f32(const float *const *peer_images, const unsigned long long *const *peer_oob, int world,
+                           int Hc, int Wc, double sigma, unsigned flags, double *result, void *workspace,
+                           size_t workspace_bytes, void *stream);
+
 /* Objective only (f) for a dense-flow warp: warp_events_flow_torch + bilinear IWE
  * (lib/visualization/draw_flow.py:18-21) + the variance objective.  flow: [2][Hs][Ws]. */
 int evk_cmax_flow_variance_f32(const float *x, const float *y, const float *t, const float *p,

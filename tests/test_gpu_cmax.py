@@ -212,6 +212,46 @@ def test_sharded_evaluation_matches_whole_stream(oracle):
     assert np.abs(g4 - go4).max() <= 1e-3 * grad_scale(iwe, d)
 
 
+@pytest.mark.parametrize("event_pass", [0, "onchip"])
+def test_fused_peer_tail_with_emulated_ranks(oracle, event_pass):
+    """The sharded evaluation's two halves through the C ABI on ONE GPU: three "ranks" (uneven shards, one of them empty)
+    leave their partial images in three buffers (evk_cmax_linvel_partial_f64), then the fused tail
+    (evk_cmax_peer_tail_f32) sums them through its pointer table and evaluates f, g: equal to the oracle on the whole
+    stream.  (On several GPUs the buffers are symmetric memory and a barrier sits between the halves: parallel.PeerCmax.)"""
+    import ctypes
+    import torch
+    from event_utils_b200 import _lib
+    L = _lib.lib()
+    x, y, t, p = make_events(57, 500003, 180, 240, dtype=np.float64)
+    X, Y, T, P = (torch.from_numpy(a).cuda() for a in (x, y, t, p))
+    cuts = [0, 200001, 200001, 500003]
+    npix = 181 * 241
+    words = 3 * npix + 5
+    off = (3 * npix + 1) // 2 * 2
+    bufs = [torch.zeros(words, dtype=torch.float32, device="cuda") for _ in range(3)]
+    ws = torch.empty(L.evk_cmax_workspace_bytes(180, 240), dtype=torch.uint8, device="cuda")
+    vflag = _lib.VARIANT_SMEM_TILE if event_pass == "onchip" else _lib.VARIANT_VECTOR_RED
+    params, tref = (30.0, -20.0), float(t[-1])
+    for r in range(3):
+        a, b = cuts[r], cuts[r + 1]
+        _lib.check(L.evk_cmax_linvel_partial_f64(X.data_ptr() + 8 * a, Y.data_ptr() + 8 * a, T.data_ptr() + 8 * a, P.data_ptr() + 8 * a,
+                                                 b - a, 1.0, params[0], params[1], tref, 180, 240, 180, 240, _lib.CMAX_WANT_GRAD | vflag,
+                                                 bufs[r].data_ptr(), bufs[r].data_ptr() + 4 * off, ws.data_ptr(), ws.numel(), None))
+    img = (ctypes.c_void_p * 3)(*[b.data_ptr() for b in bufs])
+    oob = (ctypes.c_void_p * 3)(*[b.data_ptr() + 4 * off for b in bufs])
+    res = torch.zeros(12, dtype=torch.float64, device="cuda")
+    _lib.check(L.evk_cmax_peer_tail_f32(img, oob, 3, 181, 241, 1.0, _lib.CMAX_WANT_GRAD, res.data_ptr(), ws.data_ptr(), ws.numel(), None))
+    torch.cuda.synchronize()
+    r = res.cpu().numpy()
+    fo, go = oracle.cmax_variance(params, x, y, t, p, blur_sigma=1.0)
+    iwe, d = oracle.iwe_linvel(params, x, y, t, p, (180, 240), True)
+    assert r[4] == 0 and abs(r[0] - fo) <= 1e-5 * abs(fo)
+    assert np.abs(r[1:3] - go).max() <= 1e-5 * grad_scale(iwe, d)
+    total = sum(b[: 3 * npix].view(3, 181, 241) for b in bufs).cpu().numpy()
+    assert_close_to_max(total[0], iwe, 1e-5)
+    assert_close_to_max(total[1:], d, 1e-5)
+
+
 def test_cached_results_follow_the_data(oracle):
     """the device copy of the events and the (params -> f, g) memo are keyed on content: an in-place edit of the
     caller's arrays, or a new array that happens to reuse a freed one's address, is evaluated afresh"""
