@@ -110,7 +110,47 @@ struct evk_pipeline {
     size_t ws_bytes;
     unsigned long long *oob_dev;
     unsigned long long *oob_pinned;
+    // pageable sources: pinned bounce buffers filled by host threads (cudaMemcpyAsync from pageable memory is a
+    // single-threaded staged copy inside the driver, far below PCIe speed)
+    float *bounce[2][4];
+    int64_t bounce_events;    // capacity of one bounce slot
 };
+
+namespace {
+// is `ptr` ordinary pageable host memory (not pinned / registered / managed / device)?
+bool is_pageable(const void *ptr)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// copy k arrays of `bytes` each with a few host threads (a single memcpy stream tops out well below PCIe 5 x16)
+void parallel_copy(void *const *dst, const void *const *src, int k, size_t bytes)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    int nthreads = hw ? (int)hw : 4;
+    if (nthreads > 8) nthreads = 8;
+    const size_t total = bytes * k;
+    if (total < ((size_t)4 << 20) || nthreads <= 1) {
+        for (int a = 0; a < k; ++a) memcpy(dst[a], src[a], bytes);
+        return;
+    }
+    constexpr size_t kBlock = (size_t)1 << 20;
+    const size_t blocks_per = (bytes + kBlock - 1) / kBlock, nblocks = blocks_per * k;
+    auto work = [&](size_t first) {
+        for (size_t b = first; b < nblocks; b += (size_t)nthreads) {
+            const int a = (int)(b / blocks_per);
+            const size_t off = (b % blocks_per) * kBlock, len = (bytes - off < kBlock) ? bytes - off : kBlock;
+            memcpy((char *)dst[a] + off, (const char *)src[a] + off, len);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work, (size_t)t);
+    work(0);
+    for (auto &t : th) t.join();
+}
+}  // namespace
 
 extern "C" {
 
@@ -152,6 +192,8 @@ void evk_pipeline_destroy(evk_pipeline_t *p)
     cudaFree(p->ws);
     cudaFree(p->oob_dev);
     cudaFreeHost(p->oob_pinned);
+    for (int s = 0; s < 2; ++s)
+        for (int a = 0; a < 4; ++a) cudaFreeHost(p->bounce[s][a]);
     free(p);
 }
 
@@ -183,14 +225,34 @@ int evk_voxel_host_f32(evk_pipeline_t *p, const float *x, const float *y, const 
     const float *src[4] = {x, y, t, pol};
     int64_t done = 0;
     int k = 0;
+    // ordinary (pageable) host arrays -- what the reference's callers hand over -- go through pinned bounce buffers that
+    // a few host threads fill while the previous chunk is on the wire
+    const bool bounce = n > 0 && (is_pageable(x) || is_pageable(y) || is_pageable(t) || is_pageable(pol));
+    if (bounce && p->bounce_events < p->chunk) {
+        for (int s = 0; s < 2; ++s)
+            for (int a = 0; a < 4; ++a) {
+                cudaFreeHost(p->bounce[s][a]);
+                p->bounce[s][a] = nullptr;
+                EVK_CUDA(cudaMallocHost(&p->bounce[s][a], (size_t)p->chunk * sizeof(float)));
+            }
+        p->bounce_events = p->chunk;
+    }
     // every chunk accumulates into the same grid; chunk 0 has already been zeroed above
     const unsigned cflags = (flags & ~EVK_VARIANT_MASK) | EVK_ACCUMULATE | EVK_VARIANT_GLOBAL_RED;
     while (done < n) {
         const int s = k & 1;
         const int64_t m = (n - done < p->chunk) ? (n - done) : p->chunk;
+        const float *from[4] = {src[0] + done, src[1] + done, src[2] + done, src[3] + done};
+        if (bounce) {
+            if (k >= 2) EVK_CUDA(cudaEventSynchronize(p->copied[s]));      // the bounce slot's previous H2D has left it
+            void *dst4[4] = {p->bounce[s][0], p->bounce[s][1], p->bounce[s][2], p->bounce[s][3]};
+            const void *src4[4] = {from[0], from[1], from[2], from[3]};
+            parallel_copy(dst4, src4, 4, (size_t)m * sizeof(float));
+            for (int a = 0; a < 4; ++a) from[a] = p->bounce[s][a];
+        }
         if (k >= 2) EVK_CUDA(cudaStreamWaitEvent(p->copy, p->consumed[s], 0));
         for (int a = 0; a < 4; ++a)
-            EVK_CUDA(cudaMemcpyAsync(p->stage[s][a], src[a] + done, (size_t)m * sizeof(float), cudaMemcpyHostToDevice, p->copy));
+            EVK_CUDA(cudaMemcpyAsync(p->stage[s][a], from[a], (size_t)m * sizeof(float), cudaMemcpyHostToDevice, p->copy));
         EVK_CUDA(cudaEventRecord(p->copied[s], p->copy));
         EVK_CUDA(cudaStreamWaitEvent(p->compute, p->copied[s], 0));
         int rc = evk_voxel_f32(p->stage[s][0], p->stage[s][1], p->stage[s][2], p->stage[s][3], m, t0, dt, B, H, W,

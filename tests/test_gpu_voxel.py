@@ -160,6 +160,25 @@ def test_hot_pixels(oracle):
         assert np.abs(vp.cpu().numpy() - refp).max() <= bound, variant
 
 
+def test_host_pipeline_pageable_and_pinned(oracle):
+    """Host f32 tensors take the chunked H2D pipeline (evk_voxel_host_f32): pinned sources are copied directly, ordinary
+    pageable ones -- what the reference's callers hand over -- through pinned bounce buffers filled by host threads.
+    9 M events = three 4 M-event chunks (both bounce slots are reused), same grid either way."""
+    from event_utils_b200.representations.voxel_grid import events_to_voxel_torch
+    x, y, t, p = make_events(77, 9_000_001, 260, 346)
+    ref = oracle.voxel_f32(x, y, t, p, 5, (260, 346))
+    pageable = [torch.from_numpy(a) for a in (x, y, t, p)]
+    assert not pageable[0].is_pinned()
+    out = events_to_voxel_torch(*pageable, 5, sensor_size=(260, 346))
+    assert not out.is_cuda
+    assert_close_to_max(out.numpy(), ref, 1e-5, "pageable")
+    pinned = [a.pin_memory() for a in pageable]
+    out2 = events_to_voxel_torch(*pinned, 5, sensor_size=(260, 346))
+    assert_close_to_max(out2.numpy(), ref, 1e-5, "pinned")
+    out3 = events_to_voxel_torch(*pageable, 5, sensor_size=(260, 346))          # bounce buffers reused across calls
+    assert_close_to_max(out3.numpy(), ref, 1e-5, "pageable again")
+
+
 def test_data_loader_arrays(oracle):
     """The arrays DynamicH5Dataset.get_events hands over (hdf5_dataset.py:18-23): int16 coordinates,
     float64 absolute timestamps, float64 +-1 polarities, all numpy."""
