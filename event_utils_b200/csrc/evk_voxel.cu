@@ -40,6 +40,8 @@ struct VoxelArgs {
     float *out;  // [B][H][W]
     float *ws;   // [H*W][nq][4]
     unsigned long long *oob;
+    const unsigned *skip_if;  // AUTO with the routed kernel in play: this kernel returns at once when *skip_if != 0 (the
+                              // probe chose the routed kernel, which has already built the grid)
 };
 
 enum { SINK_SCALAR = 0, SINK_QUAD = 1, SINK_QUAD_HOT = 2 };
@@ -49,7 +51,9 @@ size_t voxel_routed_workspace_bytes(int B, int H, int W);
 bool voxel_routed_supported(int B, int H, int W);
 int launch_voxel_routed(const float *x, const float *y, const float *t, const float *p, int64_t n, int64_t head, float t0, float dt,
                         int B, int H, int W, int auto_span, float *out, void *workspace, size_t workspace_bytes,
-                        unsigned long long *oob, cudaStream_t st);
+                        unsigned long long *oob, cudaStream_t st, int probe);
+const unsigned *voxel_routed_mode_flag(void *workspace, int B, int H, int W);   // device word the probe writes: 1 = routed ran
+int64_t voxel_routed_min_events();
 
 // Per-CTA write-combining cache in front of the vector reductions (SINK_QUAD_HOT): a direct-mapped
 // {quad index -> float4 partial sum} table in shared memory, same idea as evk_hot.cu.  Real sensors
@@ -313,6 +317,7 @@ __device__ __forceinline__ void scatter_events(const VoxelArgs &A, const HotCtx 
 template <int SINK, bool BIL, int LAYOUT>
 __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_kernel(const VoxelArgs A_in)
 {
+    if (A_in.skip_if && *A_in.skip_if) return;
     VoxelArgs A = A_in;
     if (A.auto_span && A.n > 0) {
         // first / last timestamp straight from the (time-sorted) stream; AoS keeps t at offset 2
@@ -372,8 +377,9 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
 // also in quad b/3-1 (slot 3).
 template <bool ACCUM>
 __global__ void __launch_bounds__(256) voxel_fold_kernel(const float *__restrict__ ws, float *__restrict__ out,
-                                                         int64_t npix, int B, int nq)
+                                                         int64_t npix, int B, int nq, const unsigned *skip_if = nullptr)
 {
+    if (skip_if && *skip_if) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += stride) {
         const float4 *src = reinterpret_cast<const float4 *>(ws) + pix * nq;
@@ -545,9 +551,15 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
     // AUTO: big streams take the vector-red path with the adaptive hot-pixel cache; small ones the
     // scalar path (no workspace, no fold).  SMEM_TILE forces the cache on, VECTOR_RED leaves it out.
     bool hot = false;
+    bool routed_probe = false;
     if (variant == EVK_VARIANT_AUTO) {
         variant = (A.n >= (int64_t)1 << 20 && workspace != nullptr) ? EVK_VARIANT_VECTOR_RED : EVK_VARIANT_GLOBAL_RED;
         hot = variant == EVK_VARIANT_VECTOR_RED && !bil;
+        // large plain streams: a probe looks at a sample of the events on the device and picks the routed kernel (unit
+        // polarities, no hot pixels) or the vector-reduction kernel below; the one not chosen returns at once
+        routed_probe = A.n >= voxel_routed_min_events() && !bil && !A.negpos && !(flags & EVK_NO_FOLD) && !accum && layout == LAYOUT_SOA4 &&
+                       voxel_routed_supported(A.B, A.H, A.W) && workspace != nullptr &&
+                       workspace_bytes >= voxel_routed_workspace_bytes(A.B, A.H, A.W) + (size_t)npix * quads_for_bins(A.B) * 16;
     } else if (variant == EVK_VARIANT_SMEM_TILE && !bil) {
         variant = EVK_VARIANT_VECTOR_RED;
         hot = true;
@@ -566,7 +578,7 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
         if (!accum) EVK_CUDA(cudaMemsetAsync(A.out, 0, (size_t)npix * A.B * sizeof(float), st));
         if (A.n == 0) return EVK_OK;
         return launch_voxel_routed(A.x, A.y, A.t, A.p, A.n, A.head, A.t0, A.dt, A.B, A.H, A.W, A.auto_span, A.out, workspace,
-                                   workspace_bytes, A.oob, st);
+                                   workspace_bytes, A.oob, st, 0);
     }
     if (no_fold) {
         // the caller folds (and reduces across GPUs) itself: the sums stay in the quad workspace
@@ -577,6 +589,17 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
     if (variant != EVK_VARIANT_VECTOR_RED && variant != EVK_VARIANT_GLOBAL_RED) {
         set_error("evk_voxel: variant 0x%x not available for this entry point", variant);
         return EVK_E_UNSUPPORTED;
+    }
+    if (routed_probe) {
+        // the routed kernel's rings come first in the workspace, the quad workspace of the fallback after them
+        EVK_CUDA(cudaMemsetAsync(A.out, 0, (size_t)npix * A.B * sizeof(float), st));
+        int rc = launch_voxel_routed(A.x, A.y, A.t, A.p, A.n, A.head, A.t0, A.dt, A.B, A.H, A.W, A.auto_span, A.out, workspace,
+                                     workspace_bytes, A.oob, st, 1);
+        if (rc) return rc;
+        A.skip_if = voxel_routed_mode_flag(workspace, A.B, A.H, A.W);
+        const size_t roff = (voxel_routed_workspace_bytes(A.B, A.H, A.W) + 255) & ~(size_t)255;
+        workspace = static_cast<char *>(workspace) + roff;
+        workspace_bytes -= roff;
     }
     const int sink = (variant == EVK_VARIANT_VECTOR_RED) ? SINK_QUAD : SINK_SCALAR;
     A.nq = quads_for_bins(A.B);
@@ -626,8 +649,8 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
                 const float *wsg = A.ws + (size_t)g * npix * A.nq * 4;
                 float *og = A.out + (size_t)g * npix * A.B;
                 if (g) prof_count(1);
-                if (accum) voxel_fold_kernel<true><<<grid, 256, 0, st>>>(wsg, og, npix, A.B, A.nq);
-                else voxel_fold_kernel<false><<<grid, 256, 0, st>>>(wsg, og, npix, A.B, A.nq);
+                if (accum) voxel_fold_kernel<true><<<grid, 256, 0, st>>>(wsg, og, npix, A.B, A.nq, A.skip_if);
+                else voxel_fold_kernel<false><<<grid, 256, 0, st>>>(wsg, og, npix, A.B, A.nq, A.skip_if);
             }
         }
         EVK_CUDA(cudaGetLastError());
@@ -656,8 +679,9 @@ size_t evk_voxel_workspace_bytes(int B, int H, int W, unsigned flags)
     size_t need = (size_t)H * W * evk::quads_for_bins(B) * 4 * sizeof(float);      // temporal quads per pixel
     const unsigned v = evk::variant_of(flags);
     if ((v == EVK_VARIANT_AUTO || v == EVK_VARIANT_ROUTED) && evk::voxel_routed_supported(B, H, W)) {
-        const size_t r = evk::voxel_routed_workspace_bytes(B, H, W);   // the routed kernel's rings
-        if (r > need) need = r;
+        // the routed kernel's rings, followed (AUTO) by the quad workspace of the kernel the probe may choose instead
+        const size_t r = (evk::voxel_routed_workspace_bytes(B, H, W) + 255) & ~(size_t)255;
+        need = (v == EVK_VARIANT_AUTO) ? r + need : (r > need ? r : need);
     }
     return need;
 }
