@@ -48,7 +48,7 @@ def test_config2_voxel_50m_every_variant_cell_by_cell(oracle, voxel_stream):
     assert ref.shape == (5, 480, 640) and abs(float(ref.astype(np.float64).sum()) - float(p.astype(np.float64).sum())) <= 2.0
     X, Y, T, P = (torch.from_numpy(a).cuda() for a in (x, y, t, p))
     worst = {}
-    for variant in (None, "global_red", "vector_red", "warp_agg", "smem_cache", "routed"):
+    for variant in (None, "global_red", "vector_red", "smem_cache", "routed"):
         if variant == "routed" and not hasattr(eu._lib, "VARIANT_ROUTED"):
             continue
         eu.config.variant = variant
