@@ -76,8 +76,13 @@ void prof_count(int launches)
     if (g_prof_on) g_launches += launches;
 }
 
+// scopes nest: only the outermost one is timed (a caller that brackets two alternative kernels -- the probe-selected voxel
+// kernels -- wants ONE duration for the pair)
+static thread_local int g_prof_depth = 0;
+
 ProfScope::ProfScope(cudaStream_t s) : st(s), slot(-1)
 {
+    if (g_prof_depth++ > 0) return;
     if (!g_prof_on || g_prof_used >= kProfSlots) return;
     if (g_prof_used >= g_prof_created) {
         if (cudaEventCreate(&g_prof_ev[g_prof_created][0]) != cudaSuccess) return;
@@ -90,6 +95,7 @@ ProfScope::ProfScope(cudaStream_t s) : st(s), slot(-1)
 
 ProfScope::~ProfScope()
 {
+    --g_prof_depth;
     if (slot >= 0) cudaEventRecord(g_prof_ev[slot][1], st);
 }
 

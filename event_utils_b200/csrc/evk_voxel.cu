@@ -590,7 +590,10 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
         set_error("evk_voxel: variant 0x%x not available for this entry point", variant);
         return EVK_E_UNSUPPORTED;
     }
+    // probe mode: ONE timed scope for "probe + the kernel it selects" (the inner scopes of the two alternatives nest in it)
+    struct OptScope { ProfScope *p = nullptr; ~OptScope() { delete p; } } outer;
     if (routed_probe) {
+        outer.p = new ProfScope(st);
         // the routed kernel's rings come first in the workspace, the quad workspace of the fallback after them
         EVK_CUDA(cudaMemsetAsync(A.out, 0, (size_t)npix * A.B * sizeof(float), st));
         int rc = launch_voxel_routed(A.x, A.y, A.t, A.p, A.n, A.head, A.t0, A.dt, A.B, A.H, A.W, A.auto_span, A.out, workspace,
@@ -638,6 +641,8 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
 #undef EVK_LAUNCH
         EVK_CUDA(cudaGetLastError());
     }
+    delete outer.p;
+    outer.p = nullptr;
     if (sink == SINK_QUAD && !no_fold) {
         const int grid = grid_simple(npix, 256);
         prof_count(1);
