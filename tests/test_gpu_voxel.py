@@ -160,6 +160,44 @@ def test_hot_pixels(oracle):
         assert np.abs(vp.cpu().numpy() - refp).max() <= bound, variant
 
 
+def test_auto_probe_picks_between_routed_and_vector_red():
+    """AUTO with the routed kernel enabled (EVK_VOXEL_ROUTED_MIN, read once at library load -> a subprocess): a device-side
+    probe looks at a sample of the stream; unit-polarity uniform streams take the routed kernel, general polarities and
+    hot-pixel streams the vector-reduction kernel; the kernel not chosen returns at once.  All three equal the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys
+import numpy as np, torch
+sys.path.insert(0, %r)
+from event_utils_b200.representations.voxel_grid import events_to_voxel_torch
+from oracle import evk_oracle as O
+O.build()
+rng = np.random.default_rng(3)
+n, H, W = 3_000_000, 260, 346
+x = (rng.random(n) * (W - 1)).astype(np.float32); y = (rng.random(n) * (H - 1)).astype(np.float32)
+t = np.sort(rng.random(n)).astype(np.float32)
+cases = {"unit": (x, y, (rng.integers(0, 2, n) * 2 - 1).astype(np.float32)),
+         "general": (x, y, rng.standard_normal(n).astype(np.float32))}
+xh, yh = x.copy(), y.copy()
+hot = rng.random(n) < 0.2
+xh[hot], yh[hot] = 17.0, 33.0
+cases["hot"] = (xh, yh, cases["unit"][2])
+for name, (cx, cy, cp) in cases.items():
+    ref = O.voxel_f32(cx, cy, t, cp, 5, (H, W))
+    out = events_to_voxel_torch(*(torch.from_numpy(a).cuda() for a in (cx, cy, t, cp)), 5, sensor_size=(H, W)).cpu().numpy()
+    err = np.abs(out - ref).max() / np.abs(ref).max()
+    assert err <= 1e-5, (name, err)
+    print(name, "ok %%.2e" %% err)
+''' % root
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600, cwd=root,
+                         env=dict(os.environ, EVK_VOXEL_ROUTED_MIN="1000000"))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "hot ok" in out.stdout
+
+
 def test_host_pipeline_pageable_and_pinned(oracle):
     """Host f32 tensors take the chunked H2D pipeline (evk_voxel_host_f32): pinned sources are copied directly, ordinary
     pageable ones -- what the reference's callers hand over -- through pinned bounce buffers filled by host threads.
