@@ -252,6 +252,49 @@ def test_fused_peer_tail_with_emulated_ranks(oracle, event_pass):
     assert_close_to_max(total[1:], d, 1e-5)
 
 
+def _peer_cmax_worker(rank, world, port, out_dir):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from event_utils_b200.parallel import PeerCmax, cmax_variance_sharded, shard_bounds
+    x, y, t, p = make_events(61, 700001, 180, 240, dtype=np.float64)
+    lo, hi = shard_bounds(len(x), world, rank)
+    sh = [torch.from_numpy(a[lo:hi]).cuda() for a in (x, y, t, p)]
+    pc = PeerCmax(torch.device("cuda", rank))
+    rows = []
+    for k, prm in enumerate([(30.0, -20.0), (31.0, -20.0), (-400.0, 900.0), (30.0, -20.0)]):     # buffers alternate and are reused
+        f, g = pc(prm, *sh, (180, 240), 1.0, t_ref=float(t[-1]))
+        fn, gn = cmax_variance_sharded(prm, *sh, (180, 240), 1.0, t_ref=float(t[-1]))
+        rows.append([f, g[0], g[1], fn, gn[0], gn[1]])
+    np.save(os.path.join(out_dir, "pcmax%d.npy" % rank), np.array(rows))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(__import__("torch").cuda.device_count() < 2, reason="needs two GPUs")
+def test_peer_cmax_two_gpus(oracle, tmp_path):
+    """parallel.PeerCmax on two real GPUs: the all-reduce of the partial images fused into the objective kernel over
+    NVLink peer memory == the NCCL formulation == the oracle on the whole stream, bit-identical on both ranks."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_peer_cmax_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "pcmax0.npy"), np.load(tmp_path / "pcmax1.npy")
+    assert np.array_equal(a[:, :3], b[:, :3])
+    x, y, t, p = make_events(61, 700001, 180, 240, dtype=np.float64)
+    for row, prm in zip(a, [(30.0, -20.0), (31.0, -20.0), (-400.0, 900.0), (30.0, -20.0)]):
+        fo, go = oracle.cmax_variance(prm, x, y, t, p, blur_sigma=1.0)
+        iwe, d = oracle.iwe_linvel(prm, x, y, t, p, (180, 240), True)
+        assert abs(row[0] - fo) <= 1e-5 * abs(fo) and abs(row[3] - fo) <= 1e-5 * abs(fo)
+        assert np.abs(row[1:3] - go).max() <= 1e-5 * grad_scale(iwe, d)
+    assert np.array_equal(a[0, :3], a[3, :3])
+
+
 def test_cached_results_follow_the_data(oracle):
     """the device copy of the events and the (params -> f, g) memo are keyed on content: an in-place edit of the
     caller's arrays, or a new array that happens to reuse a freed one's address, is evaluated afresh"""
