@@ -10,7 +10,12 @@ from conftest import assert_close_to_max, golden, make_events
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = ["global_red", "vector_red", "smem_cache", "routed", None]
+import os as _os
+
+# the routed kernel spins on inter-SM queues: a bug there is a hang, not a failure -- tools/try_routed.py is its gate
+# (run it under `timeout` first; EVK_TEST_ROUTED=0 keeps the variant out of this suite)
+ROUTED = ["routed"] if _os.environ.get("EVK_TEST_ROUTED", "1") != "0" else []
+VARIANTS = ["global_red", "vector_red", "smem_cache"] + ROUTED + [None]
 
 
 @pytest.fixture(autouse=True)
@@ -160,6 +165,7 @@ def test_hot_pixels(oracle):
         assert np.abs(vp.cpu().numpy() - refp).max() <= bound, variant
 
 
+@pytest.mark.skipif(not ROUTED, reason="EVK_TEST_ROUTED=0")
 def test_auto_probe_picks_between_routed_and_vector_red():
     """AUTO with the routed kernel enabled (EVK_VOXEL_ROUTED_MIN, read once at library load -> a subprocess): a device-side
     probe looks at a sample of the stream; unit-polarity uniform streams take the routed kernel, general polarities and
