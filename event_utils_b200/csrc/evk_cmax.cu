@@ -447,6 +447,20 @@ __device__ __forceinline__ void block_add(double v, double *dst)
     }
 }
 
+// CTA-wide sum in a FIXED order (shuffle tree, then the 8 warp sums left to right); valid on thread 0
+__device__ __forceinline__ double block_sum_ordered(double v)
+{
+    __shared__ double part2[8];
+    const int lt = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((lt & 31) == 0) part2[lt >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (lt == 0) for (int w = 0; w < 8; ++w) s += part2[w];
+    return s;
+}
+
 // Blocks -> planar images.  Block (y,x) holds the 2x2 footprint anchored at (y,x) in tap order
 // TL,TR,BL,BR, so pixel (y,x) collects TL of block (y,x), TR of (y,x-1), BL of (y-1,x) and BR of
 // (y-1,x-1), over all replicas.
@@ -747,7 +761,7 @@ __global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel_t(c
                                                                               double mix_a, double mix_b, float *__restrict__ iwe_out,
                                                                               float *__restrict__ diwe_out, double *sums,
                                                                               unsigned *ticket, const unsigned long long *oob,
-                                                                              double *result)
+                                                                              double *result, double *partials = nullptr)
 {
     __shared__ float tileI[(kTileY + 2 * kFusedMaxR) * (kTileX + 2 * kFusedMaxR)];
     __shared__ float tileT[kTileY * (kTileX + 2 * kFusedMaxR)];
@@ -799,24 +813,42 @@ __global__ void __launch_bounds__(kTileY *kTileX) cmax_fused_var_tail_kernel_t(c
     }
     if (!inside) { g = 0.0; vi = 0.f; }
     // 4. the seven sums (same slots as the separate kernels)
-    block_add((double)vi, sums + 0);
-    block_add(g, sums + 1);
-    block_add(g * g, sums + 2);
-    block_add(g * (double)d0, sums + 3);
-    block_add(g * (double)d1, sums + 4);
-    block_add((double)d0, sums + 5);
-    block_add((double)d1, sums + 6);
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x, nctas = gridDim.x * gridDim.y;
+    if (PEER) {
+        // sharded evaluation: every rank must arrive at bit-identical f and g (a BFGS driver runs replicated), so the sums
+        // are formed in a fixed order: per-CTA partials to memory, the last CTA adds them up CTA by CTA
+        const double v[7] = {(double)vi, g, g * g, g * (double)d0, g * (double)d1, (double)d0, (double)d1};
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const double sk = block_sum_ordered(v[k]);
+            if (tid == 0) partials[(size_t)cta * 8 + k] = sk;
+        }
+    } else {
+        block_add((double)vi, sums + 0);
+        block_add(g, sums + 1);
+        block_add(g * g, sums + 2);
+        block_add(g * (double)d0, sums + 3);
+        block_add(g * (double)d1, sums + 4);
+        block_add((double)d0, sums + 5);
+        block_add((double)d1, sums + 6);
+    }
     // 5. last CTA writes the result
     __shared__ bool last;
     if (tid == 0) {
         __threadfence();
-        last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+        last = atomicAdd(ticket, 1u) == (unsigned)nctas - 1;
     }
     __syncthreads();
     if (last && tid == 0) {
         __threadfence();
         double s[7];
-        for (int k = 0; k < 7; ++k) s[k] = atomicAdd(sums + k, 0.0);   // read through L2
+        if (PEER) {
+            for (int k = 0; k < 7; ++k) s[k] = 0.0;
+            for (int c = 0; c < nctas; ++c)
+                for (int k = 0; k < 7; ++k) s[k] += __ldcg(partials + (size_t)c * 8 + k);
+        } else {
+            for (int k = 0; k < 7; ++k) s[k] = atomicAdd(sums + k, 0.0);   // read through L2
+        }
         const double P = (double)Hc * (double)Wc;
         const double mean_g = s[1] / P, var = s[2] / P - mean_g * mean_g, mu = s[0] / P;
         const double g0 = -2.0 * (s[3] - mu * s[5]) / P, g1 = -2.0 * (s[4] - mu * s[6]) / P;
@@ -1180,7 +1212,7 @@ int evk_cmax_peer_tail_f32(const float *const *peer_images, const unsigned long 
     prof_count(1);
     dim3 tgrid((Wc + kTileX - 1) / kTileX, (Hc + kTileY - 1) / kTileY), tblock(kTileX, kTileY);
     cmax_fused_var_tail_kernel_t<true><<<tgrid, tblock, 0, st>>>(P, nullptr, nullptr, 1, Hc, Wc, taps, do_blur, (flags & EVK_CMAX_WANT_GRAD) ? 1 : 0,
-                                                                  mix_a, mix_b, nullptr, nullptr, ws.sums, ws.gmax, ws.oob, result);
+                                                                  mix_a, mix_b, nullptr, nullptr, ws.sums, ws.gmax, ws.oob, result, ws.w);
     EVK_CUDA(cudaGetLastError());
     return EVK_OK;
 }
