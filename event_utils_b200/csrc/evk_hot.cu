@@ -46,15 +46,21 @@ constexpr unsigned kHotBias = 0x80000000u;
 // A float-mode cell is biased by 2^31; the returning atomic tells the thread whether ITS add wrapped the 32 bits and that
 // thread carries +-2^(32-F) to the global image, so the table can never overflow silently.
 constexpr int kHotFixNearest = 10, kHotFixBilinear = 22;
+// bilinear: ONE table entry per 2x2 footprint -- key = the anchor cell, value = the four taps {TL, TR, BL, BR} -- so an event
+// is one lookup and four adjacent native atomics instead of four lookups; flushed as one vector reduction into the block
+// workspace (the layout of the uncontended path).  4096 slots (2048 two-way sets): 16 KB keys + 64 KB values.
+constexpr int kHotLog2B = 12;
+constexpr int kHotSlotsB = 1 << kHotLog2B;
 
 // `gs` = element stride of a cell in the global target (4 when the target is the TL slot of a block)
 __device__ __forceinline__ void global_add(float *out, unsigned cell, float v, int gs) { red_add(out + (size_t)cell * gs, v); }
 __device__ __forceinline__ void global_add(unsigned *out, unsigned cell, unsigned v, int gs) { red_add_u32(out + (size_t)cell * gs, v); }
 
 // find (or claim) the cell's slot in its two-way set; -1 = both ways belong to other cells
+template <int LOG2 = kHotLog2>
 __device__ __forceinline__ int hot_slot(unsigned *keys, unsigned cell)
 {
-    const unsigned s0 = ((cell * 2654435761u) >> (32 - (kHotLog2 - 1))) * 2u;
+    const unsigned s0 = ((cell * 2654435761u) >> (32 - (LOG2 - 1))) * 2u;
     const uint2 k = *reinterpret_cast<const uint2 *>(keys + s0);
     if (k.x == cell) return (int)s0;
     if (k.y == cell) return (int)s0 + 1;
@@ -141,14 +147,38 @@ __device__ __forceinline__ void hot_event(const HotArgs &A, unsigned *keys, unsi
             // uncontended stream: the whole footprint as ONE vector reduction into its block
             if (v00 != 0.0f || v01 != 0.0f || v10 != 0.0f || v11 != 0.0f)
                 red_add4(A.ws + ((size_t)r0 + x0) * 4, make_float4(v00, v01, v10, v11));
-        } else if (CACHE && fabsf(w) <= 1.0f) {
+        } else if (CACHE && fabsf(w) <= 1.0f && x1 == x0 + 1 && y1 == y0 + 1) {
+            if (w == 0.0f) return;
             const float S = (float)(1 << kHotFixBilinear);
-            const int q00 = __float2int_rn(__fmul_rn(v00, S)), q01 = __float2int_rn(__fmul_rn(v01, S));
-            const int q10 = __float2int_rn(__fmul_rn(v10, S)), q11 = __float2int_rn(__fmul_rn(v11, S));
-            if (q00) hot_add_fixed<kHotFixBilinear>(keys, vals, gf, r0 + x0, v00, (unsigned)q00, gs);
-            if (q01) hot_add_fixed<kHotFixBilinear>(keys, vals, gf, r0 + x1, v01, (unsigned)q01, gs);
-            if (q10) hot_add_fixed<kHotFixBilinear>(keys, vals, gf, r1 + x0, v10, (unsigned)q10, gs);
-            if (q11) hot_add_fixed<kHotFixBilinear>(keys, vals, gf, r1 + x1, v11, (unsigned)q11, gs);
+            const unsigned q[4] = {(unsigned)__float2int_rn(__fmul_rn(v00, S)), (unsigned)__float2int_rn(__fmul_rn(v01, S)),
+                                   (unsigned)__float2int_rn(__fmul_rn(v10, S)), (unsigned)__float2int_rn(__fmul_rn(v11, S))};
+            const unsigned cell = r0 + x0;                      // the footprint's anchor
+            const int slot = hot_slot<kHotLog2B>(keys, cell);
+            if (slot < 0) {
+                if (A.ws) red_add4(A.ws + (size_t)cell * 4, make_float4(v00, v01, v10, v11));
+                else { red_add(A.out + cell, v00); red_add(A.out + cell + 1, v01); red_add(A.out + r1 + x0, v10); red_add(A.out + r1 + x1, v11); }
+                return;
+            }
+            unsigned *vp = vals + 4 * slot;
+            const unsigned o0 = hot_atoms_ret(vp + 0, q[0]), o1 = hot_atoms_ret(vp + 1, q[1]);
+            const unsigned o2 = hot_atoms_ret(vp + 2, q[2]), o3 = hot_atoms_ret(vp + 3, q[3]);
+            const unsigned o[4] = {o0, o1, o2, o3};
+            unsigned any = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const unsigned nw = o[k] + q[k]; any |= (o[k] ^ nw) & ~(nw ^ q[k]); }
+            if (any >> 31) {
+                const unsigned cells[4] = {cell, cell + 1, r1 + x0, r1 + x1};
+                const float carry = (float)(1u << (32 - kHotFixBilinear));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned nw = o[k] + q[k];
+                    if (((o[k] ^ nw) & ~(nw ^ q[k])) >> 31) {
+                        // the wrapped tap's 2^32 goes to the global image: tap k of block `cell` (or its own pixel without blocks)
+                        if (A.ws) red_add(A.ws + (size_t)cell * 4 + k, (int)q[k] >= 0 ? carry : -carry);
+                        else red_add(A.out + cells[k], (int)q[k] >= 0 ? carry : -carry);
+                    }
+                }
+            }
         } else {
             if (v00 != 0.0f) global_add(gf, r0 + x0, v00, gs);
             if (v01 != 0.0f) global_add(gf, r0 + x1, v01, gs);
@@ -183,8 +213,10 @@ __device__ __forceinline__ void hot_loop(const HotArgs &A, unsigned *keys, unsig
 template <int MODE>
 __global__ void __launch_bounds__(kHotThreads) image_hot_kernel(const HotArgs A)
 {
-    extern __shared__ __align__(16) unsigned hot_smem[];      // [kHotSlots] keys, [kHotSlots] values
-    unsigned *keys = hot_smem, *vals = hot_smem + kHotSlots;
+    extern __shared__ __align__(16) unsigned hot_smem[];      // [slots] keys, [slots] (bilinear: [slots][4]) values
+    constexpr int kSlots = (MODE == HOT_BILINEAR) ? kHotSlotsB : kHotSlots;
+    constexpr int kValsPer = (MODE == HOT_BILINEAR) ? 4 : 1;
+    unsigned *keys = hot_smem, *vals = hot_smem + kSlots;
     const int64_t tid = (int64_t)blockIdx.x * kHotThreads + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * kHotThreads;
 
@@ -203,7 +235,8 @@ __global__ void __launch_bounds__(kHotThreads) image_hot_kernel(const HotArgs A)
     }
     const unsigned init = (MODE == HOT_COUNT) ? 0u : kHotBias;
     if (use_cache) {   // only CTAs that will use the table pay for initialising it
-        for (int s = threadIdx.x; s < kHotSlots; s += kHotThreads) { keys[s] = kEmpty; vals[s] = init; }
+        for (int s = threadIdx.x; s < kSlots; s += kHotThreads) keys[s] = kEmpty;
+        for (int s = threadIdx.x; s < kSlots * kValsPer; s += kHotThreads) vals[s] = init;
         __syncthreads();
     }
 
@@ -217,11 +250,22 @@ __global__ void __launch_bounds__(kHotThreads) image_hot_kernel(const HotArgs A)
         float *gf = (MODE == HOT_BILINEAR && A.ws) ? A.ws : A.out;
         const int gs = (MODE == HOT_BILINEAR && A.ws) ? 4 : 1;
         const float inv = 1.0f / (float)(1 << (MODE == HOT_BILINEAR ? kHotFixBilinear : kHotFixNearest));
-        for (int s = threadIdx.x; s < kHotSlots; s += kHotThreads) {
-            const unsigned k = keys[s], v = vals[s];
-            if (k == kEmpty || v == init) continue;
-            if (MODE == HOT_COUNT) red_add_u32(A.out_u32 + k, v);
-            else global_add(gf, k, __fmul_rn((float)(int)(v - kHotBias), inv), gs);
+        for (int s = threadIdx.x; s < kSlots; s += kHotThreads) {
+            const unsigned k = keys[s];
+            if (k == kEmpty) continue;
+            if (MODE == HOT_BILINEAR) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(vals + 4 * s);
+                const float4 f = make_float4(__fmul_rn((float)(int)(v.x - kHotBias), inv), __fmul_rn((float)(int)(v.y - kHotBias), inv),
+                                             __fmul_rn((float)(int)(v.z - kHotBias), inv), __fmul_rn((float)(int)(v.w - kHotBias), inv));
+                if (f.x == 0.0f && f.y == 0.0f && f.z == 0.0f && f.w == 0.0f) continue;
+                if (A.ws) red_add4(A.ws + (size_t)k * 4, f);
+                else { red_add(A.out + k, f.x); red_add(A.out + k + 1, f.y); red_add(A.out + k + A.W, f.z); red_add(A.out + k + A.W + 1, f.w); }
+            } else {
+                const unsigned v = vals[s];
+                if (v == init) continue;
+                if (MODE == HOT_COUNT) red_add_u32(A.out_u32 + k, v);
+                else global_add(gf, k, __fmul_rn((float)(int)(v - kHotBias), inv), gs);
+            }
         }
     }
     flush_oob(A.oob, oob);
@@ -230,7 +274,7 @@ __global__ void __launch_bounds__(kHotThreads) image_hot_kernel(const HotArgs A)
 template <int MODE>
 static int launch_hot_mode(const HotArgs &A, cudaStream_t st)
 {
-    const size_t smem = (size_t)kHotSlots * 2 * sizeof(unsigned);
+    const size_t smem = (MODE == HOT_BILINEAR) ? (size_t)kHotSlotsB * 5 * sizeof(unsigned) : (size_t)kHotSlots * 2 * sizeof(unsigned);
     EVK_CUDA(cudaFuncSetAttribute(image_hot_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     image_hot_kernel<MODE><<<grid_for(image_hot_kernel<MODE>, kHotThreads, A.n, kHotThreads * 16, smem), kHotThreads, smem, st>>>(A);
     return EVK_OK;
