@@ -128,9 +128,15 @@ bool is_pageable(const void *ptr)
 // copy k arrays of `bytes` each with a few host threads (a single memcpy stream tops out well below PCIe 5 x16)
 void parallel_copy(void *const *dst, const void *const *src, int k, size_t bytes)
 {
-    unsigned hw = std::thread::hardware_concurrency();
-    int nthreads = hw ? (int)hw : 4;
-    if (nthreads > 8) nthreads = 8;
+    // a quarter of the hardware threads, at most 24 (a memcpy thread moves ~5-8 GB/s; PCIe 5 x16 takes ~55 GB/s; the process
+    // may be bound to one NUMA node); EVK_HOST_COPY_THREADS overrides
+    static int nthreads = 0;
+    if (nthreads == 0) {
+        const char *e = getenv("EVK_HOST_COPY_THREADS");
+        unsigned hw = std::thread::hardware_concurrency();
+        int v = (e && *e) ? atoi(e) : (hw ? (int)(hw / 4) : 4);
+        nthreads = v < 1 ? 1 : (v > 24 ? 24 : v);
+    }
     const size_t total = bytes * k;
     if (total < ((size_t)4 << 20) || nthreads <= 1) {
         for (int a = 0; a < k; ++a) memcpy(dst[a], src[a], bytes);

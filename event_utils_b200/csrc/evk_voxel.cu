@@ -66,26 +66,58 @@ constexpr unsigned kVoxEmpty = 0xffffffffu;
 
 struct HotCtx {
     unsigned *keys;
-    float4 *vals;
+    uint4 *vals;        // biased 2^22 fixed point (round 2: native ATOMS.ADD; f32 shared-memory adds are CAS loops on sm_100a)
     bool on;
 };
 
+constexpr int kVoxFixBits = 22;
+constexpr unsigned kVoxBias = 0x80000000u;
+
+__device__ __forceinline__ unsigned vox_atoms_ret(unsigned *cell, unsigned v)
+{
+    unsigned old;
+    asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(cell)), "r"(v));
+    return old;
+}
+
+// two-way set-associative {quad index -> four fixed-point partial sums}; values the scale cannot carry (|v| > 1, NaN, inf)
+// and quads whose set is taken go straight to L2.  A wrapped cell is carried out by the thread that wrapped it (the scheme
+// of evk_cmax.cu / evk_hot.cu), so the table cannot overflow whatever the hot-pixel load.
 __device__ __forceinline__ void hot_add4(const HotCtx &hc, float *ws_base, float *addr16, float4 v)
 {
-    if (hc.on) {
+    if (hc.on && fabsf(v.x) <= 1.0f && fabsf(v.y) <= 1.0f && fabsf(v.z) <= 1.0f && fabsf(v.w) <= 1.0f) {
         const unsigned cell = (unsigned)((addr16 - ws_base) >> 2);
-        const unsigned slot = (cell * 2654435761u) >> (32 - kVoxHotLog2);
-        unsigned k = hc.keys[slot];
-        if (k == kVoxEmpty) {
-            const unsigned old = atomicCAS(&hc.keys[slot], kVoxEmpty, cell);
-            k = (old == kVoxEmpty) ? cell : old;
+        const unsigned s0 = ((cell * 2654435761u) >> (32 - (kVoxHotLog2 - 1))) * 2u;
+        int slot = -1;
+        const uint2 k = *reinterpret_cast<const uint2 *>(hc.keys + s0);
+        if (k.x == cell) slot = (int)s0;
+        else if (k.y == cell) slot = (int)s0 + 1;
+        else {
+            if (k.x == kVoxEmpty) {
+                const unsigned old = atomicCAS(hc.keys + s0, kVoxEmpty, cell);
+                if (old == kVoxEmpty || old == cell) slot = (int)s0;
+            }
+            if (slot < 0) {
+                const unsigned k1 = *(volatile unsigned *)(hc.keys + s0 + 1);
+                if (k1 == cell) slot = (int)s0 + 1;
+                else if (k1 == kVoxEmpty) {
+                    const unsigned old = atomicCAS(hc.keys + s0 + 1, kVoxEmpty, cell);
+                    if (old == kVoxEmpty || old == cell) slot = (int)s0 + 1;
+                }
+            }
         }
-        if (k == cell) {
-            float *acc = reinterpret_cast<float *>(&hc.vals[slot]);
-            if (v.x != 0.0f) atomicAdd(acc + 0, v.x);
-            if (v.y != 0.0f) atomicAdd(acc + 1, v.y);
-            if (v.z != 0.0f) atomicAdd(acc + 2, v.z);
-            if (v.w != 0.0f) atomicAdd(acc + 3, v.w);
+        if (slot >= 0) {
+            unsigned *acc = reinterpret_cast<unsigned *>(&hc.vals[slot]);
+            const float S = (float)(1 << kVoxFixBits);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned q = (unsigned)__float2int_rn(__fmul_rn(vv[j], S));
+                if (q == 0u) continue;
+                const unsigned old = vox_atoms_ret(acc + j, q), nw = old + q;
+                if (((old ^ nw) & ~(nw ^ q)) >> 31)
+                    red_add(addr16 + j, (int)q >= 0 ? (float)(1u << (32 - kVoxFixBits)) : -(float)(1u << (32 - kVoxFixBits)));
+            }
             return;
         }
     }
@@ -334,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
 
     // write-combining cache (SINK_QUAD_HOT only; the arrays vanish from the other instantiations)
     __shared__ unsigned hot_keys[SINK == SINK_QUAD_HOT ? kVoxHotSlots : 1];
-    __shared__ float4 hot_vals[SINK == SINK_QUAD_HOT ? kVoxHotSlots : 1];
+    __shared__ uint4 hot_vals[SINK == SINK_QUAD_HOT ? kVoxHotSlots : 1];
     HotCtx hc{hot_keys, hot_vals, false};
     if (SINK == SINK_QUAD_HOT) {
         hc.on = A.hot_force != 0;
@@ -352,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
             hc.on = hot_dups * 64 > kThreads;  // > 4 of 256 lanes collide inside their warp (uniform streams: ~0.03)
         }
         if (hc.on) {   // the table is only initialised (40 KB of stores) by CTAs that will use it
-            for (int s = threadIdx.x; s < kVoxHotSlots; s += kThreads) { hot_keys[s] = kVoxEmpty; hot_vals[s] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            for (int s = threadIdx.x; s < kVoxHotSlots; s += kThreads) { hot_keys[s] = kVoxEmpty; hot_vals[s] = make_uint4(kVoxBias, kVoxBias, kVoxBias, kVoxBias); }
             __syncthreads();
         }
     }
@@ -366,8 +398,12 @@ __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_ke
         if (hc.on)
             for (int s = threadIdx.x; s < kVoxHotSlots; s += kThreads) {
                 const unsigned k = hot_keys[s];
-                const float4 v = hot_vals[s];
-                if (k != kVoxEmpty && (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f)) red_add4(A.ws + (size_t)k * 4, v);
+                if (k == kVoxEmpty) continue;
+                const uint4 u = hot_vals[s];
+                const float inv = 1.0f / (float)(1 << kVoxFixBits);
+                const float4 v = make_float4(__fmul_rn((float)(int)(u.x - kVoxBias), inv), __fmul_rn((float)(int)(u.y - kVoxBias), inv),
+                                             __fmul_rn((float)(int)(u.z - kVoxBias), inv), __fmul_rn((float)(int)(u.w - kVoxBias), inv));
+                if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) red_add4(A.ws + (size_t)k * 4, v);
             }
     }
     flush_oob(A.oob, oob);
