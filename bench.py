@@ -536,7 +536,7 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
                          "traffic_source": "profiles/ncu_summary.json (dram__bytes_read+write of this kernel from the committed ncu --set full capture; NOT measured in this run)",
-                         "kernel": "voxel_scatter_kernel<QUAD_HOT> (one red.global.add.v4.f32 per event; adaptive hot-pixel cache, off for this uniform stream)",
+                         "kernel": "voxel_scatter_kernel<QUAD> (one red.global.add.v4.f32 per event), chosen over the hot-pixel-table instantiation by the launch-level contention probe; the timed scope covers probe + both launches",
                          "kernel_ms": k_ms, "launches_timed": int(ktimed.value),
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "step_frac": (alg_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak,

@@ -40,6 +40,7 @@ struct VoxelArgs {
     float *out;  // [B][H][W]
     float *ws;   // [H*W][nq][4]
     unsigned long long *oob;
+    const unsigned *skip_unless;  // launch-level choice between the plain and the hot-pixel instantiation: return unless *skip_unless != 0
     const unsigned *skip_if;  // AUTO with the routed kernel in play: this kernel returns at once when *skip_if != 0 (the
                               // probe chose the routed kernel, which has already built the grid)
 };
@@ -350,6 +351,7 @@ template <int SINK, bool BIL, int LAYOUT>
 __global__ void __launch_bounds__(kThreads, EVK_VOXEL_MIN_CTAS) voxel_scatter_kernel(const VoxelArgs A_in)
 {
     if (A_in.skip_if && *A_in.skip_if) return;
+    if (A_in.skip_unless && !*A_in.skip_unless) return;
     VoxelArgs A = A_in;
     if (A.auto_span && A.n > 0) {
         // first / last timestamp straight from the (time-sorted) stream; AoS keeps t at offset 2
@@ -575,6 +577,30 @@ __global__ void __launch_bounds__(256) voxel_fold_blocks_kernel(const float *__r
     }
 }
 
+// Launch-level contention probe (one CTA): 4096 events at a stride through the whole stream; a lane is "contended" when
+// another lane of its warp samples the same pixel.  Uniform streams over >= 1e4 pixels: ~0.1 % of the lanes; one hot pixel
+// with 1 % of the events: ~25 %.  The verdict picks between the plain vector-reduction kernel and the one with the
+// shared-memory hot-pixel table -- as two launches of which one returns at once -- because the table's 40 KB of static
+// shared memory and its registers cost the plain event loop 10 % when both live in one kernel (0.360 vs 0.327 ms).
+template <int LAYOUT>
+__global__ void __launch_bounds__(1024) voxel_hot_probe_kernel(const VoxelArgs A, unsigned *verdict)
+{
+    int dup = 0;
+    for (int64_t k = threadIdx.x; k < 4096; k += 1024) {
+        unsigned long long key = ~0ull - (unsigned long long)(threadIdx.x & 31);
+        const int64_t j = (A.n >= 4096) ? k * (A.n / 4096) : k;
+        if (j < A.n) {
+            const float ex = (LAYOUT == LAYOUT_PACKED) ? (float)A.px16[j] : (LAYOUT == LAYOUT_AOS) ? A.x[4 * j] : A.x[j];
+            const float ey = (LAYOUT == LAYOUT_PACKED) ? (float)A.py16[j] : (LAYOUT == LAYOUT_AOS) ? A.x[4 * j + 1] : A.y[j];
+            int ux, uy;
+            if (trunc_checked(ex, ux) && trunc_checked(ey, uy)) key = ((unsigned long long)(unsigned)uy << 32) | (unsigned)ux;
+        }
+        if (__popc(__match_any_sync(0xffffffffu, key)) > 1) ++dup;
+    }
+    const int dup_all = __syncthreads_count(dup > 0);
+    if (threadIdx.x == 0) *verdict = (dup_all * 64 > 1024) ? 1u : 0u;
+}
+
 static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStream_t st,
                         void *workspace, size_t workspace_bytes)
 {
@@ -642,6 +668,7 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
     }
     const int sink = (variant == EVK_VARIANT_VECTOR_RED) ? SINK_QUAD : SINK_SCALAR;
     A.nq = quads_for_bins(A.B);
+    unsigned *hot_flag = nullptr;      // device word for the launch-level contention verdict (room behind the quad workspace)
     if (sink == SINK_QUAD) {
         const size_t need = (bil ? (size_t)npix * A.B * 4 * sizeof(float) : (size_t)npix * A.nq * 4 * sizeof(float)) * grids;
         if (workspace == nullptr || workspace_bytes < need) {
@@ -651,6 +678,8 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
         if (((uintptr_t)workspace & 15) != 0) { set_error("evk_voxel: workspace must be 16-byte aligned"); return EVK_E_ARG; }
         A.ws = static_cast<float *>(workspace);
         EVK_CUDA(cudaMemsetAsync(A.ws, 0, need, st));
+        const size_t flag_off = (need + 255) & ~(size_t)255;
+        if (workspace_bytes >= flag_off + 256 && !A.skip_if) hot_flag = reinterpret_cast<unsigned *>(static_cast<char *>(workspace) + flag_off);
     } else if (!accum) {
         EVK_CUDA(cudaMemsetAsync(A.out, 0, (size_t)npix * A.B * sizeof(float) * grids, st));
     }
@@ -669,7 +698,22 @@ static int launch_voxel(const VoxelArgs &A0, unsigned flags, int layout, cudaStr
         {
             ProfScope prof(st);
             prof_count(1);
-            if (sink == SINK_QUAD && hot) EVK_DISPATCH_L(SINK_QUAD_HOT, false);
+            if (sink == SINK_QUAD && hot && !A.hot_force && hot_flag != nullptr) {
+                // adaptive, decided once per launch on the device: probe, then both instantiations -- one returns at once
+                prof_count(2);
+                if (layout == LAYOUT_SOA4 || layout == LAYOUT_SOA1) voxel_hot_probe_kernel<LAYOUT_SOA1><<<1, 1024, 0, st>>>(A, hot_flag);
+                else if (layout == LAYOUT_PACKED) voxel_hot_probe_kernel<LAYOUT_PACKED><<<1, 1024, 0, st>>>(A, hot_flag);
+                else voxel_hot_probe_kernel<LAYOUT_AOS><<<1, 1024, 0, st>>>(A, hot_flag);
+                const unsigned *outer_skip = A.skip_if;
+                A.skip_if = hot_flag;                          // plain kernel: unless the probe found contention
+                EVK_DISPATCH_L(SINK_QUAD, false);
+                A.skip_if = outer_skip;
+                A.skip_unless = hot_flag;                      // table kernel: only if it did
+                A.hot_force = 1;
+                EVK_DISPATCH_L(SINK_QUAD_HOT, false);
+                A.skip_unless = nullptr;
+                A.hot_force = 0;
+            } else if (sink == SINK_QUAD && hot) EVK_DISPATCH_L(SINK_QUAD_HOT, false);
             else if (sink == SINK_QUAD) { if (bil) EVK_DISPATCH_L(SINK_QUAD, true); else EVK_DISPATCH_L(SINK_QUAD, false); }
             else { if (bil) EVK_DISPATCH_L(SINK_SCALAR, true); else EVK_DISPATCH_L(SINK_SCALAR, false); }
         }
@@ -718,6 +762,7 @@ size_t evk_voxel_workspace_bytes(int B, int H, int W, unsigned flags)
     if (B < 1 || H < 1 || W < 1) return 0;
     if (flags & EVK_BILINEAR) return (size_t)B * H * W * 4 * sizeof(float);   // 2x2 blocks per bin
     size_t need = (size_t)H * W * evk::quads_for_bins(B) * 4 * sizeof(float);      // temporal quads per pixel
+    need = ((need + 255) & ~(size_t)255) + 256;                                    // + the launch-level contention verdict
     const unsigned v = evk::variant_of(flags);
     if ((v == EVK_VARIANT_AUTO || v == EVK_VARIANT_ROUTED) && evk::voxel_routed_supported(B, H, W)) {
         // the routed kernel's rings, followed (AUTO) by the quad workspace of the kernel the probe may choose instead

@@ -79,10 +79,12 @@ def test_workspace_queries_need_no_gpu():
     from event_utils_b200 import _lib
     L = _lib.load()
     VR = _lib.VARIANT_VECTOR_RED
-    assert L.evk_voxel_workspace_bytes(5, 480, 640, VR) == 480 * 640 * 2 * 16   # two quads per pixel
-    assert L.evk_voxel_workspace_bytes(1, 10, 10, VR) == 10 * 10 * 16
-    assert L.evk_voxel_workspace_bytes(4, 10, 10, VR) == 10 * 10 * 16
-    assert L.evk_voxel_workspace_bytes(8, 10, 10, VR) == 10 * 10 * 3 * 16
+    def quads(nbytes):                     # the quad workspace, 256-byte aligned, + 256 bytes for the launch-level contention verdict
+        return (nbytes + 255) // 256 * 256 + 256
+    assert L.evk_voxel_workspace_bytes(5, 480, 640, VR) == quads(480 * 640 * 2 * 16)   # two quads per pixel
+    assert L.evk_voxel_workspace_bytes(1, 10, 10, VR) == quads(10 * 10 * 16)
+    assert L.evk_voxel_workspace_bytes(4, 10, 10, VR) == quads(10 * 10 * 16)
+    assert L.evk_voxel_workspace_bytes(8, 10, 10, VR) == quads(10 * 10 * 3 * 16)
     # AUTO / ROUTED also cover the routed kernel's rings (one 128 KB ring per SM + its counters)
     assert L.evk_voxel_workspace_bytes(5, 480, 640, 0) >= 480 * 640 * 2 * 16
     assert 148 * 16384 * 8 <= L.evk_voxel_workspace_bytes(5, 480, 640, _lib.VARIANT_ROUTED) <= L.evk_voxel_workspace_bytes(5, 480, 640, 0)
