@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(256) voxel_fold_blocks_kernel(const float *__r
     }
 }
 
-// Launch-level contention probe (one CTA): 4096 events at a stride through the whole stream; a lane is "contended" when
+// Launch-level contention probe (one CTA): 1024 events at a stride through the whole stream; a lane is "contended" when
 // another lane of its warp samples the same pixel.  Uniform streams over >= 1e4 pixels: ~0.1 % of the lanes; one hot pixel
 // with 1 % of the events: ~25 %.  The verdict picks between the plain vector-reduction kernel and the one with the
 // shared-memory hot-pixel table -- as two launches of which one returns at once -- because the table's 40 KB of static
@@ -586,9 +586,10 @@ template <int LAYOUT>
 __global__ void __launch_bounds__(1024) voxel_hot_probe_kernel(const VoxelArgs A, unsigned *verdict)
 {
     int dup = 0;
-    for (int64_t k = threadIdx.x; k < 4096; k += 1024) {
+    {   // one sample per thread (one round of dependent HBM latency: the probe sits in front of the scatter kernel)
+        const int64_t k = threadIdx.x;
         unsigned long long key = ~0ull - (unsigned long long)(threadIdx.x & 31);
-        const int64_t j = (A.n >= 4096) ? k * (A.n / 4096) : k;
+        const int64_t j = (A.n >= 1024) ? k * (A.n / 1024) : k;
         if (j < A.n) {
             const float ex = (LAYOUT == LAYOUT_PACKED) ? (float)A.px16[j] : (LAYOUT == LAYOUT_AOS) ? A.x[4 * j] : A.x[j];
             const float ey = (LAYOUT == LAYOUT_PACKED) ? (float)A.py16[j] : (LAYOUT == LAYOUT_AOS) ? A.x[4 * j + 1] : A.y[j];
