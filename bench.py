@@ -508,8 +508,12 @@ def run_ours(args, rank, local_rank, world):
             sharded = sharded_cmax_metric(device, world, rank)
         except Exception as exc:
             sharded = {"error": repr(exc)}
+        try:
+            zipf = sharded_zipf_image_metric(device, world, rank)
+        except Exception as exc:
+            zipf = {"error": repr(exc)}
         if rank == 0:
-            extra = {"cmax_sharded": sharded, "voxel_single_call_latency": peer}
+            extra = {"cmax_sharded": sharded, "voxel_single_call_latency": peer, "image_zipf_sharded": zipf}
     if world > 1:
         # parity of the product kernels vs the oracle (runs with --no-extra too; an assertion failure fails the bench)
         oracle_check = peer_oracle_check(device, world, rank, x_chk, y_chk, t_chk, p_chk, t0, dt)
@@ -681,6 +685,40 @@ def sharded_cmax_metric(device, world, rank):
         res.update({"ms_per_eval": ms_nccl, "evals_per_s": 1e3 / ms_nccl, "Mevents_per_s": n * world / ms_nccl / 1e3, "f": f_n,
                     "g": [float(g_n[0]), float(g_n[1])], "what": "NCCL formulation (PeerCmax unavailable: %r)" % (exc,)})
     return res
+
+
+def sharded_zipf_image_metric(device, world, rank):
+    """Hot-spot (Zipf s = 1.0) event image over the ranks (BASELINE configs[3] shape at N GPUs): every rank scatters its
+    50 M-event shard through the shared-memory table kernel, one NCCL sum all-reduce joins the 1280x720 images
+    (parallel.events_to_image_sharded).  Device-timed, max over ranks; the total count is checked."""
+    import torch.distributed as dist
+    from event_utils_b200.parallel import events_to_image_sharded
+    n, Hi, Wi = N_PER_GPU, 720, 1280
+    g = torch.Generator(device=device).manual_seed(4000 + rank)
+    npx = Hi * Wi
+    w = 1.0 / torch.arange(1, npx + 1, device=device, dtype=torch.float64)
+    cdf = torch.cumsum(w, 0) / w.sum()
+    ranks = torch.searchsorted(cdf, torch.rand(n, device=device, generator=g, dtype=torch.float64)).clamp_(max=npx - 1)
+    perm = torch.randperm(npx, device=device, generator=torch.Generator(device=device).manual_seed(99))    # the same hot pixels on every rank
+    pix = perm[ranks]
+    x, y, p = (pix % Wi).float(), (pix // Wi).float(), torch.ones(n, device=device)
+    del w, cdf, ranks, perm, pix
+    for _ in range(2):
+        img = events_to_image_sharded(x, y, p, (Hi, Wi))
+    best = 1e9
+    for _ in range(5):
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); img = events_to_image_sharded(x, y, p, (Hi, Wi)); b.record()
+        torch.cuda.synchronize()
+        el = torch.tensor([a.elapsed_time(b)], device=device)
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        best = min(best, float(el))
+    assert abs(float(img.double().sum()) - n * world) < 1.0       # a count image: exact
+    return {"ms": best, "mevents_per_s": n * world / best / 1e3, "events_total": n * world,
+            "what": "Zipf(1.0) stream, %d M events per GPU -> 1280x720 nearest image: shared-memory table scatter per rank + one NCCL "
+                    "all-reduce of the 3.7 MB image" % (n // 1000000)}
 
 
 def secondary_metrics(L, _lib, device, peak):

@@ -91,6 +91,29 @@ def events_to_voxel_sharded(xs, ys, ts, ps, B, sensor_size=(180, 240), group=Non
     return grid
 
 
+def _image_local_cuda(xs, ys, ps, sensor_size, interpolation):
+    from .representations.image import events_to_image_torch
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    if xs.numel() == 0:
+        pad = 1 if interpolation == 'bilinear' else 0
+        return torch.zeros((H + pad, W + pad), dtype=torch.float32, device=xs.device)
+    return events_to_image_torch(xs, ys, ps, sensor_size=(H, W), interpolation=interpolation, clip_out_of_range=interpolation == 'bilinear')
+
+
+def events_to_image_sharded(xs, ys, ps, sensor_size=(180, 240), interpolation=None, group=None, compute=None):
+    """
+    Event image (reference image.py:46-100, events_to_image_torch) of a stream whose events are spread over the ranks of
+    `group`: each rank scatters ITS shard (hot-spot streams through the shared-memory table of csrc/evk_hot.cu), ONE sum
+    all-reduce of the image joins them.  An image is a plain sum over events, so any partition works and there is no
+    global quantity to agree on.  Every rank returns the full image.
+    @param compute local kernel `(xs, ys, ps, sensor_size, interpolation) -> tensor` (tests inject the CPU oracle)
+    """
+    img = (compute or _image_local_cuda)(xs, ys, ps, sensor_size, interpolation)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(img, op=dist.ReduceOp.SUM, group=group)
+    return img
+
+
 class ShardedVoxelStream:
     """Back-to-back sharded voxel builds (a data loader voxelising window after window): the sum
     all-reduce of build k runs on a communication stream and overlaps the scatter kernel of build

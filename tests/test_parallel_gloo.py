@@ -117,6 +117,51 @@ def test_sharded_cmax_world2(tmp_path):
     assert np.abs(g - g_ref).max() <= 1e-4 * scale and np.abs(g2 - g_ref).max() <= 1e-4 * scale
 
 
+def _image_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from event_utils_b200.parallel import events_to_image_sharded, shard_bounds
+    from oracle import evk_oracle as O
+    rng = np.random.default_rng(11)
+    n, H, W = 20001, 24, 40
+    x = (rng.random(n) * (W - 1)).astype(np.float32)
+    y = (rng.random(n) * (H - 1)).astype(np.float32)
+    x[::3], y[::3] = 7.0, 5.0                                   # a hot pixel
+    p = (rng.integers(0, 2, n) * 2 - 1).astype(np.float32)
+    lo, hi = shard_bounds(n, world, rank)
+    errs = []
+    for interp in (None, 'bilinear'):
+        def compute(xs, ys, ps, sensor_size, interpolation):
+            return torch.from_numpy(O.image_torch_f32(xs.numpy(), ys.numpy(), ps.numpy(), sensor_size=sensor_size, interpolation=interpolation,
+                                                      clip_out_of_range=interpolation == 'bilinear'))
+        img = events_to_image_sharded(*(torch.from_numpy(a[lo:hi]) for a in (x, y, p)), (H, W), interp, compute=compute)
+        full = O.image_torch_f32(x, y, p, sensor_size=(H, W), interpolation=interp, clip_out_of_range=interp == 'bilinear')
+        errs.append(np.abs(img.numpy() - full).max() / np.abs(full).max())
+    np.save(os.path.join(out_dir, "img%d.npy" % rank), np.array(errs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_image_world2(tmp_path):
+    """events_to_image_sharded: the sum over shards of the event image == the image of the whole stream (nearest: exact
+    integers; bilinear: 1e-6), with the oracle as local kernel"""
+    world = 2
+    mp.spawn(_image_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        e = np.load(tmp_path / ("img%d.npy" % r))
+        assert e[0] == 0.0 and e[1] <= 1e-6, e
+
+
+def test_numa_binding_is_a_no_op_without_nvml_device():
+    """bind_to_gpu_numa_node never raises and changes nothing where there is no GPU / NVML"""
+    from event_utils_b200.parallel import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    got = bind_to_gpu_numa_node(0)
+    if not torch.cuda.is_available():
+        assert got is None and os.sched_getaffinity(0) == before
+
+
 def test_shard_bounds_cover():
     sys.path.insert(0, ROOT)
     from event_utils_b200.parallel import shard_bounds
