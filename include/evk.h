@@ -57,7 +57,9 @@ extern "C" {
 #define EVK_VARIANT_AUTO (0u << EVK_VARIANT_SHIFT)
 #define EVK_VARIANT_GLOBAL_RED (1u << EVK_VARIANT_SHIFT) /* one scalar red.global.add.f32 per tap */
 #define EVK_VARIANT_VECTOR_RED (2u << EVK_VARIANT_SHIFT) /* one red.global.add.v4.f32 per tap pair, quad-layout workspace */
-#define EVK_VARIANT_SMEM_TILE (3u << EVK_VARIANT_SHIFT)  /* shared-memory tile privatisation + bulk reduce-store */
+#define EVK_VARIANT_SMEM_TILE (3u << EVK_VARIANT_SHIFT)  /* the shared-memory form of the entry point: voxel / image = vector or scalar reductions behind a per-CTA
+                                                          * fixed-point write-combining table (forced on; AUTO probes for contention); cmax = the whole image of
+                                                          * warped events in the CTA's shared memory, flushed by TMA bulk reductions (cmax_onchip_kernel) */
 #define EVK_VARIANT_WARP_AGG (4u << EVK_VARIANT_SHIFT)   /* warp-aggregated (match.any) global reds, for hot-spot streams */
 #define EVK_VARIANT_ROUTED (5u << EVK_VARIANT_SHIFT)     /* voxel: output tiles in shared memory, events routed to the owning SM through L2-resident rings; tiles leave by TMA bulk reduction */
 
