@@ -113,6 +113,8 @@ def _declare(L):
     L.evk_gaussian_blur_f32.argtypes = [vp, ci, ci, f64, vp, vp, vp]
     L.evk_variance_objective_f32.restype = ci
     L.evk_variance_objective_f32.argtypes = [vp, vp, ci, ci, f64, cu, vp, vp, sz, vp]
+    L.evk_peer_barrier.restype = ci
+    L.evk_peer_barrier.argtypes = [vp, ci, ci, cu, vp]
     L.evk_cmax_linvel_partial_f64.restype = ci
     L.evk_cmax_linvel_partial_f64.argtypes = [vp, vp, vp, vp, i64, f64, f64, f64, f64, ci, ci, ci, ci, cu, vp, vp, vp, sz, vp]
     L.evk_cmax_linvel_partial_f32.restype = ci

@@ -99,9 +99,48 @@ ProfScope::~ProfScope()
     if (slot >= 0) cudaEventRecord(g_prof_ev[slot][1], st);
 }
 
+// Cross-GPU barrier on the stream, for the fused peer kernels (one process per GPU).  Every rank owns `world` 32-bit slots in
+// memory that all ranks have mapped (symmetric memory); rank r signals by storing `epoch` into slot [r] of EVERY rank
+// (release, system scope) and waits until all of ITS slots have reached `epoch` (acquire).  Epochs only grow, so one slot
+// array serves any number of barriers.  One CTA, one thread per peer: a launch plus one NVLink round trip.
+constexpr int kMaxBarrierPeers = 16;
+struct PeerFlags {
+    unsigned *slots[kMaxBarrierPeers];
+};
+
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerFlags F, int world, int rank, unsigned epoch)
+{
+    const int t = threadIdx.x;
+    if (t < world) {
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(F.slots[t] + rank), "r"(epoch) : "memory");
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(F.slots[rank] + t) : "memory");
+        } while ((int)(seen - epoch) < 0);
+    }
+}
+
 }  // namespace evk
 
 extern "C" {
+
+int evk_peer_barrier(unsigned *const *peer_slots, int world, int rank, unsigned epoch, void *stream)
+{
+    using namespace evk;
+    if (!peer_slots || world < 1 || world > kMaxBarrierPeers || rank < 0 || rank >= world) {
+        set_error("evk_peer_barrier: bad arguments (world=%d rank=%d, at most %d peers)", world, rank, kMaxBarrierPeers);
+        return EVK_E_ARG;
+    }
+    PeerFlags F{};
+    for (int r = 0; r < world; ++r) {
+        if (!peer_slots[r]) { set_error("evk_peer_barrier: peer %d: null pointer", r); return EVK_E_ARG; }
+        F.slots[r] = peer_slots[r];
+    }
+    prof_count(1);
+    peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(F, world, rank, epoch);
+    EVK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
 
 int evk_prof_enable(int on)
 {

@@ -114,6 +114,36 @@ def events_to_image_sharded(xs, ys, ps, sensor_size=(180, 240), interpolation=No
     return img
 
 
+class _PeerBarrier:
+    """Cross-GPU barrier on a CUDA stream for the fused peer kernels (evk_peer_barrier): `world` 32-bit slots per rank in
+    symmetric memory, one tiny kernel per barrier (a launch + one NVLink round trip).  `EVK_PEER_BARRIER=torch` falls back
+    to the symmetric-memory handle's own barrier."""
+
+    def __init__(self, device, group, handle_for_fallback):
+        import ctypes
+        import os
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self._lib, self.L = _lib, _lib.lib()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.fallback = handle_for_fallback if os.environ.get("EVK_PEER_BARRIER", "evk") == "torch" else None
+        self.epoch = 0
+        if self.fallback is None:
+            self.slots = symm.empty(64, dtype=torch.int32, device=device)
+            self.slots.zero_()
+            h = symm.rendezvous(self.slots, group)
+            self.ptrs = (ctypes.c_void_p * self.world)(*[int(a) for a in h.buffer_ptrs])
+            torch.cuda.synchronize(device)
+            dist.barrier(group)                 # every rank's slots are zero before anybody signals
+
+    def __call__(self, stream_handle, channel=0):
+        if self.fallback is not None:
+            self.fallback.barrier(channel=channel)
+            return
+        self.epoch += 1
+        self._lib.check(self.L.evk_peer_barrier(self.ptrs, self.world, self.rank, self.epoch, stream_handle))
+
+
 class ShardedVoxelStream:
     """Back-to-back sharded voxel builds (a data loader voxelising window after window): the sum
     all-reduce of build k runs on a communication stream and overlaps the scatter kernel of build
@@ -199,20 +229,21 @@ class PeerReducedVoxel:
                 buf["mc_out"] = (ctypes.c_void_p * self.world)(*([int(h_out.multicast_ptr)] * self.world))
             self.bufs.append(buf)
         self.multicast = all(b["mc_ws"] is not None for b in self.bufs)
+        self.barrier = _PeerBarrier(self.device, group, self.bufs[0]["h_ws"])
         self.oob = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.comm = torch.cuda.Stream(self.device) if depth > 1 else None
         self.k = 0
 
     def _reduce(self, buf, stream_handle):
         _lib, L = self._lib, self.L
-        buf["h_ws"].barrier(channel=0)            # every rank's reductions have landed in its workspace
+        self.barrier(stream_handle, 0)            # every rank's reductions have landed in its workspace
         if self.multicast:
             _lib.check(L.evk_voxel_fold_allreduce_f32(buf["mc_ws"], buf["mc_out"], self.world, self.rank, self.B, self.H,
                                                       self.W, _lib.PEER_MULTICAST, stream_handle))
         else:
             _lib.check(L.evk_voxel_fold_allreduce_f32(buf["peer_ws"], buf["peer_out"], self.world, self.rank, self.B, self.H,
                                                       self.W, 0, stream_handle))
-        buf["h_ws"].barrier(channel=1)            # every rank's slice has been written into every grid
+        self.barrier(stream_handle, 1)            # every rank's slice has been written into every grid
 
     def submit(self, xs, ys, ts, ps, t0, dt):
         """This rank's shard (contiguous f32 CUDA tensors) and the stream's global (t0, dt).  Returns the
@@ -337,6 +368,7 @@ class PeerCmax:
             self.bufs.append(dict(buf=buf, h=h,
                                   img=(ctypes.c_void_p * self.world)(*ptrs),
                                   oob=(ctypes.c_void_p * self.world)(*[a + 4 * self.oob_off for a in ptrs])))
+        self.barrier = _PeerBarrier(self.device, group, self.bufs[0]["h"])
         self.ws = torch.empty(self.L.evk_cmax_workspace_bytes(self.Hs, self.Ws), dtype=torch.uint8, device=self.device)
         self.result = torch.zeros(12, dtype=torch.float64).pin_memory()
         self.result_np = self.result.numpy()
@@ -369,7 +401,7 @@ class PeerCmax:
                 _lib.check(L.evk_cmax_linvel_partial_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), n, 1.0, float(params[0]),
                                                          float(params[1]), int(img_size[0]), int(img_size[1]), self.Hs, self.Ws, flags,
                                                          img_ptr, oob_ptr, _lib.ptr(self.ws), self.ws.numel(), st.cuda_stream))
-            b["h"].barrier(channel=0)                  # every rank's partial images are in place
+            self.barrier(st.cuda_stream, 0)            # every rank's partial images are in place
             _lib.check(L.evk_cmax_peer_tail_f32(b["img"], b["oob"], self.world, self.Hs + 1, self.Ws + 1, float(blur_sigma), flags,
                                                 self.result.data_ptr(), _lib.ptr(self.ws), self.ws.numel(), st.cuda_stream))
             st.synchronize()

@@ -306,6 +306,11 @@ int evk_variance_objective_f32(const float *iwe, const float *diwe, int Hc, int 
                                unsigned flags, double *result, void *workspace,
                                size_t workspace_bytes, void *stream);
 
+/* Cross-GPU barrier on a stream, for the fused peer kernels.  peer_slots[r] = rank r's array of `world` 32-bit slots, mapped
+ * on every rank (symmetric memory), zero before the first barrier; `epoch` = 1, 2, 3, ... (the caller counts).  Rank `rank`
+ * stores `epoch` into slot [rank] of every rank and waits until all its own slots have reached it. */
+int evk_peer_barrier(unsigned *const *peer_slots, int world, int rank, unsigned epoch, void *stream);
+
 /* Sharded contrast maximisation, one process per GPU: the all-reduce of the partial images is FUSED into the
  * objective kernel over NVLink peer memory -- no NCCL call, no host synchronisation between the two halves.
  *   evk_cmax_linvel_partial_*  event pass of THIS rank's shard; leaves its planar partial images images_out[3][Hs+1][Ws+1]
