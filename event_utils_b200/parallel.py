@@ -116,8 +116,9 @@ def events_to_image_sharded(xs, ys, ps, sensor_size=(180, 240), interpolation=No
 
 class _PeerBarrier:
     """Cross-GPU barrier on a CUDA stream for the fused peer kernels (evk_peer_barrier): `world` 32-bit slots per rank in
-    symmetric memory, one tiny kernel per barrier (a launch + one NVLink round trip).  `EVK_PEER_BARRIER=torch` falls back
-    to the symmetric-memory handle's own barrier."""
+    symmetric memory, one tiny kernel per barrier (a launch + one NVLink round trip).  Default: the symmetric-memory handle's
+    own barrier; `EVK_PEER_BARRIER=evk` selects evk_peer_barrier -- measured identical at 8 GPUs (voxel single call 0.414 ms,
+    PeerCmax 0.49 ms with either, tools/bench_peer_latency.py), so the barrier is not what the multi-GPU latency is made of."""
 
     def __init__(self, device, group, handle_for_fallback):
         import ctypes
@@ -126,7 +127,7 @@ class _PeerBarrier:
         from . import _lib
         self._lib, self.L = _lib, _lib.lib()
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.fallback = handle_for_fallback if os.environ.get("EVK_PEER_BARRIER", "evk") == "torch" else None
+        self.fallback = handle_for_fallback if os.environ.get("EVK_PEER_BARRIER", "torch") == "torch" else None
         self.epoch = 0
         if self.fallback is None:
             self.slots = symm.empty(64, dtype=torch.int32, device=device)
