@@ -276,7 +276,13 @@ static int launch_hot_mode(const HotArgs &A, cudaStream_t st)
 {
     const size_t smem = (MODE == HOT_BILINEAR) ? (size_t)kHotSlotsB * 5 * sizeof(unsigned) : (size_t)kHotSlots * 2 * sizeof(unsigned);
     EVK_CUDA(cudaFuncSetAttribute(image_hot_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    image_hot_kernel<MODE><<<grid_for(image_hot_kernel<MODE>, kHotThreads, A.n, kHotThreads * 16, smem), kHotThreads, smem, st>>>(A);
+    // ONE wave of resident CTAs: every CTA that uses its table flushes it at the end (up to 8192 reductions, most of them
+    // the single count of a tail cell), so the number of CTAs is what the flush traffic scales with (4 waves: 14.5 M
+    // flush reductions per 50 M-event launch, as many as the misses themselves)
+    int64_t need = (A.n + (int64_t)kHotThreads * 16 - 1) / ((int64_t)kHotThreads * 16);
+    const int64_t cap = (int64_t)num_sms() * resident_ctas_per_sm((const void *)image_hot_kernel<MODE>, kHotThreads, smem);
+    if (need < 1) need = 1;
+    image_hot_kernel<MODE><<<(int)(need < cap ? need : cap), kHotThreads, smem, st>>>(A);
     return EVK_OK;
 }
 
