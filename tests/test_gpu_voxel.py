@@ -195,7 +195,9 @@ for name, (cx, cy, cp) in cases.items():
     ref = O.voxel_f32(cx, cy, t, cp, 5, (H, W))
     out = events_to_voxel_torch(*(torch.from_numpy(a).cuda() for a in (cx, cy, t, cp)), 5, sensor_size=(H, W)).cpu().numpy()
     err = np.abs(out - ref).max() / np.abs(ref).max()
-    assert err <= 1e-5, (name, err)
+    # the hot pixel sums 6e5 signed f32 taps: the sequential f32 oracle itself is ~sqrt(n) eps away from the exact sum
+    # (order-dependent, see test_hot_pixels_*), so that case gets the random-walk allowance instead of 1e-5
+    assert err <= (2e-4 if name == "hot" else 1e-5), (name, err)
     print(name, "ok %%.2e" %% err)
 ''' % root
     out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600, cwd=root,
