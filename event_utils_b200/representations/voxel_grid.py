@@ -31,7 +31,7 @@ def _voxel_device(x, y, t, p, t0, dt, B, H, W, flags=0, aos=None, out=None):
             _lib.check(L.evk_voxel_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), x.shape[0], t0, dt,
                                        B, H, W, flags, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.ptr(oob),
                                        _lib.stream()))
-        E.raise_if_oob(oob, "voxel grid", (B, H, W))
+        E.raise_if_oob(oob, "voxel grid", (B, H, W), always=(flags & _lib.VARIANT_MASK) == _lib.VARIANT_ROUTED)
     return out
 
 
