@@ -133,6 +133,8 @@ def _declare(L):
     L.evk_host_hash64.argtypes = [vp, sz, c.c_uint64]
     L.evk_host_hash64_multi.restype = None
     L.evk_host_hash64_multi.argtypes = [c.POINTER(vp), c.POINTER(sz), ci, c.c_uint64, c.POINTER(c.c_uint64)]
+    L.evk_host_copy.restype = None
+    L.evk_host_copy.argtypes = [c.POINTER(vp), c.POINTER(vp), ci, sz]
     L.evk_pipeline_create.restype = ci
     L.evk_pipeline_create.argtypes = [c.POINTER(vp), i64]
     L.evk_pipeline_destroy.restype = None

@@ -5,13 +5,113 @@
 // scatter itself, so the copy is chunked and double-buffered: while chunk k is scattered on the
 // compute stream, chunk k+1 is in flight on the copy stream.  The accumulation grid stays on the
 // device (L2 resident) for the whole call and is read back once.
+#include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
 #include "evk_common.cuh"
+
+// ---- persistent host worker pool -------------------------------------------------------------------
+// The staging copy of a chunk (64 MB, ~1 ms) and the content hash of an event set are too short to pay for two dozen
+// thread creations each time (~25 us apiece, serial): the workers are created once, sleep on a condition variable and
+// take jobs from one atomic counter (the caller works too).  Never destroyed: the workers are detached and end with
+// the process.  Runs are serialised, so any number of caller threads may use it.
+namespace {
+class HostPool {
+public:
+    static HostPool &get()
+    {
+        static HostPool *pool = new HostPool();      // leaked on purpose (no destruction order problems at exit)
+        return *pool;
+    }
+    int width() const { return nworkers_ + 1; }       // workers + the calling thread
+    // fn(j) for every j in [0, njobs) on at most `width` threads (the caller included); returns when all are done
+    void run(size_t njobs, int width, const std::function<void(size_t)> &fn)
+    {
+        if (njobs == 0) return;
+        int helpers = width - 1;
+        if (helpers > nworkers_) helpers = nworkers_;
+        if ((size_t)helpers > njobs - 1) helpers = (int)(njobs - 1);
+        if (helpers <= 0) { for (size_t j = 0; j < njobs; ++j) fn(j); return; }
+        std::lock_guard<std::mutex> serial(run_mutex_);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn; njobs_ = njobs; next_.store(0, std::memory_order_relaxed);
+            helpers_ = helpers; running_ = helpers;
+            ++generation_;
+        }
+        cv_work_.notify_all();
+        drain(fn, njobs);
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return running_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    HostPool()
+    {
+        // half of the CPUs this process may run on (it may be bound to the GPU's NUMA node), 3..31 workers;
+        // EVK_HOST_THREADS overrides the total (workers + caller)
+        int avail = 0;
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = CPU_COUNT(&set);
+        if (avail <= 0) avail = (int)std::thread::hardware_concurrency();
+        int total = avail / 2;
+        const char *e = getenv("EVK_HOST_THREADS");
+        if (e && *e) total = atoi(e);
+        if (total < 4 && !(e && *e)) total = 4;
+        if (total < 1) total = 1;
+        if (total > 32) total = 32;
+        nworkers_ = total - 1;
+        for (int i = 0; i < nworkers_; ++i) std::thread(&HostPool::worker, this, i).detach();
+        // a forked child (e.g. a DataLoader worker) inherits this object but none of its threads: it works serially
+        self_ = this;
+        pthread_atfork(nullptr, nullptr, [] { if (self_) self_->nworkers_ = 0; });
+    }
+    static HostPool *self_;
+    void drain(const std::function<void(size_t)> &fn, size_t njobs)
+    {
+        for (size_t j = next_.fetch_add(1, std::memory_order_relaxed); j < njobs; j = next_.fetch_add(1, std::memory_order_relaxed)) fn(j);
+    }
+    void worker(int index)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(size_t)> *fn;
+            size_t njobs;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_work_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (index >= helpers_) continue;       // this run is narrower than the pool
+                fn = fn_; njobs = njobs_;
+            }
+            drain(*fn, njobs);
+            std::lock_guard<std::mutex> lk(m_);
+            if (--running_ == 0) cv_done_.notify_one();
+        }
+    }
+    std::mutex run_mutex_, m_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(size_t)> *fn_ = nullptr;
+    size_t njobs_ = 0;
+    std::atomic<size_t> next_{0};
+    uint64_t generation_ = 0;
+    int helpers_ = 0, running_ = 0, nworkers_ = 0;
+};
+HostPool *HostPool::self_ = nullptr;
+}  // namespace
 
 // ---- content hash of a host buffer (identity of a cached event set) ---------------------------------
 // Four independent multiply-rotate lanes over 32-byte stripes (the structure of XXH64), merged and
@@ -64,20 +164,10 @@ static void hash_many(const void *const *ptrs, const size_t *nbytes, int k, cons
             jobs.push_back({n ? p + off : (const unsigned char *)"", len, seeds[a] + j, &piece_hash[a][j]});
         }
     }
-    unsigned hw = std::thread::hardware_concurrency();
-    size_t nthreads = hw ? hw : 4;
-    if (nthreads > 8) nthreads = 8;
-    if (nthreads > jobs.size() / 2) nthreads = jobs.size() / 2 ? jobs.size() / 2 : 1;
-    auto work = [&](size_t first, size_t step) {
-        for (size_t j = first; j < jobs.size(); j += step) *jobs[j].dst = hash_piece(jobs[j].p, jobs[j].len, jobs[j].seed);
-    };
-    if (nthreads <= 1) work(0, 1);
-    else {
-        std::vector<std::thread> th;
-        for (size_t t = 1; t < nthreads; ++t) th.emplace_back(work, t, nthreads);
-        work(0, nthreads);
-        for (auto &t : th) t.join();
-    }
+    // at most 8 threads (the hash runs at memory speed well before that), one job per 1 MiB piece
+    int width = (int)(jobs.size() / 2);
+    if (width > 8) width = 8;
+    HostPool::get().run(jobs.size(), width, [&](size_t j) { *jobs[j].dst = hash_piece(jobs[j].p, jobs[j].len, jobs[j].seed); });
     for (int a = 0; a < k; ++a) {
         const std::vector<uint64_t> &h = piece_hash[a];
         out[a] = (h.size() == 1) ? h[0] : hash_piece((const unsigned char *)h.data(), h.size() * sizeof(uint64_t), seeds[a] ^ (uint64_t)nbytes[a]);
@@ -112,7 +202,7 @@ struct evk_pipeline {
     unsigned long long *oob_pinned;
     // pageable sources: pinned bounce buffers filled by host threads (cudaMemcpyAsync from pageable memory is a
     // single-threaded staged copy inside the driver, far below PCIe speed)
-    float *bounce[2][4];
+    void *bounce[2][4];
     int64_t bounce_events;    // capacity of one bounce slot
 };
 
@@ -125,40 +215,79 @@ bool is_pageable(const void *ptr)
     return at.type == cudaMemoryTypeUnregistered;
 }
 
-// copy k arrays of `bytes` each with a few host threads (a single memcpy stream tops out well below PCIe 5 x16)
-void parallel_copy(void *const *dst, const void *const *src, int k, size_t bytes)
+// One block of the staging copy.  The destination is a pinned bounce buffer that the DMA engine reads next and the CPU
+// never again: non-temporal stores skip the read-for-ownership of the destination lines (2 instead of 3 memory
+// transfers per byte) and leave the caches to the source.  EVK_HOST_COPY_STREAM=0 -> plain memcpy.
+void copy_block(char *dst, const char *src, size_t n, bool stream)
 {
-    // a quarter of the hardware threads, at most 24 (a memcpy thread moves ~5-8 GB/s; PCIe 5 x16 takes ~55 GB/s; the process
-    // may be bound to one NUMA node); EVK_HOST_COPY_THREADS overrides
-    static int nthreads = 0;
-    if (nthreads == 0) {
-        const char *e = getenv("EVK_HOST_COPY_THREADS");
-        unsigned hw = std::thread::hardware_concurrency();
-        int v = (e && *e) ? atoi(e) : (hw ? (int)(hw / 4) : 4);
-        nthreads = v < 1 ? 1 : (v > 24 ? 24 : v);
-    }
-    const size_t total = bytes * k;
-    if (total < ((size_t)4 << 20) || nthreads <= 1) {
-        for (int a = 0; a < k; ++a) memcpy(dst[a], src[a], bytes);
+#if defined(__x86_64__)
+    if (stream && n >= 256) {
+        size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+        memcpy(dst, src, head);
+        dst += head; src += head; n -= head;
+        size_t i = 0;
+        for (; i + 64 <= n; i += 64) {
+            const __m128i a = _mm_loadu_si128((const __m128i *)(src + i)), b = _mm_loadu_si128((const __m128i *)(src + i + 16));
+            const __m128i c = _mm_loadu_si128((const __m128i *)(src + i + 32)), d = _mm_loadu_si128((const __m128i *)(src + i + 48));
+            _mm_stream_si128((__m128i *)(dst + i), a); _mm_stream_si128((__m128i *)(dst + i + 16), b);
+            _mm_stream_si128((__m128i *)(dst + i + 32), c); _mm_stream_si128((__m128i *)(dst + i + 48), d);
+        }
+        memcpy(dst + i, src + i, n - i);
+        _mm_sfence();                      // the stores are globally visible before the block counts as done
         return;
     }
-    constexpr size_t kBlock = (size_t)1 << 20;
-    const size_t blocks_per = (bytes + kBlock - 1) / kBlock, nblocks = blocks_per * k;
-    auto work = [&](size_t first) {
-        for (size_t b = first; b < nblocks; b += (size_t)nthreads) {
-            const int a = (int)(b / blocks_per);
-            const size_t off = (b % blocks_per) * kBlock, len = (bytes - off < kBlock) ? bytes - off : kBlock;
-            memcpy((char *)dst[a] + off, (const char *)src[a] + off, len);
-        }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nthreads; ++t) th.emplace_back(work, (size_t)t);
-    work(0);
-    for (auto &t : th) t.join();
+#endif
+    (void)stream;
+    memcpy(dst, src, n);
 }
+
+// copy k arrays (bytes[a] each) on the worker pool, 1 MiB blocks (a single memcpy stream tops out well below PCIe 5 x16)
+void parallel_copy(void *const *dst, const void *const *src, int k, const size_t *bytes)
+{
+    static const bool stream = [] { const char *e = getenv("EVK_HOST_COPY_STREAM"); return !(e && *e && atoi(e) == 0); }();
+    // 8 threads by default: 62 GB/s of staging copy (2 x Xeon 8562Y+), just ahead of PCIe 5 x16 (55 GB/s).  More threads copy
+    // faster (87 GB/s at 32) but the whole call gets SLOWER (3.0 -> 2.7 Gev/s): the copy bursts take DRAM bandwidth from
+    // the DMA reads of the previous chunk (profiles/bench_pageable_r2.log).  EVK_HOST_COPY_THREADS overrides.
+    static const int width = [] { const char *e = getenv("EVK_HOST_COPY_THREADS"); return (e && *e && atoi(e) > 0) ? atoi(e) : 8; }();
+    if (k <= 0) return;
+    constexpr size_t kBlock = (size_t)1 << 20;
+    std::vector<size_t> first((size_t)k + 1, 0);        // first[a] = index of array a's first block
+    size_t total = 0;
+    for (int a = 0; a < k; ++a) { first[a + 1] = first[a] + (bytes[a] + kBlock - 1) / kBlock; total += bytes[a]; }
+    HostPool::get().run(first[k], total < ((size_t)4 << 20) ? 1 : width, [&](size_t b) {
+        int a = 0;
+        while (first[a + 1] <= b) ++a;
+        const size_t off = (b - first[a]) * kBlock, len = (bytes[a] - off < kBlock) ? bytes[a] - off : kBlock;
+        copy_block((char *)dst[a] + off, (const char *)src[a] + off, len, stream);
+    });
+}
+
+// bytes per event a bounce / staging slot holds: x, y, polarity up to 4, timestamps up to 8 (float64 in the storage layout)
+constexpr size_t kSlotWidth[4] = {4, 4, 8, 4};
 }  // namespace
 
+// the pinned bounce slots of a pipeline (allocated at the first pageable call)
+static int ensure_bounce(evk_pipeline *p)
+{
+    if (p->bounce_events >= p->chunk) return EVK_OK;
+    for (int s = 0; s < 2; ++s)
+        for (int a = 0; a < 4; ++a) {
+            cudaFreeHost(p->bounce[s][a]);
+            p->bounce[s][a] = nullptr;
+            EVK_CUDA(cudaMallocHost(&p->bounce[s][a], (size_t)p->chunk * kSlotWidth[a]));
+        }
+    p->bounce_events = p->chunk;
+    return EVK_OK;
+}
+
 extern "C" {
+
+void evk_host_copy(void *const *dst, const void *const *src, int k, size_t nbytes)
+{
+    if (!dst || !src || k <= 0) return;
+    std::vector<size_t> bytes((size_t)k, nbytes);
+    parallel_copy(dst, src, k, bytes.data());
+}
 
 int evk_pipeline_create(evk_pipeline_t **out, int64_t chunk_events)
 {
@@ -234,15 +363,7 @@ int evk_voxel_host_f32(evk_pipeline_t *p, const float *x, const float *y, const 
     // ordinary (pageable) host arrays -- what the reference's callers hand over -- go through pinned bounce buffers that
     // a few host threads fill while the previous chunk is on the wire
     const bool bounce = n > 0 && (is_pageable(x) || is_pageable(y) || is_pageable(t) || is_pageable(pol));
-    if (bounce && p->bounce_events < p->chunk) {
-        for (int s = 0; s < 2; ++s)
-            for (int a = 0; a < 4; ++a) {
-                cudaFreeHost(p->bounce[s][a]);
-                p->bounce[s][a] = nullptr;
-                EVK_CUDA(cudaMallocHost(&p->bounce[s][a], (size_t)p->chunk * sizeof(float)));
-            }
-        p->bounce_events = p->chunk;
-    }
+    if (bounce) { int rc = ensure_bounce(p); if (rc) return rc; }
     // every chunk accumulates into the same grid; chunk 0 has already been zeroed above
     const unsigned cflags = (flags & ~EVK_VARIANT_MASK) | EVK_ACCUMULATE | EVK_VARIANT_GLOBAL_RED;
     while (done < n) {
@@ -253,8 +374,9 @@ int evk_voxel_host_f32(evk_pipeline_t *p, const float *x, const float *y, const 
             if (k >= 2) EVK_CUDA(cudaEventSynchronize(p->copied[s]));      // the bounce slot's previous H2D has left it
             void *dst4[4] = {p->bounce[s][0], p->bounce[s][1], p->bounce[s][2], p->bounce[s][3]};
             const void *src4[4] = {from[0], from[1], from[2], from[3]};
-            parallel_copy(dst4, src4, 4, (size_t)m * sizeof(float));
-            for (int a = 0; a < 4; ++a) from[a] = p->bounce[s][a];
+            const size_t bytes4[4] = {(size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)m * 4};
+            parallel_copy(dst4, src4, 4, bytes4);
+            for (int a = 0; a < 4; ++a) from[a] = (const float *)p->bounce[s][a];
         }
         if (k >= 2) EVK_CUDA(cudaStreamWaitEvent(p->copy, p->consumed[s], 0));
         for (int a = 0; a < 4; ++a)
@@ -298,14 +420,22 @@ int evk_voxel_host_packed_f32(evk_pipeline_t *p, const int16_t *x, const int16_t
     const unsigned cflags = (flags & ~(EVK_VARIANT_MASK | EVK_AUTO_SPAN)) | EVK_ACCUMULATE | EVK_VARIANT_GLOBAL_RED;
     int64_t done = 0;
     int k = 0;
+    // h5py hands over ordinary pageable arrays: pinned bounce slots filled by the worker pool, as in evk_voxel_host_f32
+    const bool bounce = n > 0 && (is_pageable(x) || is_pageable(y) || is_pageable(t) || is_pageable(pol));
+    if (bounce) { int rc = ensure_bounce(p); if (rc) return rc; }
     while (done < n) {
         const int s = k & 1;
         const int64_t m = (n - done < p->chunk) ? (n - done) : p->chunk;
+        const void *from[4] = {x + done, y + done, t + done, pol + done};
+        const size_t bytes4[4] = {(size_t)m * sizeof(int16_t), (size_t)m * sizeof(int16_t), (size_t)m * sizeof(double), (size_t)m * sizeof(uint8_t)};
+        if (bounce) {
+            if (k >= 2) EVK_CUDA(cudaEventSynchronize(p->copied[s]));      // the bounce slot's previous H2D has left it
+            void *dst4[4] = {p->bounce[s][0], p->bounce[s][1], p->bounce[s][2], p->bounce[s][3]};
+            parallel_copy(dst4, from, 4, bytes4);
+            for (int a = 0; a < 4; ++a) from[a] = p->bounce[s][a];
+        }
         if (k >= 2) EVK_CUDA(cudaStreamWaitEvent(p->copy, p->consumed[s], 0));
-        EVK_CUDA(cudaMemcpyAsync(p->stage[s][0], x + done, (size_t)m * sizeof(int16_t), cudaMemcpyHostToDevice, p->copy));
-        EVK_CUDA(cudaMemcpyAsync(p->stage[s][1], y + done, (size_t)m * sizeof(int16_t), cudaMemcpyHostToDevice, p->copy));
-        EVK_CUDA(cudaMemcpyAsync(p->stage[s][2], t + done, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, p->copy));
-        EVK_CUDA(cudaMemcpyAsync(p->stage[s][3], pol + done, (size_t)m * sizeof(uint8_t), cudaMemcpyHostToDevice, p->copy));
+        for (int a = 0; a < 4; ++a) EVK_CUDA(cudaMemcpyAsync(p->stage[s][a], from[a], bytes4[a], cudaMemcpyHostToDevice, p->copy));
         EVK_CUDA(cudaEventRecord(p->copied[s], p->copy));
         EVK_CUDA(cudaStreamWaitEvent(p->compute, p->copied[s], 0));
         int rc = evk_voxel_packed_f32((const int16_t *)p->stage[s][0], (const int16_t *)p->stage[s][1], (const double *)p->stage[s][2],

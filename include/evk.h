@@ -385,6 +385,13 @@ uint64_t evk_host_hash64(const void *data, size_t nbytes, uint64_t seed);
  * `seed` and a, so equal contents at different positions hash differently. */
 void evk_host_hash64_multi(const void *const *ptrs, const size_t *nbytes, int k, uint64_t seed, uint64_t *out);
 
+/* The staging copy of the host pipeline, for callers that fill their own pinned buffers: k host arrays of `nbytes`
+ * each, dst[a] <- src[a], in 1 MiB blocks on 8 threads (EVK_HOST_COPY_THREADS) of the library's persistent worker
+ * pool (half of the CPUs the process may run on, at most 32; EVK_HOST_THREADS) with non-temporal stores (the destination
+ * is read next by the DMA engine, not by the CPU; EVK_HOST_COPY_STREAM=0 -> memcpy).  evk_voxel_host_f32 uses it for ordinary pageable sources -- what the
+ * reference's loaders produce (lib/data_loaders/base_dataset.py:446-453).  No device work. */
+void evk_host_copy(void *const *dst, const void *const *src, int k, size_t nbytes);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

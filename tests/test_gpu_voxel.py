@@ -271,6 +271,18 @@ def test_host_pipeline_pageable_and_pinned(oracle):
     assert_close_to_max(out2.numpy(), ref, 1e-5, "pinned")
     out3 = events_to_voxel_torch(*pageable, 5, sensor_size=(260, 346))          # bounce buffers reused across calls
     assert_close_to_max(out3.numpy(), ref, 1e-5, "pageable again")
+    # the storage layout (int16, int16, float64, uint8 -- what h5py returns) through the same bounce slots: three chunks
+    from event_utils_b200.representations.voxel_grid import events_to_voxel_packed
+    xi, yi = x.astype(np.int16), y.astype(np.int16)
+    t64 = t.astype(np.float64) * 0.2 + 1.7e9
+    pb = (p > 0).astype(np.uint8)
+    rel = (t64 - t64[0]).astype(np.float32)
+    refp = oracle.voxel_f32(xi, yi, rel, np.where(pb > 0, 1.0, -1.0).astype(np.float32), 5, (260, 346), t0=0.0, dt=rel[-1])
+    packed = [torch.from_numpy(a) for a in (xi, yi, t64, pb)]
+    assert_close_to_max(events_to_voxel_packed(*packed, 5, sensor_size=(260, 346)).numpy(), refp, 1e-5, "packed pageable")
+    assert_close_to_max(events_to_voxel_packed(*(a.pin_memory() for a in packed), 5, sensor_size=(260, 346)).numpy(), refp, 1e-5,
+                        "packed pinned")
+    assert_close_to_max(events_to_voxel_torch(*pageable, 5, sensor_size=(260, 346)).numpy(), ref, 1e-5, "f32 after packed")
 
 
 def test_data_loader_arrays(oracle):
