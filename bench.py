@@ -452,6 +452,20 @@ def run_ours(args, rank, local_rank, world):
         assert abs(float(resq.double().sum()) - expect) <= 1e-6 * n + 4.0
         e2e_pageable = {"value": n / tq / 1e6, "unit": "Mevents/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 4 * B * H * W,
                         "api": "events_to_voxel_torch(ordinary pageable CPU tensors) -> CPU tensor", "steps": 3}
+        # the plain upload behind every numpy-input entry point (evk_host_upload) beside torch's pageable copy
+        from event_utils_b200 import _lib as _evk_lib
+        _evk_lib.upload([qx, qy, qt, qp], device)
+        su = time.perf_counter()
+        up = _evk_lib.upload([qx, qy, qt, qp], device)
+        tu = time.perf_counter() - su
+        del up
+        su = time.perf_counter()
+        up = [a.to(device) for a in (qx, qy, qt, qp)]
+        torch.cuda.synchronize()
+        tt = time.perf_counter() - su
+        del up
+        e2e_pageable["upload_GBps"] = 16 * n / tu / 1e9
+        e2e_pageable["torch_pageable_copy_GBps"] = 16 * n / tt / 1e9
         del qx, qy, qt, qp
     del hx, hy, ht, hp
     e2e_packed = None

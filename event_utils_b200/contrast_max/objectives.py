@@ -96,11 +96,12 @@ def _device_events(xs, ys, ts, ps):
     ev.key, ev.n, ev.mode = key, xs.shape[0], precision
     ev.t_last = float(ts[-1]) if ts.shape[0] else 0.0
     with torch.cuda.device(dev):
+        # numpy arrays are ordinary pageable memory: _lib.upload stages them through pinned bounce buffers (evk_host_upload)
         if precision == "f64":
-            ev.x, ev.y, ev.t, ev.p = (torch.from_numpy(a).to(dev) for a in (xs, ys, ts, ps))
+            ev.x, ev.y, ev.t, ev.p = _lib.upload([torch.from_numpy(a) for a in (xs, ys, ts, ps)], dev)
         else:
-            ev.x, ev.y, ev.p = (torch.from_numpy(a).to(dev).float() for a in (xs, ys, ps))
-            ev.t = torch.from_numpy(ts - ev.t_last).to(dev).float()  # relative in f64, then f32
+            # relative timestamps in f64, then f32
+            ev.x, ev.y, ev.t, ev.p = (a.float() for a in _lib.upload([torch.from_numpy(a) for a in (xs, ys, ts - ev.t_last, ps)], dev))
     _event_cache.insert(0, ev)
     del _event_cache[_CACHE_SLOTS:]
     return ev

@@ -397,6 +397,52 @@ int evk_voxel_host_f32(evk_pipeline_t *p, const float *x, const float *y, const 
     return EVK_OK;
 }
 
+// Plain upload of k host arrays into device buffers the caller allocated (the event set of a contrast-maximisation run,
+// numpy inputs of the image functions).  Pageable sources go through the pipeline's pinned bounce slots, four 16 MB
+// pieces per round filled by the worker pool while the previous round is on the wire (cudaMemcpyAsync from pageable
+// memory is a single-threaded staged copy inside the driver, ~10 GB/s); pinned / registered sources are copied directly.
+// Returns when the data is on the device (the copy stream has been synchronised).
+int evk_host_upload(evk_pipeline_t *p, void *const *dst_dev, const void *const *src_host, int k, const size_t *nbytes)
+{
+    using namespace evk;
+    if (!p || k < 0 || (k > 0 && (!dst_dev || !src_host || !nbytes))) { set_error("evk_host_upload: bad arguments"); return EVK_E_ARG; }
+    for (int a = 0; a < k; ++a)
+        if (nbytes[a] && (!dst_dev[a] || !src_host[a])) { set_error("evk_host_upload: null array %d", a); return EVK_E_ARG; }
+    const size_t piece = (size_t)p->chunk * 4;          // every bounce buffer holds at least this
+    int round = 0;
+    void *bdst[4]; const void *bsrc[4]; void *ddst[4]; size_t bbytes[4];
+    int filled = 0;
+    auto flush_round = [&]() -> int {
+        if (!filled) return EVK_OK;
+        const int s = round & 1;
+        if (round >= 2) EVK_CUDA(cudaEventSynchronize(p->copied[s]));        // the slot's previous H2D has left it
+        for (int i = 0; i < filled; ++i) bdst[i] = p->bounce[s][i];
+        parallel_copy(bdst, bsrc, filled, bbytes);
+        for (int i = 0; i < filled; ++i) EVK_CUDA(cudaMemcpyAsync(ddst[i], bdst[i], bbytes[i], cudaMemcpyHostToDevice, p->copy));
+        EVK_CUDA(cudaEventRecord(p->copied[s], p->copy));
+        ++round;
+        filled = 0;
+        return EVK_OK;
+    };
+    for (int a = 0; a < k; ++a) {
+        if (!nbytes[a]) continue;
+        if (!is_pageable(src_host[a])) {
+            EVK_CUDA(cudaMemcpyAsync(dst_dev[a], src_host[a], nbytes[a], cudaMemcpyHostToDevice, p->copy));
+            continue;
+        }
+        { int rc = ensure_bounce(p); if (rc) return rc; }
+        for (size_t off = 0; off < nbytes[a]; off += piece) {
+            bsrc[filled] = (const char *)src_host[a] + off;
+            ddst[filled] = (char *)dst_dev[a] + off;
+            bbytes[filled] = (nbytes[a] - off < piece) ? nbytes[a] - off : piece;
+            if (++filled == 4) { int rc = flush_round(); if (rc) return rc; }
+        }
+    }
+    { int rc = flush_round(); if (rc) return rc; }
+    EVK_CUDA(cudaStreamSynchronize(p->copy));
+    return EVK_OK;
+}
+
 // Same pipeline for the storage layout (int16 x, int16 y, float64 t, uint8 p): 13 B/event cross PCIe
 // instead of 16, and the casts happen on the device (evk_voxel_packed_f32).
 int evk_voxel_host_packed_f32(evk_pipeline_t *p, const int16_t *x, const int16_t *y, const double *t, const uint8_t *pol,

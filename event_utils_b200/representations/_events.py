@@ -30,14 +30,21 @@ def compute_device(*tensors):
     return d
 
 
+def to_device(t, dev):
+    """A tensor on `dev`: large host tensors through the library's upload path (_lib.upload), the rest through torch."""
+    if t.is_cuda or t.numel() * t.element_size() < _lib.UPLOAD_MIN_BYTES:
+        return t.to(dev, non_blocking=True)
+    return _lib.upload([t.contiguous()], dev)[0]
+
+
 def coords_f32(c, dev):
     """Event coordinates as contiguous f32 on `dev` with the reference's `.long()` semantics kept:
     f32 goes to the kernel untouched (it truncates); other float types are truncated first so
     that rounding to f32 cannot cross an integer; integers are exact in f32 below 2^24."""
     c = as_tensor(c).reshape(-1)
     if c.dtype == torch.float32:
-        return c.to(dev, non_blocking=True).contiguous()
-    c = c.to(dev, non_blocking=True)
+        return to_device(c, dev).contiguous()
+    c = to_device(c, dev)
     if c.dtype.is_floating_point:
         c = c.long()
     if c.dtype in (torch.int64, torch.int32):
@@ -46,7 +53,7 @@ def coords_f32(c, dev):
 
 
 def weights_f32(p, dev):
-    p = as_tensor(p).reshape(-1).to(dev, non_blocking=True)
+    p = to_device(as_tensor(p).reshape(-1), dev)
     return p.to(torch.float32).contiguous()
 
 

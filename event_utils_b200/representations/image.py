@@ -66,8 +66,8 @@ def events_to_image_torch(xs, ys, ps,
         raise RuntimeError("Index put requires the source and destination dtypes match, "
                            "got Float for the destination and Double for the source.")
     if bilinear:
-        x = xs_t.reshape(-1).to(dev).to(torch.float32).contiguous()
-        y = E.as_tensor(ys).reshape(-1).to(dev).to(torch.float32).contiguous()
+        x = E.to_device(xs_t.reshape(-1), dev).to(torch.float32).contiguous()
+        y = E.to_device(E.as_tensor(ys).reshape(-1), dev).to(torch.float32).contiguous()
     else:
         x, y = E.coords_f32(xs, dev), E.coords_f32(ys, dev)
     p = E.weights_f32(ps_t.squeeze() if bilinear else ps_t, dev)
@@ -95,14 +95,14 @@ def events_to_image(xs, ys, ps, sensor_size=(180, 240), interpolation=None, padd
         if not (np.issubdtype(xs.dtype, np.integer) and np.issubdtype(ys.dtype, np.integer)):
             raise TypeError("only int indices permitted")
         with torch.cuda.device(dev):
-            x = torch.from_numpy(np.ascontiguousarray(xs).reshape(-1)).to(dev)
-            y = torch.from_numpy(np.ascontiguousarray(ys).reshape(-1)).to(dev)
+            x = E.to_device(torch.from_numpy(np.ascontiguousarray(xs).reshape(-1)), dev)
+            y = E.to_device(torch.from_numpy(np.ascontiguousarray(ys).reshape(-1)), dev)
             if x.numel() and (int(x.min()) < 0 or int(y.min()) < 0 or int(x.max()) > W or int(y.max()) > H):
                 print("Issue with input arrays! minx={}, maxx={}, miny={}, maxy={}, sensor_size={}".format(
                     int(x.min()), int(x.max()), int(y.min()), int(y.max()), (H + 1, W + 1)))
                 raise ValueError
             xf, yf = x.to(torch.float32), y.to(torch.float32)
-            p = torch.from_numpy(np.ascontiguousarray(ps, dtype=np.float64).reshape(-1)).to(dev).to(torch.float32)
+            p = E.to_device(torch.from_numpy(np.ascontiguousarray(ps, dtype=np.float64).reshape(-1)), dev).to(torch.float32)
             img = _image_device(xf, yf, p, H + 1, W + 1, 0.0, 0.0, 0, 0.0).double().cpu().numpy()
             if meanval:
                 cnt = _image_device(xf, yf, torch.ones_like(xf), H + 1, W + 1, 0.0, 0.0, 0, 0.0).double().cpu().numpy()
@@ -122,9 +122,9 @@ def interpolate_to_image(pxs, pys, dxs, dys, weights, img):
         work = img if img.is_cuda else img.to(dev)
         if not work.is_contiguous() or work.dtype != torch.float32:
             raise RuntimeError("interpolate_to_image: img must be a contiguous float32 tensor")
-        px = E.as_tensor(pxs).reshape(-1).to(dev).long().contiguous()
-        py = E.as_tensor(pys).reshape(-1).to(dev).long().contiguous()
-        dx, dy, w = (E.as_tensor(a).reshape(-1).to(dev).to(torch.float32).contiguous() for a in (dxs, dys, weights))
+        px = E.to_device(E.as_tensor(pxs).reshape(-1), dev).long().contiguous()
+        py = E.to_device(E.as_tensor(pys).reshape(-1), dev).long().contiguous()
+        dx, dy, w = (E.to_device(E.as_tensor(a).reshape(-1), dev).to(torch.float32).contiguous() for a in (dxs, dys, weights))
         oob = _lib.oob_counter(dev)
         _lib.check(L.evk_splat_idx_f32(_lib.ptr(px), _lib.ptr(py), _lib.ptr(dx), _lib.ptr(dy), _lib.ptr(w),
                                        px.shape[0], work.shape[0], work.shape[1], _lib.ptr(work), _lib.ptr(oob),
@@ -146,12 +146,12 @@ def interpolate_to_derivative_img(pxs, pys, dxs, dys, d_img, w1, w2):
         work = d_img if d_img.is_cuda else d_img.to(dev)
         if not work.is_contiguous() or work.dtype != torch.float32:
             raise RuntimeError("interpolate_to_derivative_img: d_img must be a contiguous float32 tensor")
-        px = E.as_tensor(pxs).reshape(-1).to(dev).long().contiguous()
-        py = E.as_tensor(pys).reshape(-1).to(dev).long().contiguous()
-        dx, dy = (E.as_tensor(a).reshape(-1).to(dev).to(torch.float32).contiguous() for a in (dxs, dys))
+        px = E.to_device(E.as_tensor(pxs).reshape(-1), dev).long().contiguous()
+        py = E.to_device(E.as_tensor(pys).reshape(-1), dev).long().contiguous()
+        dx, dy = (E.to_device(E.as_tensor(a).reshape(-1), dev).to(torch.float32).contiguous() for a in (dxs, dys))
         K = work.shape[0]
-        a1 = E.as_tensor(w1).to(dev).to(torch.float32).reshape(K, -1).contiguous()
-        a2 = E.as_tensor(w2).to(dev).to(torch.float32).reshape(K, -1).contiguous()
+        a1 = E.to_device(E.as_tensor(w1), dev).to(torch.float32).reshape(K, -1).contiguous()
+        a2 = E.to_device(E.as_tensor(w2), dev).to(torch.float32).reshape(K, -1).contiguous()
         oob = _lib.oob_counter(dev)
         _lib.check(L.evk_splat_drv_idx_f32(_lib.ptr(px), _lib.ptr(py), _lib.ptr(dx), _lib.ptr(dy), _lib.ptr(a1),
                                            _lib.ptr(a2), K, px.shape[0], work.shape[1], work.shape[2],
@@ -172,8 +172,8 @@ def image_to_event_weights(xs, ys, img):
     img = np.asarray(img)
     dev = E.compute_device()
     with torch.cuda.device(dev):
-        x, y = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
-        im = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float64)).to(dev)
+        x, y = E.to_device(torch.from_numpy(xs), dev), E.to_device(torch.from_numpy(ys), dev)
+        im = E.to_device(torch.from_numpy(np.ascontiguousarray(img, dtype=np.float64)), dev)
         out = torch.empty_like(x)
         oob = _lib.oob_counter(dev)
         _lib.check(L.evk_gather_bilinear_f64(_lib.ptr(x), _lib.ptr(y), x.shape[0], _lib.ptr(im), im.shape[0],
@@ -219,7 +219,7 @@ def events_to_timestamp_image_torch(xs, ys, ts, ps,
         device = xs_t.device
     device = torch.device(device)
     dev = E.compute_device(xs, ys, ts, ps)
-    x, y, t, p = (E.as_tensor(a).squeeze().reshape(-1).to(dev).to(torch.float32).contiguous() for a in (xs, ys, ts, ps))
+    x, y, t, p = (E.to_device(E.as_tensor(a).squeeze().reshape(-1), dev).to(torch.float32).contiguous() for a in (xs, ys, ts, ps))
     fl = torch.stack((t[0], t[-1])).tolist()
     pos, neg = _timestamp_images(x, y, t, p, fl[0], fl[1], sensor_size, clip_out_of_range, interpolation, padding,
                                  timestamp_reverse)
@@ -239,8 +239,8 @@ def events_to_timestamp_image(xn, yn, ts, pn,
     dev = E.compute_device()
     ts = np.asarray(ts, dtype=np.float64).reshape(-1)
     rel = ts - ts[0]
-    x, y, p = (torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).to(dev).float().contiguous() for a in (xn, yn, pn))
-    t = torch.from_numpy(rel).to(dev).float().contiguous()
+    x, y, p = (E.to_device(torch.from_numpy(np.ascontiguousarray(a).reshape(-1)), dev).float().contiguous() for a in (xn, yn, pn))
+    t = E.to_device(torch.from_numpy(rel), dev).float().contiguous()
     # the reference divides by (ts[-1] + 1e-6) of the RELATIVE stamps (image.py:261): first = 0
     pos, neg = _timestamp_images(x, y, t, p, 0.0, float(np.float32(rel[-1])), sensor_size, clip_out_of_range,
                                  interpolation, padding, False, raw=not normalize_timestamps)
@@ -265,13 +265,13 @@ def events_to_image_drv(xn, yn, pn, jacobian_xn, jacobian_yn,
     clipy = img_size[0] if interpolation is None and padding == False else img_size[0] - 1  # noqa: E712
     with torch.cuda.device(dev):
         # image.py:179-183: the f64 -> f32 rounding point
-        x, y, p = (torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).to(dev).float().contiguous()
+        x, y, p = (E.to_device(torch.from_numpy(np.ascontiguousarray(a).reshape(-1)), dev).float().contiguous()
                    for a in (xn, yn, pn))
         img = torch.empty(img_size, dtype=torch.float32, device=dev)
         K, jx, jy, d_img = 0, None, None, None
         if compute_gradient:
-            jx = torch.from_numpy(np.ascontiguousarray(jacobian_xn)).to(dev).float().contiguous()
-            jy = torch.from_numpy(np.ascontiguousarray(jacobian_yn)).to(dev).float().contiguous()
+            jx = E.to_device(torch.from_numpy(np.ascontiguousarray(jacobian_xn)), dev).float().contiguous()
+            jy = E.to_device(torch.from_numpy(np.ascontiguousarray(jacobian_yn)), dev).float().contiguous()
             K = jx.shape[0]
             d_img = torch.empty((K,) + tuple(img_size), dtype=torch.float32, device=dev)
         oob = _lib.oob_counter(dev)

@@ -44,12 +44,12 @@ def _times_f32(ts, dev):
         # numpy float64 stamps, as the data loaders hold them (hdf5_dataset.py:18-23): the reference
         # cannot take numpy at all (quirk B4), so this is our extension -- made relative to the first
         # stamp in float64 BEFORE the cast, because absolute stamps (1.6e9 s + us) do not fit float32
-        t64 = ts.to(dev, non_blocking=True)
+        t64 = E.to_device(ts, dev)
         rel = (t64 - t64[0])
         dt = np.float32(float(rel[-1].item()))
         return rel.to(torch.float32).contiguous(), 0.0, float(dt)
     if ts.dtype == torch.float32:
-        t = ts.to(dev, non_blocking=True).contiguous()
+        t = E.to_device(ts, dev).contiguous()
         first, last = (float(v) for v in torch.stack((ts[0], ts[-1])).tolist())
         t0 = np.float32(first)
         dt = np.float32(last) - np.float32(first)
@@ -58,7 +58,7 @@ def _times_f32(ts, dev):
         # the reference fails here: index_put_ f64 weights into an f32 image (image.py:95)
         raise RuntimeError("Index put requires the source and destination dtypes match, "
                            "got Float for the destination and Double for the source.")
-    ts = ts.to(dev, non_blocking=True)
+    ts = E.to_device(ts, dev)
     if not ts.dtype.is_floating_point:
         rel = (ts - ts[0])
         dt = np.float32(float(rel[-1].item()))
@@ -160,10 +160,10 @@ def events_to_voxel_packed(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240
             raise IndexError("%d events index outside the voxel grid of shape %s" % (bad.value, (B, H, W)))
         return out if device.type == "cpu" else out.to(device)
     with torch.cuda.device(dev):
-        x = xt.to(dev, non_blocking=True).to(torch.int16).contiguous()
-        y = yt.to(dev, non_blocking=True).to(torch.int16).contiguous()
-        t = tt.to(dev, non_blocking=True).to(torch.float64).contiguous()
-        p = pt.to(dev, non_blocking=True).to(torch.uint8).contiguous()
+        x = E.to_device(xt, dev).to(torch.int16).contiguous()
+        y = E.to_device(yt, dev).to(torch.int16).contiguous()
+        t = E.to_device(tt, dev).to(torch.float64).contiguous()
+        p = E.to_device(pt, dev).to(torch.uint8).contiguous()
         out = torch.empty((B, H, W), dtype=torch.float32, device=dev)
         flags = E.variant_flag() | _lib.AUTO_SPAN
         ws = _lib.scratch("voxel_ws", L.evk_voxel_workspace_bytes(B, H, W, flags), dev)

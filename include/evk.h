@@ -391,6 +391,12 @@ void evk_host_hash64_multi(const void *const *ptrs, const size_t *nbytes, int k,
  * is read next by the DMA engine, not by the CPU; EVK_HOST_COPY_STREAM=0 -> memcpy).  evk_voxel_host_f32 uses it for ordinary pageable sources -- what the
  * reference's loaders produce (lib/data_loaders/base_dataset.py:446-453).  No device work. */
 void evk_host_copy(void *const *dst, const void *const *src, int k, size_t nbytes);
+/* Upload k host arrays (nbytes[a] each) into device buffers the caller allocated -- the event set of a
+ * contrast-maximisation run (the reference hands numpy arrays to every objective call, lib/contrast_max/objectives.py:211),
+ * numpy inputs of the image functions.  Pageable sources go through the pipeline's pinned bounce slots, filled by the
+ * worker pool while the previous pieces are on the wire; pinned sources are copied directly.  Synchronous: the data is on
+ * the device when it returns.  A pipeline serves one call at a time. */
+int evk_host_upload(evk_pipeline_t *pipe, void *const *dst_dev, const void *const *src_host, int k, const size_t *nbytes);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
