@@ -444,14 +444,18 @@ def run_ours(args, rank, local_rank, world):
         # arrays at every call (events_cmax.py:341, base_dataset.py:446-453)
         qx, qy, qt, qp = (h.clone() for h in (hx, hy, ht, hp))          # clone() of a pinned tensor is pageable
         assert not qx.is_pinned()
-        events_to_voxel_torch(qx, qy, qt, qp, B, sensor_size=(H, W))
-        sq = time.perf_counter()
-        for _ in range(3):
+        for _ in range(2):          # the first call allocates the pinned bounce slots and starts the worker pool
+            events_to_voxel_torch(qx, qy, qt, qp, B, sensor_size=(H, W))
+        each = []
+        for _ in range(5):
+            sq = time.perf_counter()
             resq = events_to_voxel_torch(qx, qy, qt, qp, B, sensor_size=(H, W))
-        tq = (time.perf_counter() - sq) / 3
+            each.append(time.perf_counter() - sq)
+        tq = sorted(each)[len(each) // 2]
         assert abs(float(resq.double().sum()) - expect) <= 1e-6 * n + 4.0
         e2e_pageable = {"value": n / tq / 1e6, "unit": "Mevents/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 4 * B * H * W,
-                        "api": "events_to_voxel_torch(ordinary pageable CPU tensors) -> CPU tensor", "steps": 3}
+                        "api": "events_to_voxel_torch(ordinary pageable CPU tensors) -> CPU tensor", "steps": 5, "stat": "median",
+                        "ms_each": [round(v * 1e3, 2) for v in each]}
         # the plain upload behind every numpy-input entry point (evk_host_upload) beside torch's pageable copy
         from event_utils_b200 import _lib as _evk_lib
         _evk_lib.upload([qx, qy, qt, qp], device)
