@@ -368,7 +368,9 @@ int evk_voxel_host_f32(evk_pipeline_t *p, const float *x, const float *y, const 
     const unsigned cflags = (flags & ~EVK_VARIANT_MASK) | EVK_ACCUMULATE | EVK_VARIANT_GLOBAL_RED;
     while (done < n) {
         const int s = k & 1;
-        const int64_t m = (n - done < p->chunk) ? (n - done) : p->chunk;
+        // pageable sources: a quarter-size first chunk, so that the wire starts after 0.25 ms of staging copy instead of 1 ms
+        const int64_t cap = (bounce && k == 0) ? ((p->chunk / 4 + 3) & ~(int64_t)3) : p->chunk;
+        const int64_t m = (n - done < cap) ? (n - done) : cap;
         const float *from[4] = {src[0] + done, src[1] + done, src[2] + done, src[3] + done};
         if (bounce) {
             if (k >= 2) EVK_CUDA(cudaEventSynchronize(p->copied[s]));      // the bounce slot's previous H2D has left it
@@ -471,7 +473,8 @@ int evk_voxel_host_packed_f32(evk_pipeline_t *p, const int16_t *x, const int16_t
     if (bounce) { int rc = ensure_bounce(p); if (rc) return rc; }
     while (done < n) {
         const int s = k & 1;
-        const int64_t m = (n - done < p->chunk) ? (n - done) : p->chunk;
+        const int64_t cap = (bounce && k == 0) ? ((p->chunk / 4 + 3) & ~(int64_t)3) : p->chunk;      // as in evk_voxel_host_f32
+        const int64_t m = (n - done < cap) ? (n - done) : cap;
         const void *from[4] = {x + done, y + done, t + done, pol + done};
         const size_t bytes4[4] = {(size_t)m * sizeof(int16_t), (size_t)m * sizeof(int16_t), (size_t)m * sizeof(double), (size_t)m * sizeof(uint8_t)};
         if (bounce) {
