@@ -61,7 +61,7 @@ extern "C" {
                                                           * fixed-point write-combining table (forced on; AUTO probes for contention); cmax = the whole image of
                                                           * warped events in the CTA's shared memory, flushed by TMA bulk reductions (cmax_onchip_kernel) */
 #define EVK_VARIANT_WARP_AGG (4u << EVK_VARIANT_SHIFT)   /* warp-aggregated (match.any) global reds, for hot-spot streams */
-#define EVK_VARIANT_ROUTED (5u << EVK_VARIANT_SHIFT)     /* voxel: output tiles in shared memory, events routed to the owning SM through L2-resident rings; tiles leave by TMA bulk reduction */
+#define EVK_VARIANT_ROUTED (5u << EVK_VARIANT_SHIFT)     /* voxel: output tiles in shared memory, events routed to the owning SM through L2-resident rings; tiles leave by TMA bulk reduction (correct, 2x SLOWER than AUTO: opt-in) */
 /* The routed kernel is a cooperative web of spin waits; a watchdog inside it gives up after 0.5 s without progress
  * (the kernel takes < 1 ms per 50 M events), lets the launch end with an INCOMPLETE grid and adds this mark to the
  * caller's `oob` counter -- the device never hangs.  Counter values >= the mark mean "result invalid", not index errors. */
