@@ -35,7 +35,6 @@ public:
         static HostPool *pool = new HostPool();      // leaked on purpose (no destruction order problems at exit)
         return *pool;
     }
-    int width() const { return nworkers_ + 1; }       // workers + the calling thread
     // fn(j) for every j in [0, njobs) on at most `width` threads (the caller included); returns when all are done
     void run(size_t njobs, int width, const std::function<void(size_t)> &fn)
     {
