@@ -104,3 +104,49 @@ def test_forked_child_works_without_the_pool_threads():
         os.kill(pid, 9)
     os.waitpid(pid, 0)
     assert ready and os.read(r, 1) == b"1"
+
+
+def test_host_pool_is_race_free_under_thread_sanitizer(tmp_path):
+    """The HostPool class text, cut out of csrc/evk_host.cu, compiled with g++ -fsanitize=thread and driven by four
+    concurrent callers with changing widths: every job runs exactly once and ThreadSanitizer reports nothing.
+    Skipped where the toolchain has no TSan runtime."""
+    import os
+    import shutil
+    import subprocess
+    import pytest
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "event_utils_b200", "csrc", "evk_host.cu")).read()
+    a = src.index("namespace {\nclass HostPool {")
+    b = src.index("HostPool *HostPool::self_ = nullptr;")
+    headers = "".join("#include <%s>\n" % h for h in ("pthread.h", "sched.h", "stdlib.h", "string.h", "stdint.h", "stdio.h", "atomic",
+                                                      "condition_variable", "functional", "mutex", "thread", "vector"))
+    harness = r'''
+int main() {
+    std::vector<std::thread> callers;
+    std::atomic<long> total{0};
+    for (int c = 0; c < 4; ++c) callers.emplace_back([&, c] {
+        for (int rep = 0; rep < 300; ++rep) {
+            std::vector<int> hit(257 + rep % 7, 0);
+            const int width = 1 + (rep * 7 + c) % 12;
+            HostPool::get().run(hit.size(), width, [&](size_t j) { hit[j] += 1; });
+            for (size_t j = 0; j < hit.size(); ++j) if (hit[j] != 1) { printf("BAD %zu %d\n", j, hit[j]); exit(1); }
+            total += (long)hit.size();
+        }
+    });
+    for (auto &t : callers) t.join();
+    printf("ok %ld\n", total.load());
+    return 0;
+}
+'''
+    cpp = tmp_path / "pool.cpp"
+    cpp.write_text(headers + src[a:b] + "HostPool *HostPool::self_ = nullptr;\n}  // namespace\n" + harness)
+    exe = tmp_path / "pool_tsan"
+    cc = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", str(cpp), "-o", str(exe), "-lpthread"],
+                        capture_output=True, text=True)
+    if cc.returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime here: " + cc.stderr[-300:])
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300, env=dict(os.environ, EVK_HOST_THREADS="8"))
+    assert run.returncode == 0 and "ok " in run.stdout, run.stdout[-1000:] + run.stderr[-3000:]
+    assert "ThreadSanitizer" not in run.stderr, run.stderr[-3000:]
